@@ -1,0 +1,193 @@
+/*
+ * bdpose.h — C ABI of libbdpose.so: the B200 (sm_100a) bin-and-delta pose hot path.
+ *
+ * The reference (JHUVisionLab/multi-modal-regression) has no FFI of its own: its boundary is a set
+ * of Python call sites.  Each entry point below names the reference call site (file:line under the
+ * reference checkout) whose arithmetic it replaces.  The Python mirror of the reference API
+ * (multi-modal-regression_b200/{axisAngle,quaternion,binDeltaLosses,binDeltaGenerators,
+ * binDeltaModels,poseModels}.py) binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - the caller owns every buffer; no entry point allocates device memory, synchronises the device
+ *     or the stream, or touches a stream other than the one passed in (`stream` is a cudaStream_t
+ *     passed as void*; NULL = legacy default stream);
+ *   - row-major, densely packed unless a leading dimension is passed;
+ *   - return value: BDP_OK (0) or a negative BDP_ERR_* code; bdp_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread;
+ *   - thread-safe for concurrent calls on distinct streams and distinct buffers.
+ */
+#ifndef BDPOSE_H_
+#define BDPOSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDP_OK 0
+#define BDP_ERR_ARG (-1)         /* bad argument (shape, alignment, enum) */
+#define BDP_ERR_CUDA (-2)        /* a CUDA runtime call / launch failed */
+#define BDP_ERR_UNSUPPORTED (-3) /* valid request this build cannot serve */
+
+#define BDP_ABI_VERSION 1
+
+int bdp_abi_version(void);
+const char* bdp_last_error(void);
+/* SM count of the current device (grid sizing on the Python side). */
+int bdp_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (b) fused bin-delta loss:  cross-entropy over the K pose bins  +  argmax key gather  +  pose
+ *     composition  +  pose loss, forward AND the hand-derived backward in one pass over the logits.
+ *
+ * Replaces, per pose_mode:
+ *   BDP_POSE_NONE        nn.CrossEntropyLoss only                    learnGeodesicBDModel.py:69,178
+ *   BDP_POSE_MSE         SimpleLoss / loss_m0  (use_keys=0)           binDeltaLosses.py:16-28, 243-256
+ *                        GeodesicLoss with my_loss=None (use_keys=1)  binDeltaLosses.py:31-50
+ *   BDP_POSE_GEODESIC_AA GeodesicLoss(my_loss=axisAngle.geodesic_loss) binDeltaLosses.py:44-50 +
+ *                        axisAngle.py:110-120; script form learnGeodesicBDModel.py:175-180
+ *   BDP_POSE_GEODESIC_Q  GeodesicLossQ(my_loss=quaternion.geodesic_loss) binDeltaLosses.py:53-72 +
+ *                        quaternion.py:156-163
+ *   BDP_POSE_RIEMANNIAN  RiemannianLoss (Rodrigues delta composed on the key rotation, trace-acos)
+ *                        binDeltaLosses.py:211-239; learnRiemannianBDModel.py:69-95
+ * With logits == NULL the cross-entropy part is skipped and the call is the stand-alone pose loss
+ * (axisAngle.geodesic_loss axisAngle.py:103-120, quaternion.geodesic_loss quaternion.py:149-163,
+ * RiemannianLoss.my_loss binDeltaLosses.py:221-225 via BDP_POSE_ROTMAT).
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  BDP_POSE_NONE = 0,
+  BDP_POSE_MSE = 1,
+  BDP_POSE_GEODESIC_AA = 2,
+  BDP_POSE_GEODESIC_Q = 3,
+  BDP_POSE_RIEMANNIAN = 4,
+  BDP_POSE_ROTMAT = 5 /* pred is a [B,9] rotation matrix: acos(clamp((tr(PᵀT)-1)/2)); no keys */
+};
+
+/* bytes of zero-initialised scratch the loss call needs for B rows (block partials + ticket).
+ * The call leaves the ticket zeroed again, so one allocation can be reused forever. */
+int64_t bdp_bd_loss_workspace_bytes(int64_t B);
+
+/*
+ * logits     [B, ld_logits] fp32, K valid columns (NULL: no cross-entropy)
+ * bin_true   [B] int64 target bin (required iff logits != NULL)
+ * pred       [B, ndim] fp32 predicted delta / pose   (ndim 3 | 4 | 9 by pose_mode)
+ * keys       use_keys: [K, ndim] fp32 key poses (axis-angle / quaternion), or [K, 9] rotation
+ *            matrices for BDP_POSE_RIEMANNIAN; the key is chosen by argmax_k logits (lowest index
+ *            on ties) and carries no gradient to the logits (learnGeodesicBDModel.py:175-176)
+ * target     [B, tdim] fp32 ground truth: ndim columns, 9 for RIEMANNIAN / ROTMAT
+ * out_loss   [2] fp32: {mean CE, mean pose loss}   (always written; unused slot = 0)
+ * row_ce, row_pose  [B] fp32 per-sample values (either may be NULL)
+ * grad_logits [B, ld_logits] fp32 = grad_scale * (softmax - onehot)              (NULL: skip)
+ * grad_pred   [B, ndim] fp32 = grad_scale * d(row pose loss)/d pred              (NULL: skip)
+ * grad_scale  1/B for the mean-reduced losses (the reference default), 1 for reduce=False
+ *             (learnProbabilisticBDModel.py:70); <= 0 selects 1/B
+ * argmax_out  [B] int64 chosen bin (NULL: skip)
+ */
+int bdp_bd_loss_fwd_bwd(const float* logits, int64_t B, int64_t K, int64_t ld_logits,
+                        const int64_t* bin_true, const float* pred, int ndim, const float* keys,
+                        int use_keys, const float* target, int pose_mode, float* out_loss,
+                        float* row_ce, float* row_pose, float* grad_logits, float* grad_pred,
+                        float grad_scale, int64_t* argmax_out, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (d) evaluation: batched geodesic error in degrees + Acc@30deg + (per-class) median.
+ *   axisAngle.get_error / get_error2   axisAngle.py:45-66, 70-95
+ *   quaternion.get_error / get_error2  quaternion.py:33-51, 55-76
+ * ---------------------------------------------------------------------------------------------- */
+enum { BDP_REPR_AXIS_ANGLE = 0, BDP_REPR_QUATERNION = 1 };
+enum { BDP_F32 = 0, BDP_F64 = 1 };
+
+/* y_gt, y_hat [N, 3|4] of `dtype`; err_deg [N] fp64 (degrees, as the reference returns) */
+int bdp_geodesic_error_deg(const void* y_gt, const void* y_hat, int dtype, int repr, int64_t N,
+                           double* err_deg, void* stream);
+
+int64_t bdp_error_stats_workspace_bytes(int64_t N, int num_classes);
+/*
+ * err_deg [N] fp64 (>= 0).  labels [N] int64 class ids in [0,num_classes) or NULL (one class).
+ * Outputs (device): median [num_classes] fp64 with np.median semantics (mean of the two middle
+ * order statistics for even counts, NaN for an empty class — axisAngle.py:92);
+ * count [num_classes] int64; below30 [1] int64 = #(err < 30); max_err [1] fp64.
+ */
+int bdp_error_stats(const double* err_deg, const int64_t* labels, int64_t N, int num_classes,
+                    double* median, int64_t* count, int64_t* below30, double* max_err,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (c) nearest-dictionary-key assignment + residual, and the k-means Lloyd step.
+ *   kmeans.predict + residual        binDeltaGenerators.py:27-30, 78-82 (quaternion keys: 67)
+ *   Riemannian residual + ydata_rot  binDeltaGenerators.py:131-137
+ *   argmax |K·q| assignment          learnObjectnetModel.py:108-109
+ *   KMeans(K).fit                    learnKmeansDictionary.py:41-42  (scikit-learn Lloyd E+M step:
+ *                                    sklearn/cluster/_k_means_lloyd.pyx, _k_means_common.pyx)
+ * ---------------------------------------------------------------------------------------------- */
+
+/*
+ * x        [N, d] rotations, fp32 or fp64 (x_dtype), d = 3 or 4
+ * centers  [K, d] fp64 dictionary (cluster_centers_)
+ * labels32 [N] int32 and/or labels64 [N] int64 nearest key, argmin_k ||x-c_k||^2 evaluated
+ *          faithfully to fp64 (fp32 screening + fp64 re-check of near ties), lowest index on ties
+ * residual [N, d] fp32 = float(x - c[label])                  (NULL: skip)
+ * min_sqdist [N] fp64 = ||x - c[label]||^2                    (NULL: skip)
+ */
+int bdp_assign_nearest(const void* x, int x_dtype, int64_t N, int d, const double* centers, int K,
+                       int32_t* labels32, int64_t* labels64, float* residual, double* min_sqdist,
+                       void* stream);
+
+/* q [N,4] unit quaternions (fp32 or fp64 by q_dtype), keys [K,4] fp64: bin = argmax_k |<key_k, q>|
+ * evaluated in fp64 (lowest index on ties), residual = float(q - keys[bin]).
+ * learnObjectnetModel.py:108-109 (fixed 16-key dictionary 60-66) */
+int bdp_assign_quatdot(const void* q, int q_dtype, int64_t N, const double* keys, int K,
+                       int64_t* bin, float* residual, void* stream);
+
+/* Riemannian residual of RBDGenerator: rot[n] = exp([x_n]x) (axisAngle.get_R), residual[n] =
+ * log(key_rot[bin_n]^T rot[n]) (axisAngle.get_y, zero vector when the axis norm <= 1e-6), all
+ * evaluated in fp64 and stored as fp32 (the reference's `.float()`).
+ * x [N,3] fp32|fp64 (x_dtype), key_rot [K,9] fp64, bin [N] int64 -> rot [N,9] fp32 (NULL: skip),
+ * residual [N,3] fp32 (NULL: skip; otherwise key_rot and bin are required).
+ * binDeltaGenerators.py:120, 131, 137; dataGenerators.py:173-178 */
+int bdp_riemannian_residual(const void* x, int x_dtype, int64_t N, const double* key_rot, int K,
+                            const int64_t* bin, float* rot, float* residual, void* stream);
+
+/* axis-angle [N,3] fp64 -> rotation matrices [N,9] fp64 (axisAngle.get_R, axisAngle.py:33-41) and
+ * unit quaternions [N,4] fp64 (quaternion.convert_dictionary, quaternion.py:79-92). Either output
+ * may be NULL. */
+int bdp_convert_axis_angle(const double* aa, int64_t N, double* rotmat, double* quat, void* stream);
+
+/*
+ * One Lloyd iteration, E-step + M-step accumulation (sklearn lloyd_iter_chunked_dense):
+ *   labels[n] = argmin_k ||x_n - c_k||^2 (fp64-faithful, lowest index on ties); the per-cluster
+ *   coordinate sums are accumulated EXACTLY in two-limb int64 fixed point (order-independent, so
+ *   the result is bit-identical for any grid, any launch and any sharding over GPUs), together
+ *   with member counts, the number of labels that changed, and the inertia of this assignment.
+ *
+ * x        [N, d] fp64 (d = 3 or 4), N < 2^30
+ * centers  [K, d] fp64
+ * labels   [N] int32 in/out (previous labels in, new labels out; -1 initially)
+ * acc      [K, 2*d + 1] int64, ADDED to (zero it before the first shard; all-reduce(SUM) it
+ *          across ranks afterwards): per cluster {hi_0, lo_0, ..., hi_{d-1}, lo_{d-1}, count}
+ *          where sum_x = hi * 2^-fix_hi_bits + lo * 2^-(fix_hi_bits+32)
+ * fix_hi_bits  fixed-point scale: requires |x| < 2^(31 - fix_hi_bits)
+ * stats    [2] int64 ADDED to: {changed labels, 0}; inertia [1] fp64 ADDED to (NULL: skip)
+ * update   0 = E-step only (labels, changed, inertia; acc untouched)
+ */
+int bdp_kmeans_lloyd_step(const double* x, int64_t N, int d, const double* centers, int K,
+                          int32_t* labels, int64_t* acc, int fix_hi_bits, int64_t* stats,
+                          double* inertia, int update, void* stream);
+
+/*
+ * M-step finalisation on the device (no host round trip): centers_new = sum / count from the
+ * fixed-point accumulators (exactly rounded sum, then one division), empty clusters take the
+ * centre of the heaviest cluster (sklearn _average_centers), shift2[0] = sum ||new - old||^2,
+ * n_empty[0] = number of empty clusters (the caller runs relocation when non-zero).
+ */
+int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
+                        const double* centers_old, double* centers_new, double* shift2,
+                        int64_t* n_empty, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDPOSE_H_ */

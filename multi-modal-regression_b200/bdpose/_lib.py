@@ -1,0 +1,78 @@
+"""ctypes binding of libbdpose.so (C ABI declared in include/bdpose.h).
+
+The library is the product; there is no fallback.  Importing this module never touches CUDA, but
+`lib()` raises if the shared object has not been built (run `python -c "import __graft_entry__ as
+g; g.build()"` or `make -C multi-modal-regression_b200/csrc`), and every wrapper raises
+RuntimeError with the library's own message on a non-zero status.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbdpose.so")
+
+BDP_OK = 0
+# pose_mode
+POSE_NONE, POSE_MSE, POSE_GEODESIC_AA, POSE_GEODESIC_Q, POSE_RIEMANNIAN, POSE_ROTMAT = range(6)
+# repr / dtype
+REPR_AXIS_ANGLE, REPR_QUATERNION = 0, 1
+F32, F64 = 0, 1
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+_f32 = C.c_float
+
+# name -> (restype, argtypes): one entry per symbol declared in include/bdpose.h
+SIGNATURES = {
+    "bdp_abi_version": (_int, []),
+    "bdp_last_error": (C.c_char_p, []),
+    "bdp_sm_count": (_int, []),
+    "bdp_bd_loss_workspace_bytes": (_i64, [_i64]),
+    "bdp_bd_loss_fwd_bwd": (_int, [_p, _i64, _i64, _i64, _p, _p, _int, _p, _int, _p, _int, _p, _p,
+                                   _p, _p, _p, _f32, _p, _p, _i64, _p]),
+    "bdp_geodesic_error_deg": (_int, [_p, _p, _int, _int, _i64, _p, _p]),
+    "bdp_error_stats_workspace_bytes": (_i64, [_i64, _int]),
+    "bdp_error_stats": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p, _p, _i64, _p]),
+    "bdp_assign_nearest": (_int, [_p, _int, _i64, _int, _p, _int, _p, _p, _p, _p, _p]),
+    "bdp_assign_quatdot": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p]),
+    "bdp_riemannian_residual": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p, _p]),
+    "bdp_convert_axis_angle": (_int, [_p, _i64, _p, _p, _p]),
+    "bdp_kmeans_lloyd_step": (_int, [_p, _i64, _int, _p, _int, _p, _p, _int, _p, _p, _int, _p]),
+    "bdp_kmeans_finalize": (_int, [_p, _int, _int, _int, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (loaded once).  Raises if it is missing: no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libbdpose.so is not built (%s). Build it with `python -c 'import __graft_entry__ as "
+                "g; g.build()'`; this package has no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != BDP_OK:
+        msg = lib().bdp_last_error()
+        raise RuntimeError("%s failed (%d): %s" % (what, status, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device (or host) address of a tensor's first element, or NULL for None."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,277 @@
+"""Pose-dictionary k-means on B200 (replaces sklearn.cluster.KMeans in learnKmeansDictionary.py:41-42
+and the .predict of the pickled estimator used by binDeltaGenerators.py:27 / binDeltaLosses.py:35).
+
+Semantics follow scikit-learn 1.9.0 Lloyd (`_kmeans_single_lloyd`, `lloyd_iter_chunked_dense`):
+mean-centre X, E-step argmin ||x-c||^2 with lowest-index ties, M-step mean (sum * (1/count)),
+empty clusters relocated to the points farthest from their centre, stop on unchanged labels or
+sum ||dc||^2 <= tol * mean(var(X)), final E-step when not strictly converged, centres un-centred at
+the end.  Everything runs on the device; the only host traffic is one 3-number read per iteration
+for the convergence test.
+
+Multi-GPU: rows are sharded over ranks, centres replicated.  The per-iteration exchange is ONE
+all-reduce(SUM) of the int64 fixed-point accumulators [K, 2d+1] plus the changed-label counter.
+Integer sums are order-independent, so every rank (and every world size) derives bit-identical centres.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def _fix_hi_bits(max_abs):
+    """Largest fixed-point scale with |x| * 2^bits < 2^31."""
+    e = 0 if max_abs <= 0 else int(np.floor(np.log2(max_abs))) + 1   # |x| < 2^e
+    return int(max(0, min(30, 31 - max(e, 0) - 1)))
+
+
+class LloydState:
+    """Device buffers of one fit (allocated once, reused every iteration)."""
+
+    def __init__(self, N, K, d, dev):
+        self.labels = torch.full((N,), -1, dtype=torch.int32, device=dev)
+        # [K*(2d+1)] accumulators followed by {changed, unused}: one all-reduce covers both
+        self.acc_stats = torch.zeros(K * (2 * d + 1) + 2, dtype=torch.int64, device=dev)
+        self.acc = self.acc_stats[: K * (2 * d + 1)]
+        self.stats = self.acc_stats[K * (2 * d + 1):]
+        self.inertia = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.shift2 = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.n_empty = torch.zeros(1, dtype=torch.int64, device=dev)
+
+
+def lloyd_step(x, centers, state, fix_hi_bits, update=True):
+    """One E(+M-accumulate) step on this rank's shard.  Adds into state.acc / stats / inertia."""
+    N, d = x.shape
+    with torch.cuda.device(x.device):
+        st = L.lib().bdp_kmeans_lloyd_step(L.ptr(x), N, d, L.ptr(centers), centers.shape[0],
+                                           L.ptr(state.labels), L.ptr(state.acc), fix_hi_bits,
+                                           L.ptr(state.stats), L.ptr(state.inertia),
+                                           1 if update else 0, L.stream_ptr())
+    L.check(st, "bdp_kmeans_lloyd_step")
+
+
+def finalize(state, centers_old, centers_new, fix_hi_bits):
+    K, d = centers_old.shape
+    with torch.cuda.device(centers_old.device):
+        st = L.lib().bdp_kmeans_finalize(L.ptr(state.acc), K, d, fix_hi_bits, L.ptr(centers_old),
+                                         L.ptr(centers_new), L.ptr(state.shift2),
+                                         L.ptr(state.n_empty), L.stream_ptr())
+    L.check(st, "bdp_kmeans_finalize")
+
+
+def _dist_on(group):
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def _relocate_empty(x, centers_old, state, fix_hi_bits, group):
+    """sklearn _relocate_empty_clusters_dense on the accumulators (rare path).  The n_empty points
+    farthest from their old centre each seed one empty cluster (in decreasing-distance order;
+    sklearn's order inside the top-n set is whatever np.argpartition leaves, identical for
+    n_empty == 1)."""
+    import torch.distributed as dist
+    K, d = centers_old.shape
+    W = 2 * d + 1
+    acc = state.acc.view(K, W)
+    empty = torch.nonzero(acc[:, 2 * d] == 0).reshape(-1)
+    n_empty = int(empty.numel())
+    if n_empty == 0:
+        return
+    lab = state.labels.long()
+    dist2 = ((x - centers_old[lab]) ** 2).sum(1)
+    k = min(n_empty, dist2.numel())
+    top_v, top_i = torch.topk(dist2, k)
+    cand_x = x[top_i]
+    cand_l = lab[top_i]
+    if _dist_on(group):
+        ws = dist.get_world_size(group)
+        pad = n_empty - k
+        pv = torch.cat([top_v, top_v.new_full((pad,), -1.0)])
+        px = torch.cat([cand_x, cand_x.new_zeros((pad, d))])
+        pl = torch.cat([cand_l, cand_l.new_zeros((pad,))])
+        gv = [torch.empty_like(pv) for _ in range(ws)]
+        gx = [torch.empty_like(px) for _ in range(ws)]
+        gl = [torch.empty_like(pl) for _ in range(ws)]
+        dist.all_gather(gv, pv, group=group)
+        dist.all_gather(gx, px, group=group)
+        dist.all_gather(gl, pl, group=group)
+        allv, allx, alll = torch.cat(gv), torch.cat(gx), torch.cat(gl)
+        top_v, sel = torch.topk(allv, n_empty)
+        cand_x, cand_l = allx[sel], alll[sel]
+    if float(top_v.max()) == 0.0:
+        return   # more clusters than distinct samples: sklearn leaves things alone
+    scale_hi = float(2.0 ** fix_hi_bits)
+    for e in range(min(n_empty, cand_x.shape[0])):
+        if float(top_v[e]) < 0:
+            break
+        xs = cand_x[e] * scale_hi
+        hi = torch.floor(xs)
+        lo = torch.trunc((xs - hi) * 4294967296.0)
+        hi, lo = hi.to(torch.int64), lo.to(torch.int64)
+        new_id, old_id = int(empty[e]), int(cand_l[e])
+        acc[old_id, 0:2 * d:2] -= hi
+        acc[old_id, 1:2 * d:2] -= lo
+        acc[old_id, 2 * d] -= 1
+        acc[new_id, 0:2 * d:2] = hi
+        acc[new_id, 1:2 * d:2] = lo
+        acc[new_id, 2 * d] = 1
+
+
+def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, center=True):
+    """Lloyd k-means on this rank's shard `x` [N_local, d] fp64 (CUDA) from explicit centres.
+
+    Returns dict(centers [K,d] fp64, labels [N_local] int32, inertia float, n_iter int).
+    With fixed_iters=n the convergence tests are skipped and exactly n E+M iterations run (the
+    benchmark's fixed-work mode); otherwise sklearn's stopping rules apply.
+    """
+    import torch.distributed as dist
+    ops._need_cuda(x, init)
+    x = x.double().contiguous()
+    dev = x.device
+    N, d = x.shape
+    K = init.shape[0]
+    distributed = _dist_on(group)
+
+    def allreduce(t, op=None):
+        if distributed:
+            dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=group)
+        return t
+
+    # global mean / variance of X (sklearn: X -= X.mean(0); tol = mean(var(X)) * tol)
+    n_tot = allreduce(torch.tensor([float(N)], dtype=torch.float64, device=dev))
+    mean = allreduce(x.sum(0)) / n_tot
+    var = allreduce(((x - mean) ** 2).sum(0)) / n_tot
+    tol_abs = float(var.mean()) * tol
+    if center:
+        x = x - mean
+        centers = (init.double().to(dev) - mean).contiguous()
+    else:
+        centers = init.double().to(dev).contiguous().clone()
+    max_abs = allreduce(x.abs().max().reshape(1), op=dist.ReduceOp.MAX if distributed else None)
+    hb = _fix_hi_bits(float(max_abs))
+
+    state = LloydState(N, K, d, dev)
+    centers_new = torch.empty_like(centers)
+    strict = False
+    n_iter = 0
+    iters = fixed_iters if fixed_iters is not None else max_iter
+    for it in range(iters):
+        state.acc_stats.zero_()
+        lloyd_step(x, centers, state, hb, update=True)
+        allreduce(state.acc_stats)
+        finalize(state, centers, centers_new, hb)
+        if fixed_iters is None:
+            # one small D2H read per iteration: {changed, n_empty} and the centre shift
+            host = torch.cat([state.stats[:1].double(), state.n_empty.double(), state.shift2]).tolist()
+            changed, n_empty, shift2 = int(host[0]), int(host[1]), host[2]
+            if n_empty > 0:
+                _relocate_empty(x, centers, state, hb, group)
+                finalize(state, centers, centers_new, hb)
+                shift2 = float(state.shift2)
+        else:
+            changed, shift2 = 1, float("inf")
+        centers, centers_new = centers_new, centers
+        n_iter = it + 1
+        if changed == 0:
+            strict = True
+            break
+        if shift2 <= tol_abs:
+            break
+    # final E-step (labels consistent with the returned centres) + inertia
+    state.acc_stats.zero_()
+    state.inertia.zero_()
+    if not strict:
+        lloyd_step(x, centers, state, hb, update=False)
+        inertia = allreduce(state.inertia.clone())
+    else:
+        lab = state.labels.long()
+        inertia = allreduce(((x - centers[lab]) ** 2).sum().reshape(1))
+    if center:
+        centers = centers + mean
+    return dict(centers=centers, labels=state.labels, inertia=float(inertia), n_iter=n_iter)
+
+
+def kmeans_plusplus(x, K, seed=0, n_local_trials=None):
+    """k-means++ seeding on the device (sklearn _kmeans_plusplusalgorithm; the random stream is
+    torch's, so seeds are not interchangeable with sklearn's — parity runs pass explicit `init`)."""
+    ops._need_cuda(x)
+    x = x.double()
+    N, d = x.shape
+    g = torch.Generator(device=x.device)
+    g.manual_seed(seed)
+    if n_local_trials is None:
+        n_local_trials = 2 + int(np.log(K))
+    centers = torch.empty((K, d), dtype=torch.float64, device=x.device)
+    first = int(torch.randint(N, (1,), generator=g, device=x.device))
+    centers[0] = x[first]
+    closest = ((x - centers[0]) ** 2).sum(1)
+    pot = closest.sum()
+    for c in range(1, K):
+        r = torch.rand(n_local_trials, generator=g, device=x.device, dtype=torch.float64) * pot
+        cum = torch.cumsum(closest, 0)
+        cand = torch.searchsorted(cum, r).clamp_(max=N - 1)
+        dc = ((x[None, :, :] - x[cand][:, None, :]) ** 2).sum(2)     # [trials, N]
+        dc = torch.minimum(dc, closest[None, :])
+        pots = dc.sum(1)
+        best = int(torch.argmin(pots))
+        centers[c] = x[cand[best]]
+        closest = dc[best]
+        pot = pots[best]
+    return centers
+
+
+class KMeans:
+    """Drop-in for the pickled sklearn estimator the reference passes around
+    (learnKmeansDictionary.py:41-47): exposes n_clusters, cluster_centers_ [K,d] float64 (numpy),
+    labels_, inertia_, n_iter_, fit(X), predict(X).  Pickles hold numpy arrays only."""
+
+    def __init__(self, n_clusters=8, init="k-means++", n_init=1, max_iter=300, tol=1e-4,
+                 verbose=0, random_state=0, n_jobs=None, device=None):
+        self.n_clusters = n_clusters
+        self.init = init
+        self.n_init = n_init
+        self.max_iter = max_iter
+        self.tol = tol
+        self.verbose = verbose
+        self.random_state = random_state
+        self.n_jobs = n_jobs          # accepted and ignored (old sklearn API used by the reference)
+        self.device = device
+
+    def _dev(self):
+        return torch.device(self.device) if self.device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+
+    def fit(self, X, y=None):
+        dev = self._dev()
+        x = torch.as_tensor(np.ascontiguousarray(X), dtype=torch.float64).to(dev)
+        best = None
+        n_init = 1 if not isinstance(self.init, str) else max(1, int(self.n_init))
+        for trial in range(n_init):
+            if isinstance(self.init, str):
+                if self.init != "k-means++":
+                    raise NameError("Unknown init passed")
+                init = kmeans_plusplus(x, self.n_clusters, seed=int(self.random_state or 0) + trial)
+            else:
+                init = torch.as_tensor(np.asarray(self.init), dtype=torch.float64).to(dev)
+            r = kmeans_lloyd(x, init, max_iter=self.max_iter, tol=self.tol)
+            if self.verbose:
+                print("kmeans trial %d: inertia %.6f after %d iterations" % (trial, r["inertia"],
+                                                                             r["n_iter"]))
+            if best is None or r["inertia"] < best["inertia"]:
+                best = r
+        self.cluster_centers_ = best["centers"].cpu().numpy()
+        self.labels_ = best["labels"].cpu().numpy()
+        self.inertia_ = best["inertia"]
+        self.n_iter_ = best["n_iter"]
+        return self
+
+    def predict(self, X):
+        dev = self._dev()
+        X = np.ascontiguousarray(X)
+        x = torch.as_tensor(X).to(dev)
+        lab, _, _ = ops.assign_nearest(x, torch.as_tensor(self.cluster_centers_).to(dev),
+                                       want_residual=False, label_dtype=torch.int32)
+        return lab.cpu().numpy()
+
+    def fit_predict(self, X, y=None):
+        return self.fit(X).labels_

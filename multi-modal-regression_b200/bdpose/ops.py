@@ -1,0 +1,296 @@
+"""Tensor-level wrappers over the C ABI (include/bdpose.h).
+
+Every function takes CUDA tensors, allocates its outputs with torch (the caller of the C ABI owns
+all memory), launches on torch's current stream and never synchronises unless it has to return a
+Python number.  CPU tensors are rejected: there is no CPU path in this package.
+"""
+import torch
+
+from . import _lib as L
+
+_loss_ws = {}     # (device index, stream) -> zero-initialised workspace, reused (kernel re-zeroes it)
+_stats_ws = {}
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("bdpose: expected CUDA tensors (this package has no CPU path); got a "
+                               "%s tensor" % t.device)
+
+
+def _loss_workspace(dev):
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _loss_ws.get(key)
+    if ws is None:
+        n = L.lib().bdp_bd_loss_workspace_bytes(1)
+        ws = torch.zeros(n, dtype=torch.uint8, device=dev)
+        _loss_ws[key] = ws
+    return ws
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return L.F32
+    if t.dtype == torch.float64:
+        return L.F64
+    raise TypeError("bdpose: expected float32 or float64, got %s" % t.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# (b) fused bin-delta loss
+# ------------------------------------------------------------------------------------------------
+def bd_loss_raw(logits, bin_true, pred, target, keys, pose_mode, use_keys, want_grad=True,
+                per_sample=False, want_rows=False):
+    """One launch of bdp_bd_loss_fwd_bwd.
+
+    Returns dict(loss=[2] fp32 {mean CE, mean pose}, grad_logits, grad_pred, argmax, row_ce,
+    row_pose).  Gradients are those of the MEAN losses (scale 1/B) unless per_sample.
+    """
+    _need_cuda(logits, bin_true, pred, target, keys)
+    ref = logits if logits is not None else pred
+    dev = ref.device
+    B = ref.shape[0]
+    K = ld = 0
+    if logits is not None:
+        if logits.dtype != torch.float32:
+            logits = logits.float()
+        if logits.stride(1) != 1 or logits.dim() != 2:
+            logits = logits.contiguous()
+        K, ld = logits.shape[1], logits.stride(0)
+        if ld < K:
+            logits = logits.contiguous()
+            ld = K
+        bin_true = bin_true.reshape(-1).to(torch.int64).contiguous()
+        if bin_true.numel() != B:
+            raise ValueError("bd_loss: bin target has %d entries for %d rows" % (bin_true.numel(), B))
+    ndim = 0
+    if pose_mode != L.POSE_NONE:
+        pred = pred.float().reshape(B, -1).contiguous()
+        target = target.float().reshape(B, -1).contiguous()
+        ndim = pred.shape[1]
+        want_t = 9 if pose_mode in (L.POSE_RIEMANNIAN, L.POSE_ROTMAT) else ndim
+        if target.shape[1] != want_t:
+            raise ValueError("bd_loss: target has %d columns, expected %d" % (target.shape[1], want_t))
+        if keys is not None:
+            keys = keys.float().reshape(keys.shape[0], -1).contiguous()
+            if logits is not None and keys.shape[0] != K:
+                raise ValueError("bd_loss: %d keys for %d bins" % (keys.shape[0], K))
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    g_logits = None
+    if want_grad and logits is not None:
+        g_logits = torch.empty((B, ld), dtype=torch.float32, device=dev)
+    g_pred = torch.empty((B, ndim), dtype=torch.float32, device=dev) \
+        if (want_grad and pose_mode != L.POSE_NONE) else None
+    amax = torch.empty(B, dtype=torch.int64, device=dev) if logits is not None else None
+    row_ce = torch.empty(B, dtype=torch.float32, device=dev) \
+        if (want_rows and logits is not None) else None
+    row_pose = torch.empty(B, dtype=torch.float32, device=dev) \
+        if ((want_rows or per_sample) and pose_mode != L.POSE_NONE) else None
+    ws = _loss_workspace(dev)
+    with torch.cuda.device(dev):
+        st = L.lib().bdp_bd_loss_fwd_bwd(
+            L.ptr(logits), B, K, ld, L.ptr(bin_true), L.ptr(pred), ndim, L.ptr(keys),
+            1 if use_keys else 0, L.ptr(target), pose_mode, L.ptr(out), L.ptr(row_ce),
+            L.ptr(row_pose), L.ptr(g_logits), L.ptr(g_pred), 1.0 if per_sample else 0.0,
+            L.ptr(amax), L.ptr(ws), ws.numel(), L.stream_ptr())
+    L.check(st, "bdp_bd_loss_fwd_bwd")
+    if g_logits is not None and ld != K:
+        g_logits = g_logits[:, :K]
+    return dict(loss=out, grad_logits=g_logits, grad_pred=g_pred, argmax=amax, row_ce=row_ce,
+                row_pose=row_pose)
+
+
+class _BDLoss(torch.autograd.Function):
+    """(Lc, Lr) = fused(logits, pred); the backward only scales the gradients the forward launch
+    already wrote (saved per call, so two forwards before one backward are fine —
+    learnGeodesicBDModel.py:116-120,183)."""
+
+    @staticmethod
+    def forward(ctx, logits, pred, bin_true, target, keys, pose_mode, use_keys):
+        need = [logits is not None and logits.requires_grad, pred is not None and pred.requires_grad]
+        r = bd_loss_raw(logits, bin_true, pred, target, keys, pose_mode, use_keys,
+                        want_grad=any(need))
+        ctx.save_for_backward(r["grad_logits"], r["grad_pred"])
+        ctx.shapes = (None if logits is None else logits.shape, None if pred is None else pred.shape)
+        ctx.mark_non_differentiable(r["argmax"]) if r["argmax"] is not None else None
+        lc, lr = r["loss"][0], r["loss"][1]
+        if r["argmax"] is None:
+            return lc, lr
+        return lc, lr, r["argmax"]
+
+    @staticmethod
+    def backward(ctx, g_lc, g_lr, *unused):
+        g_logits, g_pred = ctx.saved_tensors
+        s_logits, s_pred = ctx.shapes
+        gl = gp = None
+        if g_logits is not None and ctx.needs_input_grad[0]:
+            gl = (g_logits * g_lc).reshape(s_logits)
+        if g_pred is not None and ctx.needs_input_grad[1]:
+            gp = (g_pred * g_lr).reshape(s_pred)
+        return gl, gp, None, None, None, None, None
+
+
+def bd_loss(logits, bin_true, pred, target, keys=None, pose_mode=L.POSE_NONE, use_keys=False):
+    """Fused CE + pose loss with autograd.  Returns (Lc, Lr, argmax_bin) as 0-dim / [B] tensors."""
+    out = _BDLoss.apply(logits, pred, bin_true, target, keys, pose_mode, use_keys)
+    return out
+
+
+class _PoseLossRows(torch.autograd.Function):
+    """reduce=False pose loss: per-sample values, per-sample upstream gradients."""
+
+    @staticmethod
+    def forward(ctx, pred, target, pose_mode):
+        r = bd_loss_raw(None, None, pred, target, None, pose_mode, False,
+                        want_grad=pred.requires_grad, per_sample=True)
+        ctx.save_for_backward(r["grad_pred"])
+        ctx.shape = pred.shape
+        return r["row_pose"]
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        (g_pred,) = ctx.saved_tensors
+        if g_pred is None:
+            return None, None, None
+        return (g_pred * g_rows.reshape(-1, 1)).reshape(ctx.shape), None, None
+
+
+def pose_loss(pred, target, pose_mode, reduce=True):
+    """Stand-alone pose loss (axisAngle.geodesic_loss, quaternion.geodesic_loss, rotmat my_loss)."""
+    if reduce:
+        return _BDLoss.apply(None, pred, None, target, None, pose_mode, False)[1]
+    return _PoseLossRows.apply(pred, target, pose_mode)
+
+
+# ------------------------------------------------------------------------------------------------
+# (d) evaluation
+# ------------------------------------------------------------------------------------------------
+def geodesic_error_deg(y_gt, y_hat, quaternion=False):
+    """[N] fp64 errors in degrees (axisAngle.get_error / quaternion.get_error, per-sample part)."""
+    _need_cuda(y_gt, y_hat)
+    d = 4 if quaternion else 3
+    if y_gt.dtype != y_hat.dtype or y_gt.dtype not in (torch.float32, torch.float64):
+        y_gt, y_hat = y_gt.double(), y_hat.double()
+    y_gt = y_gt.reshape(-1, d).contiguous()
+    y_hat = y_hat.reshape(-1, d).contiguous()
+    if y_gt.shape != y_hat.shape:
+        raise ValueError("geodesic_error: shape mismatch %s vs %s" % (y_gt.shape, y_hat.shape))
+    N = y_gt.shape[0]
+    err = torch.empty(N, dtype=torch.float64, device=y_gt.device)
+    with torch.cuda.device(y_gt.device):
+        st = L.lib().bdp_geodesic_error_deg(
+            L.ptr(y_gt), L.ptr(y_hat), _dtype_code(y_gt),
+            L.REPR_QUATERNION if quaternion else L.REPR_AXIS_ANGLE, N, L.ptr(err), L.stream_ptr())
+    L.check(st, "bdp_geodesic_error_deg")
+    return err
+
+
+def error_stats(err_deg, labels=None, num_classes=1):
+    """(median[C] fp64, count[C] int64, below30[1] int64, max[1] fp64) on the device."""
+    _need_cuda(err_deg, labels)
+    err_deg = err_deg.double().reshape(-1).contiguous()
+    N = err_deg.numel()
+    dev = err_deg.device
+    if labels is not None:
+        labels = labels.reshape(-1).to(torch.int64).contiguous()
+        if labels.numel() != N:
+            raise ValueError("error_stats: %d labels for %d errors" % (labels.numel(), N))
+    C = int(num_classes)
+    med = torch.empty(C, dtype=torch.float64, device=dev)
+    cnt = torch.empty(C, dtype=torch.int64, device=dev)
+    b30 = torch.empty(1, dtype=torch.int64, device=dev)
+    mx = torch.empty(1, dtype=torch.float64, device=dev)
+    n = L.lib().bdp_error_stats_workspace_bytes(N, C)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, n)
+    ws = _stats_ws.get(key)
+    if ws is None:
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        _stats_ws[key] = ws
+    with torch.cuda.device(dev):
+        st = L.lib().bdp_error_stats(L.ptr(err_deg), L.ptr(labels), N, C, L.ptr(med), L.ptr(cnt),
+                                     L.ptr(b30), L.ptr(mx), L.ptr(ws), n, L.stream_ptr())
+    L.check(st, "bdp_error_stats")
+    return med, cnt, b30, mx
+
+
+# ------------------------------------------------------------------------------------------------
+# (c) assignment
+# ------------------------------------------------------------------------------------------------
+def assign_nearest(x, centers, want_residual=True, want_sqdist=False, label_dtype=torch.int64):
+    """kmeans.predict + residual (binDeltaGenerators.py:27-30).  x [N,d] fp32|fp64, centers [K,d].
+
+    Returns (labels [N] label_dtype, residual [N,d] fp32 | None, sqdist [N] fp64 | None)."""
+    _need_cuda(x, centers)
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.double()
+    x = x.reshape(x.shape[0], -1).contiguous()
+    centers = centers.double().contiguous()
+    N, d = x.shape
+    K = centers.shape[0]
+    if centers.shape[1] != d:
+        raise ValueError("assign_nearest: x has %d columns, centers %d" % (d, centers.shape[1]))
+    dev = x.device
+    lab32 = torch.empty(N, dtype=torch.int32, device=dev) if label_dtype == torch.int32 else None
+    lab64 = torch.empty(N, dtype=torch.int64, device=dev) if label_dtype != torch.int32 else None
+    res = torch.empty((N, d), dtype=torch.float32, device=dev) if want_residual else None
+    sq = torch.empty(N, dtype=torch.float64, device=dev) if want_sqdist else None
+    with torch.cuda.device(dev):
+        st = L.lib().bdp_assign_nearest(L.ptr(x), _dtype_code(x), N, d, L.ptr(centers), K,
+                                        L.ptr(lab32), L.ptr(lab64), L.ptr(res), L.ptr(sq),
+                                        L.stream_ptr())
+    L.check(st, "bdp_assign_nearest")
+    return (lab32 if lab32 is not None else lab64), res, sq
+
+
+def assign_quatdot(q, keys):
+    """bin = argmax_k |<key_k, q>|, residual = q - keys[bin] (learnObjectnetModel.py:108-109)."""
+    _need_cuda(q, keys)
+    if q.dtype not in (torch.float32, torch.float64):
+        q = q.double()
+    q = q.reshape(-1, 4).contiguous()
+    keys = keys.double().reshape(-1, 4).contiguous()
+    N = q.shape[0]
+    b = torch.empty(N, dtype=torch.int64, device=q.device)
+    res = torch.empty((N, 4), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        st = L.lib().bdp_assign_quatdot(L.ptr(q), _dtype_code(q), N, L.ptr(keys), keys.shape[0],
+                                        L.ptr(b), L.ptr(res), L.stream_ptr())
+    L.check(st, "bdp_assign_quatdot")
+    return b, res
+
+
+def riemannian_residual(x, key_rot=None, bins=None, want_rot=True):
+    """ydata_rot = get_R(x) and res = get_y(R_key[bin]^T R) (binDeltaGenerators.py:131-137)."""
+    _need_cuda(x, key_rot, bins)
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.double()
+    x = x.reshape(-1, 3).contiguous()
+    N = x.shape[0]
+    dev = x.device
+    rot = torch.empty((N, 3, 3), dtype=torch.float32, device=dev) if want_rot else None
+    res = None
+    K = 0
+    if key_rot is not None:
+        key_rot = key_rot.double().reshape(-1, 9).contiguous()
+        K = key_rot.shape[0]
+        bins = bins.reshape(-1).to(torch.int64).contiguous()
+        res = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = L.lib().bdp_riemannian_residual(L.ptr(x), _dtype_code(x), N, L.ptr(key_rot), K,
+                                             L.ptr(bins), L.ptr(rot), L.ptr(res), L.stream_ptr())
+    L.check(st, "bdp_riemannian_residual")
+    return rot, res
+
+
+def convert_axis_angle(aa, want_rot=True, want_quat=True):
+    """axis-angle [N,3] -> (rotation matrices [N,3,3] fp64, unit quaternions [N,4] fp64)."""
+    _need_cuda(aa)
+    aa = aa.double().reshape(-1, 3).contiguous()
+    N = aa.shape[0]
+    rot = torch.empty((N, 3, 3), dtype=torch.float64, device=aa.device) if want_rot else None
+    quat = torch.empty((N, 4), dtype=torch.float64, device=aa.device) if want_quat else None
+    with torch.cuda.device(aa.device):
+        st = L.lib().bdp_convert_axis_angle(L.ptr(aa), N, L.ptr(rot), L.ptr(quat), L.stream_ptr())
+    L.check(st, "bdp_convert_axis_angle")
+    return rot, quat

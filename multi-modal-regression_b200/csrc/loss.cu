@@ -1,0 +1,502 @@
+// (b) Fused bin-delta loss for sm_100a: softmax cross-entropy over the K pose bins, argmax key
+// gather, pose composition (additive or Rodrigues-on-key) and the geodesic / MSE pose loss, with
+// the closed-form backward written in the same pass.
+//
+// Layout: one warp walks R consecutive rows.  For each row the 32 lanes cooperate on the logits
+// (128-bit streaming loads held in registers, shuffle max/argmax/sum, gradient written straight
+// back with 128-bit streaming stores: the logits are read once and the gradient written once);
+// lane r then keeps (ce, argmax) of row r, and after the R rows all lanes do their row's pose
+// math in parallel (so the transcendental tail costs one instruction stream per 32 rows instead
+// of one per row).  R adapts to B so that small training batches still spread over the chip.
+//
+// Algorithmic traffic per row (K=200, fp32): 2*K*4 (logits in, grad out) + 8 (bin) + 12 (delta)
+// + 12..36 (target) + 12 (grad delta) = 1644..1668 B  — the kernel is HBM-bound.
+#include "common.cuh"
+
+namespace {
+
+struct LossParams {
+  const float* logits;
+  int64_t B, K, ld;
+  const int64_t* bin_true;
+  const float* pred;
+  int ndim;
+  const float* keys;
+  int use_keys;
+  const float* target;
+  int tdim;
+  int pose_mode;
+  float* out_loss;
+  float* row_ce;
+  float* row_pose;
+  float* grad_logits;
+  float* grad_pred;
+  int64_t* argmax_out;
+  double* partials;       // [gridDim.x * 2]
+  unsigned int* ticket;   // [1], zero on entry, zero on exit
+  int rows_per_warp;      // R in [1,32]
+  float inv_B;              // gradient scale: 1/B (mean) or 1 (per-sample)
+};
+
+// ---- pose losses: value + gradient w.r.t. the composed prediction ---------------------------
+// All follow the reference's fp32 formulas; eps / clamp conventions cited inline.
+
+// axisAngle.geodesic_loss.forward, axisAngle.py:110-120.  p = predicted axis-angle (key + delta),
+// t = ground truth.  Returns theta; g = d theta / d p.
+__device__ __forceinline__ float pose_geodesic_aa(const float p[3], const float t[3], float g[3]) {
+  const float ap = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  const float at = sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  const float ipn = 1.f / fmaxf(ap, BDP_NORM_EPS);   // F.normalize: v / max(||v||, 1e-12)
+  const float itn = 1.f / fmaxf(at, BDP_NORM_EPS);
+  const float ph[3] = {p[0] * ipn, p[1] * ipn, p[2] * ipn};
+  const float th[3] = {t[0] * itn, t[1] * itn, t[2] * itn};
+  const float d = th[0] * ph[0] + th[1] * ph[1] + th[2] * ph[2];
+  float sp, cp, st, ct;
+  sincosf(0.5f * ap, &sp, &cp);
+  sincosf(0.5f * at, &st, &ct);
+  const float w = ct * cp + st * sp * d;
+  const float c = fabsf(w);
+  const float cc = fminf(c, 1.f - BDP_EPS);            // clamp(|w|, -1+eps, 1-eps); |w| >= 0
+  const float theta = 2.f * acosf(cc);
+  // backward: zero where the clamp saturates (torch.clamp passes the
+  // gradient on the closed interval), sign(0) = 0 from torch.abs.
+  float dth_dw = 0.f;
+  if (c <= 1.f - BDP_EPS && w != 0.f) dth_dw = (w > 0.f ? -2.f : 2.f) * rsqrtf(1.f - c * c);
+  const float dw_dap = 0.5f * (st * cp * d - ct * sp);
+  const float k = st * sp;                              // dw/d p_hat = k * t_hat
+  if (ap > BDP_NORM_EPS) {
+    // d ap/dp = p_hat ; d p_hat/dp = (I - p_hat p_hat^T)/ap
+    const float proj = k * d;                           // p_hat . (k t_hat)
+    const float ia = 1.f / ap;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      g[i] = dth_dw * (dw_dap * ph[i] + (k * th[i] - proj * ph[i]) * ia);
+  } else {
+    // ||p|| <= 1e-12: normalize is p/eps (linear), torch.norm's subgradient at 0 is 0
+    const float s = (ap > 0.f) ? dw_dap / ap : 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) g[i] = dth_dw * (s * p[i] + k * th[i] * (1.f / BDP_NORM_EPS));
+  }
+  return theta;
+}
+
+// quaternion.geodesic_loss.forward, quaternion.py:156-163.
+__device__ __forceinline__ float pose_geodesic_quat(const float q[4], const float t[4],
+                                                    float g[4]) {
+  const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const float in = 1.f / fmaxf(n, BDP_NORM_EPS);
+  const float qh[4] = {q[0] * in, q[1] * in, q[2] * in, q[3] * in};
+  const float w = t[0] * qh[0] + t[1] * qh[1] + t[2] * qh[2] + t[3] * qh[3];
+  const float c = fabsf(w);
+  const float theta = 2.f * acosf(fminf(c, 1.f - BDP_EPS));
+  float dth_dw = 0.f;
+  if (c <= 1.f - BDP_EPS && w != 0.f) dth_dw = (w > 0.f ? -2.f : 2.f) * rsqrtf(1.f - c * c);
+  if (n > BDP_NORM_EPS) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = dth_dw * (t[i] - qh[i] * w) * in;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = dth_dw * t[i] * (1.f / BDP_NORM_EPS);
+  }
+  return theta;
+}
+
+// RiemannianLoss, binDeltaLosses.py:221-239: R_hat = Key * exp([r]x), phi = acos(clamp((tr(R_hat^T
+// R) - 1)/2)).  With M = Key^T R:  tr = sum_ij E_ij M_ij,  E = I + sin(th)[a]x + (1-cos th)[a]x^2.
+__device__ __forceinline__ float pose_riemannian(const float r[3], const float* __restrict__ key,
+                                                 const float R[9], float g[3]) {
+  float M[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      M[i * 3 + j] = key[0 * 3 + i] * R[0 * 3 + j] + key[1 * 3 + i] * R[1 * 3 + j] +
+                     key[2 * 3 + i] * R[2 * 3 + j];
+  const float th = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  const float in = 1.f / fmaxf(th, BDP_NORM_EPS);
+  const float a[3] = {r[0] * in, r[1] * in, r[2] * in};
+  float s, c;
+  sincosf(th, &s, &c);
+  const float omc = 1.f - c;
+  // skew from the reference's `proj` rows (binDeltaLosses.py:217): [[0,-a3,a2],[a3,0,-a1],[-a2,a1,0]]
+  const float A[9] = {0.f, -a[2], a[1], a[2], 0.f, -a[0], -a[1], a[0], 0.f};
+  float tr = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float AA = A[i * 3 + 0] * A[0 * 3 + j] + A[i * 3 + 1] * A[1 * 3 + j] +
+                       A[i * 3 + 2] * A[2 * 3 + j];
+      const float E = (i == j ? 1.f : 0.f) + s * A[i * 3 + j] + omc * AA;
+      tr += E * M[i * 3 + j];
+    }
+  const float u = 0.5f * (tr - 1.f);
+  const float uc = fminf(fmaxf(u, -1.f + BDP_EPS), 1.f - BDP_EPS);
+  const float phi = acosf(uc);
+  float dphi_dt = 0.f;
+  if (u >= -1.f + BDP_EPS && u <= 1.f - BDP_EPS) dphi_dt = -0.5f * rsqrtf(1.f - u * u);
+  if (th > BDP_NORM_EPS) {
+    const float trM = M[0] + M[4] + M[8];
+    const float m[3] = {M[7] - M[5], M[2] - M[6], M[3] - M[1]};
+    const float am = a[0] * m[0] + a[1] * m[1] + a[2] * m[2];
+    float Sa[3];  // (M + M^T) a
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      Sa[i] = (M[i * 3 + 0] + M[0 * 3 + i]) * a[0] + (M[i * 3 + 1] + M[1 * 3 + i]) * a[1] +
+              (M[i * 3 + 2] + M[2 * 3 + i]) * a[2];
+    const float aMa = 0.5f * (a[0] * Sa[0] + a[1] * Sa[1] + a[2] * Sa[2]);
+    const float dt_dth = c * am + s * (aMa - trM);
+    float v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = s * m[i] + omc * Sa[i];
+    const float av = a[0] * v[0] + a[1] * v[1] + a[2] * v[2];
+    const float ith = 1.f / th;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) g[i] = dphi_dt * (dt_dth * a[i] + (v[i] - av * a[i]) * ith);
+  } else {
+    g[0] = g[1] = g[2] = 0.f;
+  }
+  return phi;
+}
+
+// RiemannianLoss.my_loss on explicit matrices (binDeltaLosses.py:221-225): P predicted, T truth.
+__device__ __forceinline__ float pose_rotmat(const float P[9], const float T[9], float g[9]) {
+  float tr = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) tr += P[i] * T[i];
+  const float u = 0.5f * (tr - 1.f);
+  const float uc = fminf(fmaxf(u, -1.f + BDP_EPS), 1.f - BDP_EPS);
+  float dphi_dt = 0.f;
+  if (u >= -1.f + BDP_EPS && u <= 1.f - BDP_EPS) dphi_dt = -0.5f * rsqrtf(1.f - u * u);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) g[i] = dphi_dt * T[i];
+  return acosf(uc);
+}
+
+// Per-row pose phase. Returns the row's pose-loss value, writes the row's gradient.
+__device__ __forceinline__ float pose_row(const LossParams& P, int64_t row, int ind) {
+  const int nd = P.ndim;
+  float p[9], t[9], g[9];
+  const float* pr = P.pred + row * nd;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) p[i] = (i < nd) ? __ldg(pr + i) : 0.f;
+  const float* tg = P.target + row * P.tdim;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) t[i] = (i < P.tdim) ? __ldg(tg + i) : 0.f;
+  float val = 0.f;
+  if (P.pose_mode == BDP_POSE_RIEMANNIAN) {
+    val = pose_riemannian(p, P.keys + (int64_t)ind * 9, t, g);
+  } else {
+    if (P.use_keys) {
+      const float* key = P.keys + (int64_t)ind * nd;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < nd) p[i] += __ldg(key + i);
+    }
+    if (P.pose_mode == BDP_POSE_GEODESIC_AA) {
+      val = pose_geodesic_aa(p, t, g);
+    } else if (P.pose_mode == BDP_POSE_GEODESIC_Q) {
+      val = pose_geodesic_quat(p, t, g);
+    } else if (P.pose_mode == BDP_POSE_ROTMAT) {
+      val = pose_rotmat(p, t, g);
+    } else {  // BDP_POSE_MSE: nn.MSELoss mean over B*ndim elements
+      const float ind_nd = 1.f / (float)nd;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const float e = (i < nd) ? p[i] - t[i] : 0.f;
+        val += e * e;
+        g[i] = 2.f * e * ind_nd;
+      }
+      val *= ind_nd;
+    }
+  }
+  if (P.grad_pred) {
+    float* gp = P.grad_pred + row * nd;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (i < nd) gp[i] = g[i] * P.inv_B;
+  }
+  if (P.row_pose) P.row_pose[row] = val;
+  return val;
+}
+
+// ---- logits phase, vector path: K % 4 == 0, rows 16-byte aligned, K <= KV*128 -----------------
+template <int KV>
+__device__ __forceinline__ void row_load(const LossParams& P, int64_t row, int lane, int nvec,
+                                         float4 v[KV]) {
+  const float4* src = reinterpret_cast<const float4*>(P.logits + row * P.ld);
+#pragma unroll
+  for (int j = 0; j < KV; ++j) {
+    const int i = lane + j * 32;
+    v[j] = (i < nvec) ? ldg_stream(src + i)
+                      : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  }
+}
+
+template <int KV>
+__device__ __forceinline__ void row_softmax_ce(const LossParams& P, int64_t row, int lane,
+                                               int nvec, float4 v[KV], float& ce, int& amax) {
+  // max + argmax (lowest index wins)
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < KV; ++j) {
+    const int base = (lane + j * 32) * 4;
+    const float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (e[q] > m) { m = e[q]; mi = base + q; }   // ascending index order inside a lane
+  }
+  warp_argmax(m, mi);
+  const int tgt = (int)__ldg(P.bin_true + row);
+  float s = 0.f, xt = 0.f;
+#pragma unroll
+  for (int j = 0; j < KV; ++j) {
+    const int base = (lane + j * 32) * 4;
+    float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (base + q == tgt) xt = e[q];
+      e[q] = expf(e[q] - m);                      // exp(-inf) = 0 for the padding lanes
+      s += e[q];
+    }
+    v[j] = make_float4(e[0], e[1], e[2], e[3]);
+  }
+  s = warp_sum(s);
+  xt = warp_sum(xt);
+  ce = (m - xt) + logf(s);
+  amax = mi;
+  if (P.grad_logits) {
+    const float sc = P.inv_B / s;
+    float4* dst = reinterpret_cast<float4*>(P.grad_logits + row * P.ld);
+#pragma unroll
+    for (int j = 0; j < KV; ++j) {
+      const int i = lane + j * 32;
+      if (i < nvec) {
+        const int base = i * 4;
+        float4 o = make_float4(v[j].x * sc, v[j].y * sc, v[j].z * sc, v[j].w * sc);
+        if (tgt >= base && tgt < base + 4) {
+          const int q = tgt - base;
+          if (q == 0) o.x -= P.inv_B; else if (q == 1) o.y -= P.inv_B;
+          else if (q == 2) o.z -= P.inv_B; else o.w -= P.inv_B;
+        }
+        stg_stream(dst + i, o);
+      }
+    }
+  }
+}
+
+// scalar path: any K / alignment; three passes over the row (the 2nd and 3rd hit L1/L2).
+__device__ __forceinline__ void row_softmax_ce_scalar(const LossParams& P, int64_t row, int lane,
+                                                      float& ce, int& amax) {
+  const float* x = P.logits + row * P.ld;
+  const int K = (int)P.K;
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int i = lane; i < K; i += 32) {
+    const float e = x[i];
+    if (e > m) { m = e; mi = i; }
+  }
+  warp_argmax(m, mi);
+  const int tgt = (int)__ldg(P.bin_true + row);
+  float s = 0.f;
+  for (int i = lane; i < K; i += 32) s += expf(x[i] - m);
+  s = warp_sum(s);
+  const float xt = x[tgt];
+  ce = (m - xt) + logf(s);
+  amax = mi;
+  if (P.grad_logits) {
+    const float sc = P.inv_B / s;
+    float* dst = P.grad_logits + row * P.ld;
+    for (int i = lane; i < K; i += 32)
+      dst[i] = expf(x[i] - m) * sc - (i == tgt ? P.inv_B : 0.f);
+  }
+}
+
+template <int KV>   // KV == 0: scalar path
+__global__ void __launch_bounds__(256) bd_loss_kernel(const LossParams P) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int R = P.rows_per_warp;
+  const int64_t n_groups = (P.B + R - 1) / R;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nvec = (int)(P.K >> 2);
+  const bool has_ce = P.logits != nullptr;
+  const bool has_pose = P.pose_mode != BDP_POSE_NONE;
+
+  double acc_ce = 0.0, acc_pose = 0.0;
+
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; g < n_groups;
+       g += warps_total) {
+    const int64_t row0 = g * R;
+    const int nrows = (int)min((int64_t)R, P.B - row0);
+    float my_ce = 0.f;
+    int my_ind = 0;
+    if (has_ce) {
+      if (KV > 0) {
+        // two rows in flight per warp: both rows' loads are issued before either is reduced
+        int r = 0;
+        for (; r + 1 < nrows; r += 2) {
+          float4 va[KV > 0 ? KV : 1], vb[KV > 0 ? KV : 1];
+          row_load<(KV > 0 ? KV : 1)>(P, row0 + r, lane, nvec, va);
+          row_load<(KV > 0 ? KV : 1)>(P, row0 + r + 1, lane, nvec, vb);
+          float ce_a, ce_b;
+          int ia, ib;
+          row_softmax_ce<(KV > 0 ? KV : 1)>(P, row0 + r, lane, nvec, va, ce_a, ia);
+          row_softmax_ce<(KV > 0 ? KV : 1)>(P, row0 + r + 1, lane, nvec, vb, ce_b, ib);
+          if (lane == r) { my_ce = ce_a; my_ind = ia; }
+          if (lane == r + 1) { my_ce = ce_b; my_ind = ib; }
+        }
+        if (r < nrows) {
+          float4 va[KV > 0 ? KV : 1];
+          row_load<(KV > 0 ? KV : 1)>(P, row0 + r, lane, nvec, va);
+          float ce_a;
+          int ia;
+          row_softmax_ce<(KV > 0 ? KV : 1)>(P, row0 + r, lane, nvec, va, ce_a, ia);
+          if (lane == r) { my_ce = ce_a; my_ind = ia; }
+        }
+      } else {
+        for (int r = 0; r < nrows; ++r) {
+          float ce_a;
+          int ia;
+          row_softmax_ce_scalar(P, row0 + r, lane, ce_a, ia);
+          if (lane == r) { my_ce = ce_a; my_ind = ia; }
+        }
+      }
+    }
+    if (lane < nrows) {
+      const int64_t row = row0 + lane;
+      if (has_ce) {
+        acc_ce += (double)my_ce;
+        if (P.row_ce) P.row_ce[row] = my_ce;
+        if (P.argmax_out) P.argmax_out[row] = (int64_t)my_ind;
+      }
+      if (has_pose) acc_pose += (double)pose_row(P, row, my_ind);
+    }
+  }
+
+  // deterministic reduction: warp -> block (fixed order) -> per-block partial -> last block sums
+  // the partials in block order.
+  __shared__ double s_part[2][8];
+  __shared__ bool s_last;
+  acc_ce = warp_sum(acc_ce);
+  acc_pose = warp_sum(acc_pose);
+  if (lane == 0) { s_part[0][warp] = acc_ce; s_part[1][warp] = acc_pose; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_part[0][w]; b += s_part[1][w]; }
+    P.partials[2 * blockIdx.x + 0] = a;
+    P.partials[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    const unsigned int t = atomicAdd(P.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    // lanes take interleaved blocks, then a fixed-shape shuffle tree: order is launch-invariant
+    for (int i = lane; i < (int)gridDim.x; i += 32) {
+      a += __ldcg(P.partials + 2 * i + 0);
+      b += __ldcg(P.partials + 2 * i + 1);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      P.out_loss[0] = (float)(a / (double)P.B);
+      P.out_loss[1] = (float)(b / (double)P.B);
+      *P.ticket = 0u;   // leave the workspace reusable
+    }
+  }
+}
+
+constexpr int kLossThreads = 256;
+constexpr int kLossMaxBlocks = 148 * 8;
+
+}  // namespace
+
+extern "C" int64_t bdp_bd_loss_workspace_bytes(int64_t /*B*/) {
+  return (int64_t)kLossMaxBlocks * 2 * sizeof(double) + 64;
+}
+
+extern "C" int bdp_bd_loss_fwd_bwd(const float* logits, int64_t B, int64_t K, int64_t ld_logits,
+                                   const int64_t* bin_true, const float* pred, int ndim,
+                                   const float* keys, int use_keys, const float* target,
+                                   int pose_mode, float* out_loss, float* row_ce, float* row_pose,
+                                   float* grad_logits, float* grad_pred, float grad_scale,
+                                   int64_t* argmax_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  BDP_REQUIRE(B > 0, "bd_loss: B must be positive (got %lld)", (long long)B);
+  BDP_REQUIRE(out_loss != nullptr, "bd_loss: out_loss is NULL");
+  BDP_REQUIRE(workspace != nullptr && workspace_bytes >= bdp_bd_loss_workspace_bytes(B),
+              "bd_loss: workspace too small (%lld < %lld)", (long long)workspace_bytes,
+              (long long)bdp_bd_loss_workspace_bytes(B));
+  BDP_REQUIRE(pose_mode >= BDP_POSE_NONE && pose_mode <= BDP_POSE_ROTMAT,
+              "bd_loss: unknown pose_mode %d", pose_mode);
+  if (logits) {
+    BDP_REQUIRE(K > 0 && ld_logits >= K, "bd_loss: bad K=%lld ld=%lld", (long long)K,
+                (long long)ld_logits);
+    BDP_REQUIRE(bin_true != nullptr, "bd_loss: bin_true is NULL with logits given");
+  } else {
+    BDP_REQUIRE(!use_keys && pose_mode != BDP_POSE_RIEMANNIAN,
+                "bd_loss: key gather needs logits (argmax)");
+    BDP_REQUIRE(pose_mode != BDP_POSE_NONE, "bd_loss: nothing to compute");
+  }
+  int tdim = ndim;
+  if (pose_mode != BDP_POSE_NONE) {
+    BDP_REQUIRE(pred != nullptr && target != nullptr, "bd_loss: pred/target is NULL");
+    switch (pose_mode) {
+      case BDP_POSE_MSE: BDP_REQUIRE(ndim >= 1 && ndim <= 9, "bd_loss: MSE ndim %d", ndim); break;
+      case BDP_POSE_GEODESIC_AA: BDP_REQUIRE(ndim == 3, "bd_loss: axis-angle needs ndim=3"); break;
+      case BDP_POSE_GEODESIC_Q: BDP_REQUIRE(ndim == 4, "bd_loss: quaternion needs ndim=4"); break;
+      case BDP_POSE_RIEMANNIAN:
+        BDP_REQUIRE(ndim == 3 && keys != nullptr, "bd_loss: riemannian needs ndim=3 and keys");
+        tdim = 9;
+        break;
+      case BDP_POSE_ROTMAT: BDP_REQUIRE(ndim == 9 && !use_keys, "bd_loss: rotmat needs ndim=9"); break;
+    }
+    if (use_keys) BDP_REQUIRE(keys != nullptr && ndim <= 4, "bd_loss: use_keys needs keys, ndim<=4");
+  }
+
+  LossParams P;
+  P.logits = logits; P.B = B; P.K = K; P.ld = ld_logits; P.bin_true = bin_true;
+  P.pred = pred; P.ndim = ndim; P.keys = keys; P.use_keys = use_keys; P.target = target;
+  P.tdim = tdim; P.pose_mode = pose_mode; P.out_loss = out_loss; P.row_ce = row_ce;
+  P.row_pose = row_pose; P.grad_logits = grad_logits; P.grad_pred = grad_pred;
+  P.argmax_out = argmax_out;
+  P.partials = reinterpret_cast<double*>(workspace);
+  P.ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) +
+                                             (size_t)kLossMaxBlocks * 2 * sizeof(double));
+  P.inv_B = grad_scale > 0.f ? grad_scale : 1.f / (float)B;
+
+  // rows per warp: keep >= ~16 warps per SM busy before making warps walk several rows
+  const int sms = bdp_num_sms();
+  const int64_t want_warps = (int64_t)sms * 16;
+  int R = (int)((B + want_warps - 1) / want_warps);
+  R = R < 1 ? 1 : (R > 32 ? 32 : R);
+  if (R > 1 && (R & 1)) ++R;          // even, so the 2-rows-in-flight loop has no tail
+  if (R > 32) R = 32;
+  P.rows_per_warp = R;
+  const int64_t groups = (B + R - 1) / R;
+  const int warps_per_block = kLossThreads / 32;
+  int64_t blocks = (groups + warps_per_block - 1) / warps_per_block;
+  if (blocks > kLossMaxBlocks) blocks = kLossMaxBlocks;
+
+  const bool vec_ok = logits && (K % 4 == 0) && (ld_logits % 4 == 0) && K <= 1024 &&
+                      ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+                      (!grad_logits || (reinterpret_cast<uintptr_t>(grad_logits) & 15) == 0);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!logits || !vec_ok) {
+    bd_loss_kernel<0><<<(unsigned)blocks, kLossThreads, 0, st>>>(P);
+  } else if (K <= 128) {
+    bd_loss_kernel<1><<<(unsigned)blocks, kLossThreads, 0, st>>>(P);
+  } else if (K <= 256) {
+    bd_loss_kernel<2><<<(unsigned)blocks, kLossThreads, 0, st>>>(P);
+  } else if (K <= 512) {
+    bd_loss_kernel<4><<<(unsigned)blocks, kLossThreads, 0, st>>>(P);
+  } else {
+    bd_loss_kernel<8><<<(unsigned)blocks, kLossThreads, 0, st>>>(P);
+  }
+  BDP_CUDA_CHECK_LAUNCH("bd_loss_kernel");
+  return BDP_OK;
+}
