@@ -39,182 +39,199 @@ struct LossParams {
 };
 
 // ---- pose losses: value + gradient w.r.t. the composed prediction ---------------------------
-// All follow the reference's fp32 formulas; eps / clamp conventions cited inline.
+// The per-row pose math is O(1) next to the O(K) logits, and its conditioning is poor exactly where
+// training ends up (small angles: acos near 1, 1/sqrt(1 - w^2)), so it is evaluated in fp64 from
+// the fp32 inputs and rounded once.  The result is the correctly rounded value of the reference's
+// formula; the reference's own fp32 evaluation differs from it by its rounding noise
+// (~2^-24 / (1 - w^2) relative).  eps / clamp conventions are the reference's, cited inline.
+#define BDP_EPS_D 1e-6
+#define BDP_NORM_EPS_D 1e-12
 
 // axisAngle.geodesic_loss.forward, axisAngle.py:110-120.  p = predicted axis-angle (key + delta),
 // t = ground truth.  Returns theta; g = d theta / d p.
-__device__ __forceinline__ float pose_geodesic_aa(const float p[3], const float t[3], float g[3]) {
-  const float ap = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-  const float at = sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
-  const float ipn = 1.f / fmaxf(ap, BDP_NORM_EPS);   // F.normalize: v / max(||v||, 1e-12)
-  const float itn = 1.f / fmaxf(at, BDP_NORM_EPS);
-  const float ph[3] = {p[0] * ipn, p[1] * ipn, p[2] * ipn};
-  const float th[3] = {t[0] * itn, t[1] * itn, t[2] * itn};
-  const float d = th[0] * ph[0] + th[1] * ph[1] + th[2] * ph[2];
-  float sp, cp, st, ct;
-  sincosf(0.5f * ap, &sp, &cp);
-  sincosf(0.5f * at, &st, &ct);
-  const float w = ct * cp + st * sp * d;
-  const float c = fabsf(w);
-  const float cc = fminf(c, 1.f - BDP_EPS);            // clamp(|w|, -1+eps, 1-eps); |w| >= 0
-  const float theta = 2.f * acosf(cc);
+__device__ __forceinline__ double pose_geodesic_aa(const double p[3], const double t[3],
+                                                   double g[3]) {
+  const double ap = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  const double at = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  const double ipn = 1.0 / fmax(ap, BDP_NORM_EPS_D);   // F.normalize: v / max(||v||, 1e-12)
+  const double itn = 1.0 / fmax(at, BDP_NORM_EPS_D);
+  const double ph[3] = {p[0] * ipn, p[1] * ipn, p[2] * ipn};
+  const double th[3] = {t[0] * itn, t[1] * itn, t[2] * itn};
+  const double d = th[0] * ph[0] + th[1] * ph[1] + th[2] * ph[2];
+  double sp, cp, st, ct;
+  sincos(0.5 * ap, &sp, &cp);
+  sincos(0.5 * at, &st, &ct);
+  const double w = ct * cp + st * sp * d;
+  const double c = fabs(w);
+  const double cc = fmin(c, 1.0 - BDP_EPS_D);          // clamp(|w|, -1+eps, 1-eps); |w| >= 0
+  const double theta = 2.0 * acos(cc);
   // backward: zero where the clamp saturates (torch.clamp passes the
   // gradient on the closed interval), sign(0) = 0 from torch.abs.
-  float dth_dw = 0.f;
-  if (c <= 1.f - BDP_EPS && w != 0.f) dth_dw = (w > 0.f ? -2.f : 2.f) * rsqrtf(1.f - c * c);
-  const float dw_dap = 0.5f * (st * cp * d - ct * sp);
-  const float k = st * sp;                              // dw/d p_hat = k * t_hat
-  if (ap > BDP_NORM_EPS) {
+  double dth_dw = 0.0;
+  if (c <= 1.0 - BDP_EPS_D && w != 0.0) dth_dw = (w > 0.0 ? -2.0 : 2.0) / sqrt(1.0 - c * c);
+  const double dw_dap = 0.5 * (st * cp * d - ct * sp);
+  const double k = st * sp;                             // dw/d p_hat = k * t_hat
+  if (ap > BDP_NORM_EPS_D) {
     // d ap/dp = p_hat ; d p_hat/dp = (I - p_hat p_hat^T)/ap
-    const float proj = k * d;                           // p_hat . (k t_hat)
-    const float ia = 1.f / ap;
+    const double proj = k * d;                          // p_hat . (k t_hat)
+    const double ia = 1.0 / ap;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       g[i] = dth_dw * (dw_dap * ph[i] + (k * th[i] - proj * ph[i]) * ia);
   } else {
     // ||p|| <= 1e-12: normalize is p/eps (linear), torch.norm's subgradient at 0 is 0
-    const float s = (ap > 0.f) ? dw_dap / ap : 0.f;
+    const double s = (ap > 0.0) ? dw_dap / ap : 0.0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) g[i] = dth_dw * (s * p[i] + k * th[i] * (1.f / BDP_NORM_EPS));
+    for (int i = 0; i < 3; ++i) g[i] = dth_dw * (s * p[i] + k * th[i] * (1.0 / BDP_NORM_EPS_D));
   }
   return theta;
 }
 
 // quaternion.geodesic_loss.forward, quaternion.py:156-163.
-__device__ __forceinline__ float pose_geodesic_quat(const float q[4], const float t[4],
-                                                    float g[4]) {
-  const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  const float in = 1.f / fmaxf(n, BDP_NORM_EPS);
-  const float qh[4] = {q[0] * in, q[1] * in, q[2] * in, q[3] * in};
-  const float w = t[0] * qh[0] + t[1] * qh[1] + t[2] * qh[2] + t[3] * qh[3];
-  const float c = fabsf(w);
-  const float theta = 2.f * acosf(fminf(c, 1.f - BDP_EPS));
-  float dth_dw = 0.f;
-  if (c <= 1.f - BDP_EPS && w != 0.f) dth_dw = (w > 0.f ? -2.f : 2.f) * rsqrtf(1.f - c * c);
-  if (n > BDP_NORM_EPS) {
+__device__ __forceinline__ double pose_geodesic_quat(const double q[4], const double t[4],
+                                                     double g[4]) {
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double in = 1.0 / fmax(n, BDP_NORM_EPS_D);
+  const double qh[4] = {q[0] * in, q[1] * in, q[2] * in, q[3] * in};
+  const double w = t[0] * qh[0] + t[1] * qh[1] + t[2] * qh[2] + t[3] * qh[3];
+  const double c = fabs(w);
+  const double theta = 2.0 * acos(fmin(c, 1.0 - BDP_EPS_D));
+  double dth_dw = 0.0;
+  if (c <= 1.0 - BDP_EPS_D && w != 0.0) dth_dw = (w > 0.0 ? -2.0 : 2.0) / sqrt(1.0 - c * c);
+  if (n > BDP_NORM_EPS_D) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) g[i] = dth_dw * (t[i] - qh[i] * w) * in;
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) g[i] = dth_dw * t[i] * (1.f / BDP_NORM_EPS);
+    for (int i = 0; i < 4; ++i) g[i] = dth_dw * t[i] * (1.0 / BDP_NORM_EPS_D);
   }
   return theta;
 }
 
 // RiemannianLoss, binDeltaLosses.py:221-239: R_hat = Key * exp([r]x), phi = acos(clamp((tr(R_hat^T
 // R) - 1)/2)).  With M = Key^T R:  tr = sum_ij E_ij M_ij,  E = I + sin(th)[a]x + (1-cos th)[a]x^2.
-__device__ __forceinline__ float pose_riemannian(const float r[3], const float* __restrict__ key,
-                                                 const float R[9], float g[3]) {
-  float M[9];
+__device__ __forceinline__ double pose_riemannian(const double r[3], const float* __restrict__ key,
+                                                  const double R[9], double g[3]) {
+  double Kd[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Kd[i] = (double)__ldg(key + i);
+  double M[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      M[i * 3 + j] = key[0 * 3 + i] * R[0 * 3 + j] + key[1 * 3 + i] * R[1 * 3 + j] +
-                     key[2 * 3 + i] * R[2 * 3 + j];
-  const float th = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-  const float in = 1.f / fmaxf(th, BDP_NORM_EPS);
-  const float a[3] = {r[0] * in, r[1] * in, r[2] * in};
-  float s, c;
-  sincosf(th, &s, &c);
-  const float omc = 1.f - c;
+      M[i * 3 + j] = Kd[0 * 3 + i] * R[0 * 3 + j] + Kd[1 * 3 + i] * R[1 * 3 + j] +
+                     Kd[2 * 3 + i] * R[2 * 3 + j];
+  const double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  const double in = 1.0 / fmax(th, BDP_NORM_EPS_D);
+  const double a[3] = {r[0] * in, r[1] * in, r[2] * in};
+  double s, c;
+  sincos(th, &s, &c);
+  const double omc = 1.0 - c;
   // skew from the reference's `proj` rows (binDeltaLosses.py:217): [[0,-a3,a2],[a3,0,-a1],[-a2,a1,0]]
-  const float A[9] = {0.f, -a[2], a[1], a[2], 0.f, -a[0], -a[1], a[0], 0.f};
-  float tr = 0.f;
+  const double A[9] = {0.0, -a[2], a[1], a[2], 0.0, -a[0], -a[1], a[0], 0.0};
+  double tr = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const float AA = A[i * 3 + 0] * A[0 * 3 + j] + A[i * 3 + 1] * A[1 * 3 + j] +
-                       A[i * 3 + 2] * A[2 * 3 + j];
-      const float E = (i == j ? 1.f : 0.f) + s * A[i * 3 + j] + omc * AA;
+      const double AA = A[i * 3 + 0] * A[0 * 3 + j] + A[i * 3 + 1] * A[1 * 3 + j] +
+                        A[i * 3 + 2] * A[2 * 3 + j];
+      const double E = (i == j ? 1.0 : 0.0) + s * A[i * 3 + j] + omc * AA;
       tr += E * M[i * 3 + j];
     }
-  const float u = 0.5f * (tr - 1.f);
-  const float uc = fminf(fmaxf(u, -1.f + BDP_EPS), 1.f - BDP_EPS);
-  const float phi = acosf(uc);
-  float dphi_dt = 0.f;
-  if (u >= -1.f + BDP_EPS && u <= 1.f - BDP_EPS) dphi_dt = -0.5f * rsqrtf(1.f - u * u);
-  if (th > BDP_NORM_EPS) {
-    const float trM = M[0] + M[4] + M[8];
-    const float m[3] = {M[7] - M[5], M[2] - M[6], M[3] - M[1]};
-    const float am = a[0] * m[0] + a[1] * m[1] + a[2] * m[2];
-    float Sa[3];  // (M + M^T) a
+  const double u = 0.5 * (tr - 1.0);
+  const double uc = fmin(fmax(u, -1.0 + BDP_EPS_D), 1.0 - BDP_EPS_D);
+  const double phi = acos(uc);
+  double dphi_dt = 0.0;
+  if (u >= -1.0 + BDP_EPS_D && u <= 1.0 - BDP_EPS_D) dphi_dt = -0.5 / sqrt(1.0 - u * u);
+  if (th > BDP_NORM_EPS_D) {
+    const double trM = M[0] + M[4] + M[8];
+    const double m[3] = {M[7] - M[5], M[2] - M[6], M[3] - M[1]};
+    const double am = a[0] * m[0] + a[1] * m[1] + a[2] * m[2];
+    double Sa[3];  // (M + M^T) a
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       Sa[i] = (M[i * 3 + 0] + M[0 * 3 + i]) * a[0] + (M[i * 3 + 1] + M[1 * 3 + i]) * a[1] +
               (M[i * 3 + 2] + M[2 * 3 + i]) * a[2];
-    const float aMa = 0.5f * (a[0] * Sa[0] + a[1] * Sa[1] + a[2] * Sa[2]);
-    const float dt_dth = c * am + s * (aMa - trM);
-    float v[3];
+    const double aMa = 0.5 * (a[0] * Sa[0] + a[1] * Sa[1] + a[2] * Sa[2]);
+    const double dt_dth = c * am + s * (aMa - trM);
+    double v[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) v[i] = s * m[i] + omc * Sa[i];
-    const float av = a[0] * v[0] + a[1] * v[1] + a[2] * v[2];
-    const float ith = 1.f / th;
+    const double av = a[0] * v[0] + a[1] * v[1] + a[2] * v[2];
+    const double ith = 1.0 / th;
 #pragma unroll
     for (int i = 0; i < 3; ++i) g[i] = dphi_dt * (dt_dth * a[i] + (v[i] - av * a[i]) * ith);
   } else {
-    g[0] = g[1] = g[2] = 0.f;
+    g[0] = g[1] = g[2] = 0.0;
   }
   return phi;
 }
 
 // RiemannianLoss.my_loss on explicit matrices (binDeltaLosses.py:221-225): P predicted, T truth.
-__device__ __forceinline__ float pose_rotmat(const float P[9], const float T[9], float g[9]) {
-  float tr = 0.f;
+__device__ __forceinline__ double pose_rotmat(const double P[9], const double T[9], double g[9]) {
+  double tr = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) tr += P[i] * T[i];
-  const float u = 0.5f * (tr - 1.f);
-  const float uc = fminf(fmaxf(u, -1.f + BDP_EPS), 1.f - BDP_EPS);
-  float dphi_dt = 0.f;
-  if (u >= -1.f + BDP_EPS && u <= 1.f - BDP_EPS) dphi_dt = -0.5f * rsqrtf(1.f - u * u);
+  const double u = 0.5 * (tr - 1.0);
+  const double uc = fmin(fmax(u, -1.0 + BDP_EPS_D), 1.0 - BDP_EPS_D);
+  double dphi_dt = 0.0;
+  if (u >= -1.0 + BDP_EPS_D && u <= 1.0 - BDP_EPS_D) dphi_dt = -0.5 / sqrt(1.0 - u * u);
 #pragma unroll
   for (int i = 0; i < 9; ++i) g[i] = dphi_dt * T[i];
-  return acosf(uc);
+  return acos(uc);
 }
 
 // Per-row pose phase. Returns the row's pose-loss value, writes the row's gradient.
 __device__ __forceinline__ float pose_row(const LossParams& P, int64_t row, int ind) {
   const int nd = P.ndim;
-  float p[9], t[9], g[9];
+  float p[9], t[9];
   const float* pr = P.pred + row * nd;
 #pragma unroll
   for (int i = 0; i < 9; ++i) p[i] = (i < nd) ? __ldg(pr + i) : 0.f;
   const float* tg = P.target + row * P.tdim;
 #pragma unroll
   for (int i = 0; i < 9; ++i) t[i] = (i < P.tdim) ? __ldg(tg + i) : 0.f;
-  float val = 0.f;
-  if (P.pose_mode == BDP_POSE_RIEMANNIAN) {
-    val = pose_riemannian(p, P.keys + (int64_t)ind * 9, t, g);
+  if (P.use_keys && P.pose_mode != BDP_POSE_RIEMANNIAN) {
+    // centers[argmax] + delta: one fp32 add, as the reference composes it
+    // (learnGeodesicBDModel.py:176-177, binDeltaLosses.py:48-49)
+    const float* key = P.keys + (int64_t)ind * nd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nd) p[i] = __fadd_rn(p[i], __ldg(key + i));
+  }
+  float val;
+  float gf[9];
+  if (P.pose_mode == BDP_POSE_MSE) {   // nn.MSELoss: mean over B*ndim elements (fp32, as torch)
+    const float ind_nd = 1.f / (float)nd;
+    val = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float e = (i < nd) ? p[i] - t[i] : 0.f;
+      val += e * e;
+      gf[i] = 2.f * e * ind_nd;
+    }
+    val *= ind_nd;
   } else {
-    if (P.use_keys) {
-      const float* key = P.keys + (int64_t)ind * nd;
+    double pd[9], td[9], g[9];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < nd) p[i] += __ldg(key + i);
-    }
-    if (P.pose_mode == BDP_POSE_GEODESIC_AA) {
-      val = pose_geodesic_aa(p, t, g);
-    } else if (P.pose_mode == BDP_POSE_GEODESIC_Q) {
-      val = pose_geodesic_quat(p, t, g);
-    } else if (P.pose_mode == BDP_POSE_ROTMAT) {
-      val = pose_rotmat(p, t, g);
-    } else {  // BDP_POSE_MSE: nn.MSELoss mean over B*ndim elements
-      const float ind_nd = 1.f / (float)nd;
+    for (int i = 0; i < 9; ++i) { pd[i] = (double)p[i]; td[i] = (double)t[i]; g[i] = 0.0; }
+    double v;
+    if (P.pose_mode == BDP_POSE_RIEMANNIAN) v = pose_riemannian(pd, P.keys + (int64_t)ind * 9, td, g);
+    else if (P.pose_mode == BDP_POSE_GEODESIC_AA) v = pose_geodesic_aa(pd, td, g);
+    else if (P.pose_mode == BDP_POSE_GEODESIC_Q) v = pose_geodesic_quat(pd, td, g);
+    else v = pose_rotmat(pd, td, g);
+    val = (float)v;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const float e = (i < nd) ? p[i] - t[i] : 0.f;
-        val += e * e;
-        g[i] = 2.f * e * ind_nd;
-      }
-      val *= ind_nd;
-    }
+    for (int i = 0; i < 9; ++i) gf[i] = (float)(g[i] * (double)P.inv_B);
   }
   if (P.grad_pred) {
     float* gp = P.grad_pred + row * nd;
+    const float sc = (P.pose_mode == BDP_POSE_MSE) ? P.inv_B : 1.f;
 #pragma unroll
     for (int i = 0; i < 9; ++i)
-      if (i < nd) gp[i] = g[i] * P.inv_B;
+      if (i < nd) gp[i] = gf[i] * sc;
   }
   if (P.row_pose) P.row_pose[row] = val;
   return val;
