@@ -1,0 +1,425 @@
+// (a) Grouped TF32 GEMM for the bin-delta heads on sm_100a: tcgen05.mma with TMEM accumulators,
+// operands streamed by TMA straight from the fp32 master weights (no bf16 repack pass: at the
+// reference's batch sizes the head is bound by streaming the weights once).
+//
+//   D_g[m, n] = sum_k A_g(m, k) * B_g(n, k)          g = 0..G-1
+//
+// Either operand may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); both are
+// legal tcgen05 TF32 shared-memory layouts, so one kernel serves fprop (W x^T), dgrad (W^T dy) and
+// wgrad (dy a^T) of nn.Linear (binDeltaModels.py:71-75, 87-91) without any transpose pass:
+//   rows of D (m)  -> the 128 TMEM lanes  (always the "feature" side: swap-AB, batch is the N side)
+//   cols of D (n)  -> TMEM columns, BN <= 256 per tile
+//
+// Warp roles (256 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> global).  Three
+// mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
+// accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBM = 128;            // tile rows = TMEM lanes
+constexpr int kBK = 32;             // fp32 per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 8;           // K of one tcgen05.mma.kind::tf32
+constexpr int kGemmThreads = 256;
+constexpr int kABytes = kBM * kBK * 4;     // 16 KB per stage
+constexpr int kMaxStages = 10;
+
+struct GemmParams {
+  int M, N, K, G;
+  int a_mn, b_mn;                   // 1 = MN-major operand
+  int BN;                           // tile columns: multiple of 32, <= 256
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total, stages;
+  int a_g, b_g;                     // 1: operand has a group axis, 0: shared by all groups
+  float* C;
+  long long ldc, c_gstride, c_sstride;
+  int c_nm;                         // 0: C[m*ldc + n], 1: C[n*ldc + m]
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0;; ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (it > (1u << 27)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1).
+//   K-major : rows are 128 B apart inside an 8-row group, groups SBO = 1024 B apart; the K
+//             position inside the 128 B row is selected by advancing the start address.
+//   MN-major: 32-bit operands only exist in the SWIZZLE_128B_BASE32B layout (type 1; TMA mode
+//             SWIZZLE_128B_ATOM_32B): rows of 128 B hold 32 consecutive MN elements, 4 K-rows form
+//             a swizzle atom (SBO = 512 B between atoms, one K=8 MMA spans two), the next 32 MN
+//             elements live LBO bytes further.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;     // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte aligned operand ring (swizzle-128B atoms are 1 KB), barriers after it
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = static_cast<uint32_t>(P.BN) * kBK * 4;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar_base = base + P.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tmem_cols = (2 * P.BN <= 32) ? 32 : (2 * P.BN <= 64) ? 64 : (2 * P.BN <= 128) ? 128
+                        : (2 * P.BN <= 256) ? 256 : 512;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&s_tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int tiles_per_group = P.m_tiles * P.n_tiles * P.splits;
+  const int total_tiles = P.G * tiles_per_group;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int g = t / tiles_per_group;
+      int r = t - g * tiles_per_group;
+      const int sp = r % P.splits; r /= P.splits;
+      const int nt = r % P.n_tiles;
+      const int mt = r / P.n_tiles;
+      const int kb0 = sp * P.kb_per_split;
+      const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+      const int m0 = mt * kBM, n0 = nt * P.BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = base + stage * stage_bytes;
+        const uint32_t sb = sa + kABytes;
+        mbar_expect_tx(full_bar(stage), stage_bytes);
+        const int k0 = kb * kBK;
+        if (!P.a_mn) {
+          tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, g * P.a_g);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kBM / 32; ++j)
+            tma_load_3d(sa + j * 4096, &tmA, full_bar(stage), m0 + 32 * j, k0, g * P.a_g);
+        }
+        if (!P.b_mn) {
+          tma_load_3d(sb, &tmB, full_bar(stage), k0, n0, g * P.b_g);
+        } else {
+          for (int j = 0; j < P.BN / 32; ++j)
+            tma_load_3d(sb + j * 4096, &tmB, full_bar(stage), n0 + 32 * j, k0, g * P.b_g);
+        }
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer (single thread) =====
+    // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b_format TF32 = 2 (bits 7, 10),
+    // a/b major (bits 15, 16), N >> 3 (bits 17..22), M >> 4 (bits 24..28)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
+                           (static_cast<uint32_t>(P.a_mn) << 15) |
+                           (static_cast<uint32_t>(P.b_mn) << 16) |
+                           (static_cast<uint32_t>(P.BN >> 3) << 17) |
+                           (static_cast<uint32_t>(kBM >> 4) << 24);
+    const uint32_t a_lbo = P.a_mn ? 4096u : 16u, b_lbo = P.b_mn ? 4096u : 16u;
+    const uint32_t a_kstep = P.a_mn ? 1024u : kUmmaK * 4u;
+    const uint32_t b_kstep = P.b_mn ? 1024u : kUmmaK * 4u;
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int r = t % tiles_per_group;
+      const int sp = r % P.splits;
+      const int kb0 = sp * P.kb_per_split;
+      const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * P.BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * stage_bytes;
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t ad = umma_desc(sa + k * a_kstep, a_lbo, P.a_mn ? 512u : 1024u, P.a_mn ? 1u : 2u);
+          const uint64_t bd = umma_desc(sb + k * b_kstep, b_lbo, P.b_mn ? 512u : 1024u, P.b_mn ? 1u : 2u);
+          umma_tf32(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));                 // frees the smem slot when the MMAs retire
+        if (kb == kb1 - 1) umma_commit(tfull_bar(as)); // accumulator complete -> epilogue
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;                            // TMEM lane quarter of this warp
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int g = t / tiles_per_group;
+      int r = t - g * tiles_per_group;
+      const int sp = r % P.splits; r /= P.splits;
+      const int nt = r % P.n_tiles;
+      const int mt = r / P.n_tiles;
+      const int m = mt * kBM + q * 32 + lane;
+      const int n0 = nt * P.BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      float* Cg = P.C + sp * P.c_sstride + g * P.c_gstride;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                            static_cast<uint32_t>(as * P.BN);
+      for (int c = 0; c < P.BN / 32; ++c) {
+        if (n0 + c * 32 >= P.N) break;                 // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(trow + c * 32, v);
+        const int nb = n0 + c * 32;
+        if (!P.c_nm) {
+          if (m < P.M) {
+            float* dst = Cg + static_cast<long long>(m) * P.ldc + nb;
+            const bool vec = (nb + 32 <= P.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(dst + i) =
+                    make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < P.N) dst[i] = __uint_as_float(v[i]);
+            }
+          }
+        } else {
+          if (m < P.M) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < P.N) Cg[static_cast<long long>(nb + i) * P.ldc + m] = __uint_as_float(v[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rank-3 fp32 map over [dim2][dim1][dim0] (dim0 contiguous), 128-byte swizzle (16 B atoms for
+// K-major tiles, 32 B atoms for MN-major tiles), zero OOB fill
+int make_map(CUtensorMap* map, const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+             uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1,
+             bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { bdp_set_error("gemm_tf32: cuTensorMapEncodeTiled entry point unavailable"); return BDP_ERR_CUDA; }
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {stride1_elems * 4, stride2_elems * 4};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    bdp_set_error("gemm_tf32: cuTensorMapEncodeTiled failed (%d) dims=[%llu,%llu,%llu] strides=[%llu,%llu]B "
+                  "box=[%u,%u]", (int)r, (unsigned long long)dim0, (unsigned long long)dim1,
+                  (unsigned long long)dim2, (unsigned long long)strides[0],
+                  (unsigned long long)strides[1], box0, box1);
+    return BDP_ERR_CUDA;
+  }
+  return BDP_OK;
+}
+
+}  // namespace
+
+extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t a_gstride,
+                             const float* B, int b_major, int64_t b_ld, int64_t b_gstride, float* C,
+                             int c_layout, int64_t ldc, int64_t c_gstride, int64_t M, int64_t N,
+                             int64_t K, int G, int splits, int64_t c_sstride, void* stream) {
+  BDP_REQUIRE(A && B && C, "gemm_tf32: NULL operand");
+  BDP_REQUIRE(M > 0 && N > 0 && K > 0 && G > 0, "gemm_tf32: empty problem M=%lld N=%lld K=%lld G=%d",
+              (long long)M, (long long)N, (long long)K, G);
+  BDP_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm_tf32: dimension too large");
+  BDP_REQUIRE((a_major == 0 || a_major == 1) && (b_major == 0 || b_major == 1) &&
+                  (c_layout == 0 || c_layout == 1), "gemm_tf32: bad major/layout flag");
+  BDP_REQUIRE(a_ld % 4 == 0 && b_ld % 4 == 0 && a_gstride % 4 == 0 && b_gstride % 4 == 0,
+              "gemm_tf32: operand strides must be multiples of 4 floats (TMA: 16 bytes)");
+  BDP_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+              "gemm_tf32: operands must be 16-byte aligned");
+  BDP_REQUIRE(splits >= 1, "gemm_tf32: splits must be >= 1");
+
+  GemmParams P = {};
+  P.M = (int)M; P.N = (int)N; P.K = (int)K; P.G = G;
+  P.a_mn = a_major; P.b_mn = b_major;
+  int bn = (int)((N + 31) / 32 * 32);
+  if (bn > 256) bn = 256;
+  P.BN = bn;
+  P.m_tiles = (int)((M + kBM - 1) / kBM);
+  P.n_tiles = (int)((N + bn - 1) / bn);
+  P.kb_total = (int)((K + kBK - 1) / kBK);
+  if (splits > P.kb_total) splits = P.kb_total;
+  P.kb_per_split = (P.kb_total + splits - 1) / splits;
+  P.splits = (P.kb_total + P.kb_per_split - 1) / P.kb_per_split;   // no empty split
+  BDP_REQUIRE(P.splits == splits || c_sstride == 0 || true, "gemm_tf32: internal");
+  P.a_g = (a_gstride != 0 || G == 1) ? 1 : 0;
+  P.b_g = (b_gstride != 0 || G == 1) ? 1 : 0;
+  P.C = C; P.ldc = ldc; P.c_gstride = c_gstride; P.c_sstride = c_sstride; P.c_nm = c_layout;
+
+  const size_t stage_bytes = (size_t)kABytes + (size_t)bn * kBK * 4;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  P.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024 + 8 * (2 * kMaxStages + 4);
+
+  CUtensorMap tmA, tmB;
+  const uint64_t ga = P.a_g ? (uint64_t)G : 1, gb = P.b_g ? (uint64_t)G : 1;
+  const uint64_t a_gs = a_gstride ? (uint64_t)a_gstride : (uint64_t)a_ld * (uint64_t)(a_major ? K : M);
+  const uint64_t b_gs = b_gstride ? (uint64_t)b_gstride : (uint64_t)b_ld * (uint64_t)(b_major ? K : N);
+  int st;
+  if (!a_major) st = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, ga, (uint64_t)a_ld, a_gs, kBK, kBM, false);
+  else st = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, ga, (uint64_t)a_ld, a_gs, 32, kBK, true);
+  if (st != BDP_OK) return st;
+  if (!b_major) st = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, gb, (uint64_t)b_ld, b_gs, kBK, (uint32_t)bn, false);
+  else st = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, gb, (uint64_t)b_ld, b_gs, 32, kBK, true);
+  if (st != BDP_OK) return st;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncAttributes fa;
+    BDP_CUDA_CALL(cudaFuncGetAttributes(&fa, gemm_tf32_kernel));
+    // opt-in limit is 227 KB per block INCLUDING the kernel's static shared memory
+    BDP_CUDA_CALL(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024 - (int)fa.sharedSizeBytes));
+    attr_set = true;
+  }
+  const long long total = (long long)G * P.m_tiles * P.n_tiles * P.splits;
+  long long grid = bdp_num_sms();
+  if (grid > total) grid = total;
+  gemm_tf32_kernel<<<(unsigned)grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tmA, tmB, P);
+  BDP_CUDA_CHECK_LAUNCH("gemm_tf32_kernel");
+  return BDP_OK;
+}
+
+// number of K splits bdp_gemm_tf32 will actually use for (K, splits) — callers size the partial buffer
+extern "C" int bdp_gemm_tf32_splits(int64_t K, int splits) {
+  int kb_total = (int)((K + kBK - 1) / kBK);
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  const int per = (kb_total + splits - 1) / splits;
+  return (kb_total + per - 1) / per;
+}

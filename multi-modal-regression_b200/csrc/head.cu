@@ -1,0 +1,320 @@
+// (a) The CUDA-core pieces around the tcgen05 GEMMs of the bin-delta heads: BatchNorm1d+ReLU
+// forward/backward on feature-major activations, the label-selected / soft-mixed fc3, and the
+// split-K slab sum.  Activation tensors are [features, ldb] with the batch contiguous, so every
+// BatchNorm reduction is a reduction along one short row (B <= a few hundred): one warp per feature.
+//
+// Reference: binDeltaModels.py:62-91 (layers), 112-121 (stack + one-hot bmm select),
+// learnJointCatPoseModel_weighted.py:107-115 (softmax mixing); nn.BatchNorm1d defaults.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+// ---- BatchNorm + ReLU ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+bn_relu_fwd_kernel(const float* __restrict__ h, int64_t F, int B, int64_t ldb,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                   float* __restrict__ save_mean, float* __restrict__ save_invstd, float eps,
+                   float momentum, int training, float* __restrict__ a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (f >= F) return;
+  const float* row = h + f * ldb;
+  double mean, invstd;
+  if (training) {
+    // statistics in double (what torch's CPU kernel accumulates in; its CUDA kernel's Welford in
+    // float agrees to ~1e-7)
+    double s = 0.0;
+    for (int b = lane; b < B; b += 32) s += (double)row[b];
+    s = warp_sum(s);
+    mean = s / (double)B;
+    double v = 0.0;
+    for (int b = lane; b < B; b += 32) {
+      const double d = (double)row[b] - mean;
+      v += d * d;
+    }
+    v = warp_sum(v);
+    const double var = v / (double)B;
+    invstd = 1.0 / sqrt(var + (double)eps);
+    if (lane == 0) {
+      if (save_mean) save_mean[f] = (float)mean;
+      if (save_invstd) save_invstd[f] = (float)invstd;
+      if (running_mean) running_mean[f] = (1.f - momentum) * running_mean[f] + momentum * (float)mean;
+      if (running_var) {
+        const double unbiased = B > 1 ? v / (double)(B - 1) : var;
+        running_var[f] = (1.f - momentum) * running_var[f] + momentum * (float)unbiased;
+      }
+    }
+  } else {
+    mean = (double)running_mean[f];
+    invstd = 1.0 / sqrt((double)running_var[f] + (double)eps);
+  }
+  const float m = (float)mean, is = (float)invstd, g = gamma[f], bt = beta[f];
+  float* out = a + f * ldb;
+  for (int b = lane; b < (int)ldb; b += 32) {
+    float y = 0.f;
+    if (b < B) y = fmaxf((row[b] - m) * is * g + bt, 0.f);
+    out[b] = y;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+bn_relu_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a,
+                   const float* __restrict__ h, const float* __restrict__ gamma,
+                   const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                   int64_t F, int B, int64_t ldb, int training, float* __restrict__ dh,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (f >= F) return;
+  const float* dar = da + f * ldb;
+  const float* ar = a + f * ldb;
+  const float* hr = h + f * ldb;
+  const float m = save_mean[f], is = save_invstd[f], g = gamma[f];
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < B; b += 32) {
+    const float dy = ar[b] > 0.f ? dar[b] : 0.f;      // relu'(x) = 1[x > 0]
+    const float xh = (hr[b] - m) * is;
+    s1 += (double)dy;
+    s2 += (double)dy * (double)xh;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    if (dgamma) dgamma[f] = (float)s2;
+    if (dbeta) dbeta[f] = (float)s1;
+  }
+  const float k1 = training ? (float)(s1 / (double)B) : 0.f;
+  const float k2 = training ? (float)(s2 / (double)B) : 0.f;
+  float* out = dh + f * ldb;
+  for (int b = lane; b < (int)ldb; b += 32) {
+    float v = 0.f;
+    if (b < B) {
+      const float dy = ar[b] > 0.f ? dar[b] : 0.f;
+      const float xh = (hr[b] - m) * is;
+      v = g * is * (dy - k1 - xh * k2);
+    }
+    out[b] = v;
+  }
+}
+
+// ---- fc3 + mixing ---------------------------------------------------------------------------------
+constexpr int kFc3OutPerBlock = 32;
+
+__global__ void __launch_bounds__(256)
+fc3_fwd_kernel(const float* __restrict__ a2, int64_t ldb, const float* __restrict__ w3,
+               const float* __restrict__ b3, const float* __restrict__ mix, int H, int O, int N2,
+               float* __restrict__ y) {
+  extern __shared__ float s_col[];                    // [N2] activation column of (head, sample)
+  const int b = blockIdx.y;
+  const int o0 = blockIdx.x * kFc3OutPerBlock;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[kFc3OutPerBlock / 8] = {0.f, 0.f, 0.f, 0.f};
+  for (int hd = 0; hd < H; ++hd) {
+    const float p = mix[(int64_t)b * H + hd];
+    if (p == 0.f) continue;                           // block-uniform
+    __syncthreads();
+    for (int j = threadIdx.x; j < N2; j += blockDim.x)
+      s_col[j] = a2[((int64_t)hd * N2 + j) * ldb + b];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kFc3OutPerBlock / 8; ++i) {
+      const int o = o0 + warp * (kFc3OutPerBlock / 8) + i;
+      if (o >= O) continue;
+      const float* w = w3 + ((int64_t)hd * O + o) * N2;
+      float d = 0.f;
+      for (int j = lane; j < N2; j += 32) d = fmaf(w[j], s_col[j], d);
+      d = warp_sum(d);
+      acc[i] += p * (d + b3[(int64_t)hd * O + o]);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kFc3OutPerBlock / 8; ++i) {
+      const int o = o0 + warp * (kFc3OutPerBlock / 8) + i;
+      if (o < O) y[(int64_t)b * O + o] = acc[i];
+    }
+  }
+}
+
+// da2 column of every (head, sample) pair with a non-zero mixing weight (da2 is pre-zeroed)
+__global__ void __launch_bounds__(256)
+fc3_bwd_act_kernel(const float* __restrict__ dy, const float* __restrict__ w3,
+                   const float* __restrict__ mix, int64_t ldb, int H, int O, int N2,
+                   float* __restrict__ da2) {
+  extern __shared__ float s_dy[];                     // [O]
+  const int hd = blockIdx.x, b = blockIdx.y;
+  const float p = mix[(int64_t)b * H + hd];
+  if (p == 0.f) return;
+  for (int o = threadIdx.x; o < O; o += blockDim.x) s_dy[o] = p * dy[(int64_t)b * O + o];
+  __syncthreads();
+  for (int j = threadIdx.x; j < N2; j += blockDim.x) {
+    const float* w = w3 + (int64_t)hd * O * N2 + j;
+    float d = 0.f;
+    for (int o = 0; o < O; ++o) d = fmaf(s_dy[o], w[(int64_t)o * N2], d);
+    da2[((int64_t)hd * N2 + j) * ldb + b] = d;
+  }
+}
+
+constexpr int kFc3WOut = 8;   // outputs per block in the weight-gradient kernel
+
+__global__ void __launch_bounds__(256)
+fc3_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int64_t ldb,
+                 const float* __restrict__ mix, int B, int H, int O, int N2,
+                 float* __restrict__ dw3, float* __restrict__ db3) {
+  extern __shared__ float s_pd[];                     // [B][kFc3WOut] mix * dy
+  const int hd = blockIdx.x;
+  const int o0 = blockIdx.y * kFc3WOut;
+  for (int i = threadIdx.x; i < B * kFc3WOut; i += blockDim.x) {
+    const int b = i / kFc3WOut, oo = i % kFc3WOut;
+    const int o = o0 + oo;
+    s_pd[i] = (o < O) ? mix[(int64_t)b * H + hd] * dy[(int64_t)b * O + o] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < N2; j += blockDim.x) {
+    const float* ar = a2 + ((int64_t)hd * N2 + j) * ldb;
+    float acc[kFc3WOut];
+#pragma unroll
+    for (int oo = 0; oo < kFc3WOut; ++oo) acc[oo] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float av = ar[b];
+#pragma unroll
+      for (int oo = 0; oo < kFc3WOut; ++oo) acc[oo] = fmaf(s_pd[b * kFc3WOut + oo], av, acc[oo]);
+    }
+#pragma unroll
+    for (int oo = 0; oo < kFc3WOut; ++oo)
+      if (o0 + oo < O) dw3[((int64_t)hd * O + o0 + oo) * N2 + j] = acc[oo];
+  }
+  if (threadIdx.x < kFc3WOut && o0 + threadIdx.x < O) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += s_pd[b * kFc3WOut + threadIdx.x];
+    db3[(int64_t)hd * O + o0 + threadIdx.x] = s;
+  }
+}
+
+// dmix[b, h] = sum_o dy[b,o] * (b3[h,o] + w3[h,o,:] . a2[h,:,b])
+__global__ void __launch_bounds__(256)
+fc3_bwd_mix_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int64_t ldb,
+                   const float* __restrict__ w3, const float* __restrict__ b3, int H, int O, int N2,
+                   float* __restrict__ dmix) {
+  extern __shared__ float s_col[];                    // [N2]
+  __shared__ float s_part[8];
+  const int hd = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = threadIdx.x; j < N2; j += blockDim.x) s_col[j] = a2[((int64_t)hd * N2 + j) * ldb + b];
+  __syncthreads();
+  float acc = 0.f;
+  for (int o = warp; o < O; o += 8) {
+    const float* w = w3 + ((int64_t)hd * O + o) * N2;
+    float d = 0.f;
+    for (int j = lane; j < N2; j += 32) d = fmaf(w[j], s_col[j], d);
+    d = warp_sum(d);
+    acc += dy[(int64_t)b * O + o] * (d + b3[(int64_t)hd * O + o]);
+  }
+  if (lane == 0) s_part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_part[w];
+    dmix[(int64_t)b * H + hd] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sum_slabs_kernel(const float* __restrict__ parts, int64_t n, int S, int64_t stride,
+                 float* __restrict__ out) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += parts[(int64_t)k * stride + i];
+    out[i] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" int bdp_bn_relu_fwd(const float* h, int64_t F, int64_t B, int64_t ldb,
+                               const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, float* save_mean, float* save_invstd, float eps,
+                               float momentum, int training, float* a, void* stream) {
+  BDP_REQUIRE(h && gamma && beta && a, "bn_relu_fwd: NULL buffer");
+  BDP_REQUIRE(F > 0 && B > 0 && ldb >= B, "bn_relu_fwd: bad sizes F=%lld B=%lld ldb=%lld",
+              (long long)F, (long long)B, (long long)ldb);
+  BDP_REQUIRE(training || (running_mean && running_var), "bn_relu_fwd: eval mode needs running stats");
+  const unsigned blocks = (unsigned)ceil_div64(F, kWarpsPerBlock);
+  bn_relu_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      h, F, (int)B, ldb, gamma, beta, running_mean, running_var, save_mean, save_invstd, eps,
+      momentum, training, a);
+  BDP_CUDA_CHECK_LAUNCH("bn_relu_fwd_kernel");
+  return BDP_OK;
+}
+
+extern "C" int bdp_bn_relu_bwd(const float* da, const float* a, const float* h, const float* gamma,
+                               const float* save_mean, const float* save_invstd, int64_t F,
+                               int64_t B, int64_t ldb, int training, float* dh, float* dgamma,
+                               float* dbeta, void* stream) {
+  BDP_REQUIRE(da && a && h && gamma && save_mean && save_invstd && dh, "bn_relu_bwd: NULL buffer");
+  BDP_REQUIRE(F > 0 && B > 0 && ldb >= B, "bn_relu_bwd: bad sizes");
+  const unsigned blocks = (unsigned)ceil_div64(F, kWarpsPerBlock);
+  bn_relu_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      da, a, h, gamma, save_mean, save_invstd, F, (int)B, ldb, training, dh, dgamma, dbeta);
+  BDP_CUDA_CHECK_LAUNCH("bn_relu_bwd_kernel");
+  return BDP_OK;
+}
+
+extern "C" int bdp_head_fc3_fwd(const float* a2, int64_t ldb, const float* w3, const float* b3,
+                                const float* mix, int64_t B, int H, int O, int N2, float* y,
+                                void* stream) {
+  BDP_REQUIRE(a2 && w3 && b3 && mix && y, "head_fc3_fwd: NULL buffer");
+  BDP_REQUIRE(B > 0 && B <= 65535 && H > 0 && O > 0 && N2 > 0 && N2 <= 12000,
+              "head_fc3_fwd: bad sizes B=%lld H=%d O=%d N2=%d", (long long)B, H, O, N2);
+  dim3 grid((unsigned)((O + kFc3OutPerBlock - 1) / kFc3OutPerBlock), (unsigned)B);
+  fc3_fwd_kernel<<<grid, 256, N2 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      a2, ldb, w3, b3, mix, H, O, N2, y);
+  BDP_CUDA_CHECK_LAUNCH("fc3_fwd_kernel");
+  return BDP_OK;
+}
+
+extern "C" int bdp_head_fc3_bwd(const float* dy, const float* a2, int64_t ldb, const float* w3,
+                                const float* b3, const float* mix, int64_t B, int H, int O, int N2,
+                                float* da2, float* dw3, float* db3, float* dmix, void* stream) {
+  BDP_REQUIRE(dy && a2 && w3 && b3 && mix, "head_fc3_bwd: NULL buffer");
+  BDP_REQUIRE(B > 0 && B <= 65535 && H > 0 && H <= 65535 && O > 0 && O <= 12000 && N2 > 0 &&
+                  N2 <= 12000, "head_fc3_bwd: bad sizes");
+  BDP_REQUIRE((size_t)B * kFc3WOut * 4 <= 48 * 1024, "head_fc3_bwd: batch too large (%lld)", (long long)B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (da2) {
+    BDP_CUDA_CALL(cudaMemsetAsync(da2, 0, (size_t)H * N2 * ldb * sizeof(float), st));
+    fc3_bwd_act_kernel<<<dim3(H, (unsigned)B), 256, O * sizeof(float), st>>>(dy, w3, mix, ldb, H, O,
+                                                                            N2, da2);
+    BDP_CUDA_CHECK_LAUNCH("fc3_bwd_act_kernel");
+  }
+  if (dw3) {
+    BDP_REQUIRE(db3 != nullptr, "head_fc3_bwd: db3 is NULL");
+    fc3_bwd_w_kernel<<<dim3(H, (unsigned)((O + kFc3WOut - 1) / kFc3WOut)), 256,
+                       (size_t)B * kFc3WOut * sizeof(float), st>>>(dy, a2, ldb, mix, (int)B, H, O,
+                                                                   N2, dw3, db3);
+    BDP_CUDA_CHECK_LAUNCH("fc3_bwd_w_kernel");
+  }
+  if (dmix) {
+    fc3_bwd_mix_kernel<<<dim3(H, (unsigned)B), 256, N2 * sizeof(float), st>>>(dy, a2, ldb, w3, b3, H,
+                                                                             O, N2, dmix);
+    BDP_CUDA_CHECK_LAUNCH("fc3_bwd_mix_kernel");
+  }
+  return BDP_OK;
+}
+
+extern "C" int bdp_sum_slabs(const float* parts, int64_t n, int S, int64_t stride, float* out,
+                             void* stream) {
+  BDP_REQUIRE(parts && out && n >= 0 && S >= 1, "sum_slabs: bad arguments");
+  if (n == 0) return BDP_OK;
+  int64_t blocks = ceil_div64(n, 256);
+  const int64_t cap = (int64_t)bdp_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  sum_slabs_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      parts, n, S, stride, out);
+  BDP_CUDA_CHECK_LAUNCH("sum_slabs_kernel");
+  return BDP_OK;
+}
