@@ -208,12 +208,15 @@ int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
  * output  c_layout 0: C[s*c_sstride + g*c_gstride + m*ldc + n]     1: C[... + n*ldc + m]
  * splits > 1 cuts K into bdp_gemm_tf32_splits(K, splits) ranges whose partial products land in
  * consecutive c_sstride slabs (the caller sums them: deterministic, no atomics).
+ * precise 0: plain TF32 (operands truncated to 10 mantissa bits, ~1e-3 relative error);
+ * precise 1: 3xTF32 — operand tiles are split into tf32 hi/lo halves in shared memory and three MMAs
+ *            are accumulated per k-step: fp32-class results (~1e-6) at the same HBM traffic.
  * Serves nn.Linear forward (W x^T), input gradient (W^T dy) and weight gradient (dy a^T).
  */
 int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t a_gstride, const float* B,
                   int b_major, int64_t b_ld, int64_t b_gstride, float* C, int c_layout, int64_t ldc,
                   int64_t c_gstride, int64_t M, int64_t N, int64_t K, int G, int splits,
-                  int64_t c_sstride, void* stream);
+                  int64_t c_sstride, int precise, void* stream);
 int bdp_gemm_tf32_splits(int64_t K, int splits);
 
 /*

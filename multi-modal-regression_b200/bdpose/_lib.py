@@ -41,7 +41,7 @@ SIGNATURES = {
     "bdp_kmeans_lloyd_step": (_int, [_p, _i64, _int, _p, _int, _p, _p, _int, _p, _p, _int, _p]),
     "bdp_kmeans_finalize": (_int, [_p, _int, _int, _int, _p, _p, _p, _p, _p]),
     "bdp_gemm_tf32": (_int, [_p, _int, _i64, _i64, _p, _int, _i64, _i64, _p, _int, _i64, _i64, _i64,
-                             _i64, _i64, _int, _int, _i64, _p]),
+                             _i64, _i64, _int, _int, _i64, _int, _p]),
     "bdp_gemm_tf32_splits": (_int, [_i64, _int]),
     "bdp_bn_relu_fwd": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _f32, _f32, _int, _p,
                                _p]),

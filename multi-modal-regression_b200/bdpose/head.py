@@ -14,10 +14,13 @@ descriptors, BatchNorm backward, fc3 backward).  Every head sees every sample in
 as the reference does (binDeltaModels.py:114-115): BatchNorm couples the batch inside each head, so
 routing samples to their own category's head only would change the statistics.
 
-Precision: the GEMMs run on the tensor cores in TF32 (10-bit mantissa operands, fp32 accumulate)
-straight from the fp32 master weights — the "reduced-precision head GEMM" of the north star, with a
-tighter error than bf16 (tolerance 2e-3 relative in the tests).
+Precision: the GEMMs run on the tensor cores straight from the fp32 master weights.  The default
+"fp32" mode accumulates three TF32 MMAs per k-step on hi/lo operand splits (fp32-class results,
+tolerance 1e-5 of the tensor scale in the tests); "tf32" issues one MMA per k-step — the
+reduced-precision head GEMM of the north star (tolerance 2e-3), tighter than bf16.
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -30,13 +33,27 @@ def _pad4(n):
     return (n + 3) // 4 * 4
 
 
+# Head GEMM precision: "fp32" = 3xTF32 split accumulation (parity mode, default), "tf32" = one TF32
+# MMA per k-step (the reduced-precision head GEMM; ~1e-3 relative, a few ReLU masks may flip).
+PRECISION = os.environ.get("BDPOSE_HEAD_PRECISION", "fp32")
+
+
+def set_precision(mode):
+    global PRECISION
+    if mode not in ("fp32", "tf32"):
+        raise NameError("Unknown head precision passed")
+    PRECISION = mode
+
+
 def gemm_tf32(A, a_major, a_ld, a_gs, B, b_major, b_ld, b_gs, C, c_layout, ldc, c_gs, M, N, K, G=1,
-              splits=1, c_ss=0):
+              splits=1, c_ss=0, precise=None):
     """Raw launch of bdp_gemm_tf32 (see include/bdpose.h for the operand conventions)."""
+    if precise is None:
+        precise = PRECISION == "fp32"
     with torch.cuda.device(A.device):
         st = L.lib().bdp_gemm_tf32(L.ptr(A), a_major, a_ld, a_gs, L.ptr(B), b_major, b_ld, b_gs,
                                    L.ptr(C), c_layout, ldc, c_gs, M, N, K, G, splits, c_ss,
-                                   L.stream_ptr())
+                                   1 if precise else 0, L.stream_ptr())
     L.check(st, "bdp_gemm_tf32")
 
 
@@ -108,74 +125,207 @@ def sum_slabs(parts, n, S, stride, out):
 
 
 # ------------------------------------------------------------------------------------------------
+# stacked parameter storage
+# ------------------------------------------------------------------------------------------------
+_SLOTS = (("w1", "fc1", "weight"), ("g1", "bn1", "weight"), ("be1", "bn1", "bias"),
+          ("w2", "fc2", "weight"), ("g2", "bn2", "weight"), ("be2", "bn2", "bias"))
+_BUFS = (("rm1", "bn1", "running_mean"), ("rv1", "bn1", "running_var"),
+         ("rm2", "bn2", "running_mean"), ("rv2", "bn2", "running_var"),
+         ("nb1", "bn1", "num_batches_tracked"), ("nb2", "bn2", "num_batches_tracked"))
+
+
+class HeadStack:
+    """Keeps the parameters of a list of identical 3-layer MLP modules (fc1, bn1, fc2, bn2, fc3) in
+    STACKED device buffers that the grouped kernels consume, while every module keeps its own
+    nn.Parameter objects (state_dict keys, optimizers and per-index calls are untouched): each
+    Parameter's .data is a view into the stacked buffer.  The views are re-established lazily
+    (`ensure`) whenever something replaced the storage (.cuda(), .to(), deepcopy ...).
+
+    `groups` is a list of module lists; all modules share the fc1/fc2 shapes, modules of one group
+    share the fc3 shape (OneBinDeltaModel: [bin_models, res_models])."""
+
+    def __init__(self, groups):
+        self.groups = [list(g) for g in groups]
+        self.heads = [m for g in self.groups for m in g]
+        self.buf = None
+        self.grad = None
+        self.anchor = None
+
+    # -- storage ---------------------------------------------------------------------------------
+    def _is_current(self):
+        if self.buf is None:
+            return False
+        w1 = self.buf["w1"]
+        for i, m in enumerate(self.heads):
+            p = m.fc1.weight
+            if p.device != w1.device or p.data_ptr() != w1[i].data_ptr():
+                return False
+            if m.bn1.running_mean.data_ptr() != self.buf["rm1"][i].data_ptr():
+                return False
+        off = 0
+        for gi, g in enumerate(self.groups):
+            w3 = self.buf["w3"][gi]
+            for i, m in enumerate(g):
+                if m.fc3.weight.data_ptr() != w3[i].data_ptr():
+                    return False
+        return True
+
+    def ensure(self):
+        if self._is_current():
+            return self.buf
+        heads = self.heads
+        dev = heads[0].fc1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("bdpose heads run on CUDA only (parameters are on %s); call .cuda()" % dev)
+        buf = {}
+        with torch.no_grad():
+            for key, sub, name in _SLOTS:
+                src = [getattr(getattr(m, sub), name) for m in heads]
+                st = torch.stack([p.detach().to(dev, torch.float32) for p in src]).contiguous()
+                for i, p in enumerate(src):
+                    p.data = st[i]
+                buf[key] = st
+            for key, sub, name in _BUFS:
+                src = [getattr(getattr(m, sub), name) for m in heads]
+                st = torch.stack([b.detach().to(dev) for b in src]).contiguous()
+                for i, m in enumerate(heads):
+                    getattr(m, sub)._buffers[name] = st[i]
+                buf[key] = st
+            buf["w3"], buf["b3"] = [], []
+            for g in self.groups:
+                w = torch.stack([m.fc3.weight.detach().to(dev, torch.float32) for m in g]).contiguous()
+                b = torch.stack([m.fc3.bias.detach().to(dev, torch.float32) for m in g]).contiguous()
+                for i, m in enumerate(g):
+                    m.fc3.weight.data = w[i]
+                    m.fc3.bias.data = b[i]
+                buf["w3"].append(w)
+                buf["b3"].append(b)
+        self.buf = buf
+        self.grad = None
+        if self.anchor is None or self.anchor.device != dev:
+            self.anchor = torch.zeros(1, device=dev, requires_grad=True)
+        return buf
+
+    # -- gradients ---------------------------------------------------------------------------------
+    def _param_lists(self):
+        out = {key: [getattr(getattr(m, sub), name) for m in self.heads] for key, sub, name in _SLOTS}
+        for gi, g in enumerate(self.groups):
+            out["w3_%d" % gi] = [m.fc3.weight for m in g]
+            out["b3_%d" % gi] = [m.fc3.bias for m in g]
+        return out
+
+    def deposit(self, grads):
+        """Hand the stacked gradients of one backward call to the per-module Parameters: `.grad`
+        becomes a view into the stacked gradient (no copies); a second backward before the next
+        zero_grad accumulates (two forwards, one backward: learnGeodesicBDModel.py:116-120, 183).
+        Every head gets a dense gradient, zeros included, as in the reference."""
+        plists = self._param_lists()
+        first = self.heads[0].fc1.weight.grad
+        if first is None:
+            for key, plist in plists.items():
+                gk = grads[key]
+                for i, p in enumerate(plist):
+                    p.grad = gk[i]
+            self.grad = grads
+            return
+        mine = self.grad is not None and first.data_ptr() == self.grad["w1"][0].data_ptr() and \
+            self.heads[-1].fc1.weight.grad is not None and \
+            self.heads[-1].fc1.weight.grad.data_ptr() == self.grad["w1"][-1].data_ptr()
+        if mine:
+            for key in plists:
+                self.grad[key].add_(grads[key])
+        else:
+            for key, plist in plists.items():
+                gk = grads[key]
+                for i, p in enumerate(plist):
+                    if p.grad is None:
+                        p.grad = gk[i].clone()
+                    else:
+                        p.grad.add_(gk[i])
+
+
+# ------------------------------------------------------------------------------------------------
 # the stacked 3-layer head: forward + backward
 # ------------------------------------------------------------------------------------------------
 class _HeadFn(torch.autograd.Function):
-    """y = heads(x; stacked params, mix).  Inputs: x [B,N0], mix [B,Hm] (Hm heads per output group),
-    then the stacked parameters.  Two output groups share fc1/fc2 machinery when `split` is given:
-    heads [0, split) produce y1 with fc3 `w3a`, heads [split, H) produce y2 with `w3b` (the bin and
-    res model lists of OneBinDeltaModel, which see the same features)."""
+    """(y_0, y_1, ...) = heads(x, mix) for a HeadStack: one output per fc3 group.  Differentiable
+    inputs are x, mix and the stack's anchor (which only keeps the node alive when neither x nor mix
+    needs a gradient); parameter gradients are deposited on the modules' Parameters directly."""
 
     @staticmethod
-    def forward(ctx, x, mix, w1, g1, be1, w2, g2, be2, w3a, b3a, w3b, b3b, rm1, rv1, rm2, rv2,
-                training):
+    def forward(ctx, x, mix, anchor, stack, training):
+        buf = stack.ensure()
+        w1, w2 = buf["w1"], buf["w2"]
         H, N1, N0 = w1.shape
         N2 = w2.shape[1]
         B = x.shape[0]
         dev = x.device
         ldb = _pad4(B)
-        x = x.contiguous()
-        if x.shape[1] % 4 != 0:
-            raise ValueError("head: feature width must be a multiple of 4 (got %d)" % x.shape[1])
+        if x.shape[1] != N0:
+            raise RuntimeError("head: input has %d features, fc1 expects %d" % (x.shape[1], N0))
+        if N0 % 4 or N1 % 4 or N2 % 4:
+            raise RuntimeError("head: layer widths must be multiples of 4 (got %d, %d, %d)" % (N0, N1, N2))
+        if training and B < 2:
+            raise ValueError("Expected more than 1 value per channel when training, got input size "
+                             "[%d, %d]" % (B, N1))
+        x = x.detach().float().contiguous()
+        mix = mix.detach().float().contiguous()
         # fc1: H1^T [H*N1, ldb] = W1 [H*N1, N0] (K-major) x X [B, N0] (K-major)
         h1 = torch.empty((H * N1, ldb), dtype=torch.float32, device=dev)
         gemm_tf32(w1, 0, N0, 0, x, 0, N0, 0, h1, 0, ldb, 0, H * N1, B, N0)
-        a1, m1, is1 = bn_relu_fwd(h1, B, g1.reshape(-1), be1.reshape(-1),
-                                  None if rm1 is None else rm1.view(-1),
-                                  None if rv1 is None else rv1.view(-1), training)
+        a1, m1, is1 = bn_relu_fwd(h1, B, buf["g1"].view(-1), buf["be1"].view(-1), buf["rm1"].view(-1),
+                                  buf["rv1"].view(-1), training)
         # fc2 (grouped): H2^T_g [N2, ldb] = W2_g [N2, N1] (K-major) x A1^T_g [N1, ldb] (MN-major)
         h2 = torch.empty((H * N2, ldb), dtype=torch.float32, device=dev)
         gemm_tf32(w2, 0, N1, N2 * N1, a1, 1, ldb, N1 * ldb, h2, 0, ldb, N2 * ldb, N2, B, N1, G=H)
-        a2, m2, is2 = bn_relu_fwd(h2, B, g2.reshape(-1), be2.reshape(-1),
-                                  None if rm2 is None else rm2.view(-1),
-                                  None if rv2 is None else rv2.view(-1), training)
-        Ha = w3a.shape[0]
-        mix = mix.contiguous().float()
-        y1 = fc3_fwd(a2[:Ha * N2], w3a, b3a, mix, B)
-        y2 = fc3_fwd(a2[Ha * N2:], w3b, b3b, mix, B) if w3b is not None else None
-        ctx.save_for_backward(x, mix, w1, g1, w2, g2, w3a, b3a, w3b, b3b, h1, a1, m1, is1, h2, a2, m2,
-                              is2, rm1, rv1, rm2, rv2)
+        a2, m2, is2 = bn_relu_fwd(h2, B, buf["g2"].view(-1), buf["be2"].view(-1), buf["rm2"].view(-1),
+                                  buf["rv2"].view(-1), training)
+        if training:
+            buf["nb1"] += 1
+            buf["nb2"] += 1
+        ys, off = [], 0
+        for w3, b3 in zip(buf["w3"], buf["b3"]):
+            Hg = w3.shape[0]
+            if mix.shape[1] != Hg:
+                raise RuntimeError("head: mixing weights have %d columns for %d heads" % (mix.shape[1], Hg))
+            ys.append(fc3_fwd(a2[off * N2:(off + Hg) * N2], w3, b3, mix, B))
+            off += Hg
+        ctx.stack = stack
+        ctx.saved = (x, mix, h1, a1, m1, is1, h2, a2, m2, is2)
         ctx.training = training
-        ctx.dims = (H, N0, N1, N2, B, ldb, Ha)
-        if y2 is None:
-            return y1
-        return y1, y2
+        ctx.dims = (H, N0, N1, N2, B, ldb)
+        return tuple(ys)
 
     @staticmethod
-    def backward(ctx, dy1, dy2=None):
-        (x, mix, w1, g1, w2, g2, w3a, b3a, w3b, b3b, h1, a1, m1, is1, h2, a2, m2, is2, rm1, rv1, rm2,
-         rv2) = ctx.saved_tensors
-        H, N0, N1, N2, B, ldb, Ha = ctx.dims
+    def backward(ctx, *dys):
+        stack = ctx.stack
+        buf = stack.buf
+        x, mix, h1, a1, m1, is1, h2, a2, m2, is2 = ctx.saved
+        H, N0, N1, N2, B, ldb = ctx.dims
         training = ctx.training
         dev = x.device
+        w1, w2 = buf["w1"], buf["w2"]
         want_dmix = ctx.needs_input_grad[1]
         if not training:
-            m1, is1 = rm1.view(-1), torch.rsqrt(rv1.view(-1) + BN_EPS)
-            m2, is2 = rm2.view(-1), torch.rsqrt(rv2.view(-1) + BN_EPS)
-        # fc3 backward
+            m1, is1 = buf["rm1"].view(-1), torch.rsqrt(buf["rv1"].view(-1) + BN_EPS)
+            m2, is2 = buf["rm2"].view(-1), torch.rsqrt(buf["rv2"].view(-1) + BN_EPS)
+        grads = {}
+        # fc3 backward, group by group
         da2 = torch.empty_like(a2)
-        dy1 = dy1.contiguous().float()
-        da2a, dw3a, db3a, dmix = fc3_bwd(dy1, a2[:Ha * N2], w3a, b3a, mix, B, want_dmix)
-        da2[:Ha * N2] = da2a
-        dw3b = db3b = None
-        if w3b is not None:
-            dy2 = dy2.contiguous().float()
-            da2b, dw3b, db3b, dmix_b = fc3_bwd(dy2, a2[Ha * N2:], w3b, b3b, mix, B, want_dmix)
-            da2[Ha * N2:] = da2b
+        dmix, off = None, 0
+        for gi, (w3, b3) in enumerate(zip(buf["w3"], buf["b3"])):
+            Hg, O = w3.shape[0], w3.shape[1]
+            dy = dys[gi]
+            dy = torch.zeros((B, O), device=dev) if dy is None else dy.contiguous().float()
+            sl = slice(off * N2, (off + Hg) * N2)
+            d_a, d_w, d_b, d_m = fc3_bwd(dy, a2[sl], w3, b3, mix, B, want_dmix)
+            da2[sl] = d_a
+            grads["w3_%d" % gi], grads["b3_%d" % gi] = d_w, d_b
             if want_dmix:
-                dmix = dmix + dmix_b
+                dmix = d_m if dmix is None else dmix + d_m
+            off += Hg
         # bn2 backward
-        dh2, dg2, dbe2 = bn_relu_bwd(da2, a2, h2, g2.reshape(-1), m2, is2, B, training)
+        dh2, dg2, dbe2 = bn_relu_bwd(da2, a2, h2, buf["g2"].view(-1), m2, is2, B, training)
         # fc2 wgrad: dW2_g [N2, N1] = dH2^T_g [N2, B] (K-major over the batch) x A1^T_g [N1, B] (K-major)
         dw2 = torch.empty_like(w2)
         gemm_tf32(dh2, 0, ldb, N2 * ldb, a1, 0, ldb, N1 * ldb, dw2, 0, N1, N2 * N1, N2, N1, B, G=H)
@@ -183,27 +333,36 @@ class _HeadFn(torch.autograd.Function):
         da1 = torch.empty_like(a1)
         gemm_tf32(w2, 1, N1, N2 * N1, dh2, 1, ldb, N2 * ldb, da1, 0, ldb, N1 * ldb, N1, B, N2, G=H)
         # bn1 backward
-        dh1, dg1, dbe1 = bn_relu_bwd(da1, a1, h1, g1.reshape(-1), m1, is1, B, training)
+        dh1, dg1, dbe1 = bn_relu_bwd(da1, a1, h1, buf["g1"].view(-1), m1, is1, B, training)
         # fc1 wgrad: dW1 [H*N1, N0] = dH1^T [H*N1, B] (K-major) x X [B, N0] (MN-major: batch rows)
         dw1 = torch.empty_like(w1)
         gemm_tf32(dh1, 0, ldb, 0, x, 1, N0, 0, dw1, 0, N0, 0, H * N1, N0, B)
+        grads.update(w1=dw1, g1=dg1.view(H, N1), be1=dbe1.view(H, N1), w2=dw2, g2=dg2.view(H, N2),
+                     be2=dbe2.view(H, N2))
+        stack.deposit(grads)
         dx = None
         if ctx.needs_input_grad[0]:
             # fc1 dgrad: dX [B, N0]: D[m = feature, n = sample] = sum_k W1[k, m] dH1^T[k, n], split-K
             KK = H * N1
-            splits = gemm_splits(KK, max(1, min(32, (L.lib().bdp_sm_count() * 128) // max(N0, 1))))
+            m_tiles = (N0 + 127) // 128
+            splits = gemm_splits(KK, max(1, min(64, L.lib().bdp_sm_count() // m_tiles)))
             parts = torch.empty((splits, B, N0), dtype=torch.float32, device=dev)
             gemm_tf32(w1, 1, N0, 0, dh1, 1, ldb, 0, parts, 1, N0, 0, N0, B, KK, splits=splits,
                       c_ss=B * N0)
             dx = torch.empty((B, N0), dtype=torch.float32, device=dev)
             sum_slabs(parts, B * N0, splits, B * N0, dx)
-        return (dx, dmix, dw1, dg1.view_as(g1), dbe1.view_as(g1), dw2, dg2.view_as(g2),
-                dbe2.view_as(g2), dw3a, db3a, dw3b, db3b, None, None, None, None, None)
+        return dx, dmix, None, None, None
 
 
-def head_forward(x, mix, params, training):
-    """params: dict with stacked tensors w1,g1,be1,w2,g2,be2,w3a,b3a,(w3b,b3b),rm1,rv1,rm2,rv2."""
-    return _HeadFn.apply(x, mix, params["w1"], params["g1"], params["be1"], params["w2"],
-                         params["g2"], params["be2"], params["w3a"], params["b3a"],
-                         params.get("w3b"), params.get("b3b"), params["rm1"], params["rv1"],
-                         params["rm2"], params["rv2"], training)
+def run_heads(stack, x, mix, training):
+    """All heads of `stack` on features x [B, N0] with mixing weights mix [B, heads per group].
+    Returns one [B, O_g] tensor per fc3 group."""
+    stack.ensure()
+    return _HeadFn.apply(x, mix, stack.anchor, stack, training)
+
+
+def onehot(label, num_classes):
+    """[B,1] (or [B]) int64 labels -> [B, C] float one-hot built on the device (the reference builds
+    it on the CPU and copies it back every forward: binDeltaModels.py:116-117)."""
+    label = label.reshape(-1, 1).long()
+    return torch.zeros(label.shape[0], num_classes, device=label.device).scatter_(1, label, 1.0)

@@ -1,0 +1,215 @@
+# -*- coding: utf-8 -*-
+"""Drop-in for the reference's binDeltaModels module (binDeltaModels.py:1-178) on the B200 head
+kernels.
+
+* `bin_3layer` / `res_3layer` keep the reference's layer names (fc1, bn1, fc2, bn2, fc3), so
+  state_dict keys, optimizers and `model.bin_models[i](x)` calls are unchanged; a single module runs
+  as a one-head stack through the same tcgen05 GEMM / BatchNorm / fc3 kernels.
+* `OneBinDeltaModel.forward(x, label)` runs all 2*C heads of the model fused: one flattened fc1 GEMM,
+  one grouped fc2 GEMM, BatchNorm on feature-major activations, label-selected fc3 — with the one-hot
+  built on the device (the reference round-trips it through the CPU every forward,
+  binDeltaModels.py:116-117).  `forward_mixed(x, mix)` is the soft-mixing form the joint
+  category+pose scripts build by hand (learnJointCatPoseModel_weighted.py:107-115).
+* The 1- and 2-layer blocks and the one-delta-per-bin models keep the reference's
+  structure on stock torch layers.
+"""
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from bdpose import head as _head
+
+
+def _feature_model(feature_network):
+    import featureModels
+    if feature_network == 'resnet':
+        return featureModels.resnet_model('resnet50', 'layer4').cuda()
+    if feature_network == 'vgg':
+        return featureModels.vgg_model('vgg13', 'fc6').cuda()
+    return None    # the reference silently leaves feature_model undefined for other strings
+
+
+# ---- building blocks ----------------------------------------------------------------------------------
+class bin_1layer(nn.Module):
+    """binDeltaModels.py:16-23"""
+
+    def __init__(self, N0, num_clusters):
+        super().__init__()
+        self.fc = nn.Linear(N0, num_clusters)
+
+    def forward(self, x):
+        return self.fc(x)
+
+
+class res_1layer(nn.Module):
+    """binDeltaModels.py:26-33"""
+
+    def __init__(self, N0, ndim):
+        super().__init__()
+        self.fc = nn.Linear(N0, ndim)
+
+    def forward(self, x):
+        return self.fc(x)
+
+
+class _mlp2(nn.Module):
+    """fc2(relu(bn1(fc1 x))) — bin_2layer / res_2layer, binDeltaModels.py:36-59"""
+
+    def __init__(self, N0, N1, Nout):
+        super().__init__()
+        self.fc1 = nn.Linear(N0, N1, bias=False)
+        self.bn1 = nn.BatchNorm1d(N1)
+        self.fc2 = nn.Linear(N1, Nout)
+
+    def forward(self, x):
+        return self.fc2(F.relu(self.bn1(self.fc1(x))))
+
+
+class bin_2layer(_mlp2):
+    def __init__(self, N0, N1, num_clusters):
+        super().__init__(N0, N1, num_clusters)
+
+
+class res_2layer(_mlp2):
+    def __init__(self, N0, N1, ndim):
+        super().__init__(N0, N1, ndim)
+
+
+class _mlp3(nn.Module):
+    """fc3(relu(bn2(fc2(relu(bn1(fc1 x)))))) with fc1/fc2 bias-free — binDeltaModels.py:62-91."""
+
+    def __init__(self, N0, N1, N2, Nout):
+        super().__init__()
+        self.fc1 = nn.Linear(N0, N1, bias=False)
+        self.bn1 = nn.BatchNorm1d(N1)
+        self.fc2 = nn.Linear(N1, N2, bias=False)
+        self.bn2 = nn.BatchNorm1d(N2)
+        self.fc3 = nn.Linear(N2, Nout)
+        object.__setattr__(self, '_solo', None)
+
+    def forward(self, x):
+        # a single head = a stack of one, mixing weight 1 (used by scripts that call
+        # `self.bin_models[i](x)` themselves: learnJointCatPoseModel_weighted.py:112-113)
+        solo = self._solo
+        if solo is None or solo.heads[0] is not self:
+            solo = _head.HeadStack([[self]])
+            object.__setattr__(self, '_solo', solo)
+        ones = torch.ones(x.shape[0], 1, device=x.device)
+        return _head.run_heads(solo, x, ones, self.training)[0]
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == '_solo':
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        object.__setattr__(new, '_solo', None)
+        return new
+
+
+class bin_3layer(_mlp3):
+    def __init__(self, N0, N1, N2, num_clusters):
+        super().__init__(N0, N1, N2, num_clusters)
+
+
+class res_3layer(_mlp3):
+    def __init__(self, N0, N1, N2, ndim):
+        super().__init__(N0, N1, N2, ndim)
+
+
+# ---- models ---------------------------------------------------------------------------------------------
+class OneBinDeltaModel(nn.Module):
+    """binDeltaModels.py:99-121.  forward(x, label) -> [y1 [B, num_clusters], y2 [B, ndim]]."""
+
+    def __init__(self, feature_network, num_classes, num_clusters, N0, N1, N2, ndim):
+        super().__init__()
+        self.num_classes = num_classes
+        self.num_clusters = num_clusters
+        self.ndim = ndim
+        fm = _feature_model(feature_network)
+        if fm is not None:
+            self.feature_model = fm
+        self.bin_models = nn.ModuleList([bin_3layer(N0, N1, N2, num_clusters) for i in range(self.num_classes)]).cuda()
+        self.res_models = nn.ModuleList([res_3layer(N0, N1, N2, ndim) for i in range(self.num_classes)]).cuda()
+        object.__setattr__(self, '_stack', None)
+
+    def _heads(self):
+        st = self.__dict__.get('_stack')
+        bins, ress = list(self.bin_models), list(self.res_models)
+        if st is None or len(st.heads) != len(bins) + len(ress) or \
+                any(a is not b for a, b in zip(st.heads, bins + ress)):
+            st = _head.HeadStack([bins, ress])
+            object.__setattr__(self, '_stack', st)
+        return st
+
+    def forward_features(self, feat, label=None, mix=None):
+        """Heads only, on precomputed features [B, N0]: label [B,1] int64 or mix [B, C] weights."""
+        if mix is None:
+            mix = _head.onehot(label, self.num_classes)
+        y1, y2 = _head.run_heads(self._heads(), feat, mix, self.training)
+        return [y1, y2]
+
+    def forward_mixed(self, x, mix):
+        """Soft category mixing (learnJointCatPoseModel_weighted.py:107-115) with gradient to mix."""
+        return self.forward_features(self.feature_model(x), mix=mix)
+
+    def forward(self, x, label):
+        x = self.feature_model(x)
+        return self.forward_features(x, label=label)
+
+
+def _onehot_cpu_like(idx, n):
+    return torch.zeros(idx.size(0), n, device=idx.device).scatter_(1, idx, 1.0)
+
+
+class OneDeltaPerBinModel(nn.Module):
+    """binDeltaModels.py:124-151: C bin heads (fused stack) + C*K res_2layer heads (stock torch layers,
+    SURVEY §8(f)-1), delta selected by class then by argmax bin."""
+
+    def __init__(self, feature_network, num_classes, num_clusters, N0, N1, N2, N3, ndim):
+        super().__init__()
+        self.num_classes = num_classes
+        self.num_clusters = num_clusters
+        self.ndim = ndim
+        fm = _feature_model(feature_network)
+        if fm is not None:
+            self.feature_model = fm
+        self.bin_models = nn.ModuleList([bin_3layer(N0, N1, N2, num_clusters) for i in range(self.num_classes)]).cuda()
+        self.res_models = nn.ModuleList([res_2layer(N0, N3, ndim) for i in range(self.num_classes * self.num_clusters)]).cuda()
+        object.__setattr__(self, '_stack', None)
+
+    def _bin_scores(self, x, mix):
+        st = self.__dict__.get('_stack')
+        bins = list(self.bin_models)
+        if st is None or any(a is not b for a, b in zip(st.heads, bins)) or len(st.heads) != len(bins):
+            st = _head.HeadStack([bins])
+            object.__setattr__(self, '_stack', st)
+        return _head.run_heads(st, x, mix, self.training)[0]
+
+    def _all_deltas(self, x, class_mix):
+        y2 = torch.stack([m(x) for m in self.res_models])
+        y2 = y2.view(self.num_classes, self.num_clusters, -1, self.ndim).permute(1, 2, 3, 0)
+        return torch.squeeze(torch.matmul(y2, class_mix.unsqueeze(2)), 3)          # [K, B, ndim]
+
+    def forward(self, x, class_label):
+        x = self.feature_model(x)
+        class_mix = _onehot_cpu_like(class_label, self.num_classes)
+        y1 = self._bin_scores(x, class_mix)
+        y2 = self._all_deltas(x, class_mix)
+        pose_label = torch.argmax(y1, dim=1, keepdim=True)
+        pose_mix = _onehot_cpu_like(pose_label, self.num_clusters).unsqueeze(2)
+        y2 = torch.squeeze(torch.bmm(y2.permute(1, 2, 0), pose_mix), 2)
+        return [y1, y2]
+
+
+class ProbabilisticOneDeltaPerBinModel(OneDeltaPerBinModel):
+    """binDeltaModels.py:154-178: as above but returns all K deltas, [B, K, ndim]."""
+
+    def forward(self, x, class_label):
+        x = self.feature_model(x)
+        class_mix = _onehot_cpu_like(class_label, self.num_classes)
+        y1 = self._bin_scores(x, class_mix)
+        y2 = self._all_deltas(x, class_mix).permute(1, 0, 2)
+        return [y1, y2]

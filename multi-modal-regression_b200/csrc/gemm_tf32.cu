@@ -10,10 +10,24 @@
 //   rows of D (m)  -> the 128 TMEM lanes  (always the "feature" side: swap-AB, batch is the N side)
 //   cols of D (n)  -> TMEM columns, BN <= 256 per tile
 //
-// Warp roles (256 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer
-// (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> global).  Three
-// mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
-// accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1).
+// Warp roles (384 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> global),
+// warps 8-11 = operand splitters (precise mode only).  mbarrier pipelines: smem full/empty
+// (TMA <-> MMA), split-ready (splitters -> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator
+// stages so the epilogue of tile i overlaps the mainloop of tile i+1).
+//
+// Precision.  precise = 0: one TF32 MMA per k-step (operands truncated to 10 mantissa bits by the
+// tensor core, ~1e-3 relative).  precise = 1 ("3xTF32"): every fp32 operand tile is split in shared
+// memory into hi = tf32(x) and lo = tf32(x - hi), and D += Ahi*Bhi + Ahi*Blo + Alo*Bhi; the dropped
+// terms are ~2^-20 relative, i.e. fp32-class results (needed for parity: at 1e-3 a few ReLU masks
+// flip and gradients drift by percents).  The weights still stream from HBM exactly once.
+//
+// Accumulator chains.  The tensor core adds each K=8 partial sum into the fp32 accumulator with
+// truncation, so one long chain drifts by ~(#k-steps) * ulp(acc)/2 (measured: 1.6e-5 of the result
+// scale at K=2048).  When the tile is narrow the spare TMEM columns hold `chains` independent
+// accumulators per tile: k-steps go round-robin over `chains_hi` of them, the small hi*lo cross terms
+// go to the remaining ones (where ulp is ~2^-11 smaller), and the epilogue adds the chains in
+// registers with round-to-nearest.  BN = 32 -> 8 chains, 64 -> 4, 128 -> 2, 256 -> 1.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -23,7 +37,8 @@ namespace {
 constexpr int kBM = 128;            // tile rows = TMEM lanes
 constexpr int kBK = 32;             // fp32 per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;           // K of one tcgen05.mma.kind::tf32
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
+constexpr int kSplitThreads = 128;   // warps 8-11
 constexpr int kABytes = kBM * kBK * 4;     // 16 KB per stage
 constexpr int kMaxStages = 10;
 
@@ -36,6 +51,8 @@ struct GemmParams {
   float* C;
   long long ldc, c_gstride, c_sstride;
   int c_nm;                         // 0: C[m*ldc + n], 1: C[n*ldc + m]
+  int precise;                      // 1: 3xTF32 split-operand accumulation
+  int chains, chains_hi;            // TMEM accumulator chains per tile (see below)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -134,20 +151,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // 1024-byte aligned operand ring (swizzle-128B atoms are 1 KB), barriers after it
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = static_cast<uint32_t>(P.BN) * kBK * 4;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t tile_bytes = kABytes + b_bytes;                 // what TMA delivers per stage
+  const uint32_t stage_bytes = P.precise ? 2u * tile_bytes : tile_bytes;   // + the lo copies
   const uint32_t bar_base = base + P.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto split_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxStages + 2 + s); };
   __shared__ uint32_t s_tmem_base;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tmem_cols = (2 * P.BN <= 32) ? 32 : (2 * P.BN <= 64) ? 64 : (2 * P.BN <= 128) ? 128
-                        : (2 * P.BN <= 256) ? 256 : 512;
+  const int need_cols = 2 * P.chains * P.BN;
+  const int tmem_cols = (need_cols <= 32) ? 32 : (need_cols <= 64) ? 64 : (need_cols <= 128) ? 128
+                        : (need_cols <= 256) ? 256 : 512;
+  const int chains_x = P.chains - P.chains_hi;       // chains reserved for the cross terms
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), kSplitThreads / 32);
+    }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -180,7 +205,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = base + stage * stage_bytes;
         const uint32_t sb = sa + kABytes;
-        mbar_expect_tx(full_bar(stage), stage_bytes);
+        mbar_expect_tx(full_bar(stage), tile_bytes);
         const int k0 = kb * kBK;
         if (!P.a_mn) {
           tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, g * P.a_g);
@@ -219,23 +244,80 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * P.BN);
+      const uint32_t tmem_t = tmem_base + static_cast<uint32_t>(as * P.chains * P.BN);
+      uint32_t started = 0;                            // chains that already hold a partial sum
+      int step = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait(P.precise ? split_bar(stage) : full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + stage * stage_bytes;
         const uint32_t sb = sa + kABytes;
+        const uint32_t a_sbo = P.a_mn ? 512u : 1024u, a_lt = P.a_mn ? 1u : 2u;
+        const uint32_t b_sbo = P.b_mn ? 512u : 1024u, b_lt = P.b_mn ? 1u : 2u;
 #pragma unroll
         for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t ad = umma_desc(sa + k * a_kstep, a_lbo, P.a_mn ? 512u : 1024u, P.a_mn ? 1u : 2u);
-          const uint64_t bd = umma_desc(sb + k * b_kstep, b_lbo, P.b_mn ? 512u : 1024u, P.b_mn ? 1u : 2u);
-          umma_tf32(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          const uint64_t ad = umma_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t bd = umma_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
+          const int ch = step % P.chains_hi;
+          const uint32_t d_hi = tmem_t + static_cast<uint32_t>(ch * P.BN);
+          if (P.precise) {
+            const int cx = chains_x > 0 ? P.chains_hi + step % chains_x : ch;
+            const uint32_t d_x = tmem_t + static_cast<uint32_t>(cx * P.BN);
+            const uint64_t adl = umma_desc(sa + tile_bytes + k * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t bdl = umma_desc(sb + tile_bytes + k * b_kstep, b_lbo, b_sbo, b_lt);
+            umma_tf32(d_x, adl, bd, idesc, (started >> cx) & 1u);
+            started |= 1u << cx;
+            umma_tf32(d_x, ad, bdl, idesc, 1u);
+            umma_tf32(d_hi, ad, bd, idesc, (started >> ch) & 1u);
+            started |= 1u << ch;
+          } else {
+            umma_tf32(d_hi, ad, bd, idesc, (started >> ch) & 1u);
+            started |= 1u << ch;
+          }
+          ++step;
         }
         umma_commit(empty_bar(stage));                 // frees the smem slot when the MMAs retire
         if (kb == kb1 - 1) umma_commit(tfull_bar(as)); // accumulator complete -> epilogue
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 8) {
+    // ===== operand splitters (precise mode): x -> hi = tf32(x) in place, lo = tf32(x - hi) =====
+    if (P.precise) {
+      const int tid = threadIdx.x - 8 * 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nvec = static_cast<int>(tile_bytes / 16);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int sp = (t % tiles_per_group) % P.splits;
+        const int kb0 = sp * P.kb_per_split;
+        const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          const uint32_t sa = base + stage * stage_bytes;
+          for (int i = tid; i < nvec; i += kSplitThreads) {
+            uint32_t x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sa + 16u * i));
+            const uint32_t h0 = x0 & 0xFFFFE000u, h1 = x1 & 0xFFFFE000u, h2 = x2 & 0xFFFFE000u,
+                           h3 = x3 & 0xFFFFE000u;
+            const uint32_t l0 = __float_as_uint(__uint_as_float(x0) - __uint_as_float(h0)) & 0xFFFFE000u;
+            const uint32_t l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1)) & 0xFFFFE000u;
+            const uint32_t l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2)) & 0xFFFFE000u;
+            const uint32_t l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3)) & 0xFFFFE000u;
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 16u * i), "r"(h0),
+                         "r"(h1), "r"(h2), "r"(h3) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + tile_bytes + 16u * i),
+                         "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+          }
+          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(split_bar(stage));
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global =====
@@ -254,11 +336,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       float* Cg = P.C + sp * P.c_sstride + g * P.c_gstride;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                            static_cast<uint32_t>(as * P.BN);
+                            static_cast<uint32_t>(as * P.chains * P.BN);
+      // chains that received at least one k-step of this tile
+      const int nsteps = (min(P.kb_total, sp * P.kb_per_split + P.kb_per_split) - sp * P.kb_per_split) *
+                         (kBK / kUmmaK);
+      const int used_hi = min(P.chains_hi, nsteps);
+      const int used_x = (P.precise && chains_x > 0) ? min(chains_x, nsteps) : 0;
       for (int c = 0; c < P.BN / 32; ++c) {
         if (n0 + c * 32 >= P.N) break;                 // warp-uniform
         uint32_t v[32];
         tmem_ld32(trow + c * 32, v);
+        for (int chn = 1; chn < used_hi + used_x; ++chn) {
+          const int cc = chn < used_hi ? chn : P.chains_hi + (chn - used_hi);
+          uint32_t w[32];
+          tmem_ld32(trow + cc * P.BN + c * 32, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+        }
         const int nb = n0 + c * 32;
         if (!P.c_nm) {
           if (m < P.M) {
@@ -348,7 +442,8 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t dim0, uint64_t dim1, u
 extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t a_gstride,
                              const float* B, int b_major, int64_t b_ld, int64_t b_gstride, float* C,
                              int c_layout, int64_t ldc, int64_t c_gstride, int64_t M, int64_t N,
-                             int64_t K, int G, int splits, int64_t c_sstride, void* stream) {
+                             int64_t K, int G, int splits, int64_t c_sstride, int precise,
+                             void* stream) {
   BDP_REQUIRE(A && B && C, "gemm_tf32: NULL operand");
   BDP_REQUIRE(M > 0 && N > 0 && K > 0 && G > 0, "gemm_tf32: empty problem M=%lld N=%lld K=%lld G=%d",
               (long long)M, (long long)N, (long long)K, G);
@@ -378,12 +473,17 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   P.b_g = (b_gstride != 0 || G == 1) ? 1 : 0;
   P.C = C; P.ldc = ldc; P.c_gstride = c_gstride; P.c_sstride = c_sstride; P.c_nm = c_layout;
 
-  const size_t stage_bytes = (size_t)kABytes + (size_t)bn * kBK * 4;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  P.precise = precise ? 1 : 0;
+  P.chains = 256 / bn;                               // 2 accumulator stages * chains * BN <= 512 columns
+  if (P.chains < 1) P.chains = 1;
+  if (P.chains > 8) P.chains = 8;
+  P.chains_hi = (precise && P.chains >= 2) ? P.chains - (P.chains >= 4 ? P.chains / 4 : 1) : P.chains;
+  const size_t stage_bytes = ((size_t)kABytes + (size_t)bn * kBK * 4) * (precise ? 2 : 1);
+  int stages = (int)((208 * 1024) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   P.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024 + 8 * (2 * kMaxStages + 4);
+  const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * kMaxStages + 4);
 
   CUtensorMap tmA, tmB;
   const uint64_t ga = P.a_g ? (uint64_t)G : 1, gb = P.b_g ? (uint64_t)G : 1;

@@ -337,7 +337,7 @@ class OneBinDeltaHeads(nn.Module):
         y2 = torch.stack([m(x) for m in self.res_models]).permute(1, 2, 0)
         if mix is None:
             mix = torch.zeros(label.size(0), self.num_classes).scatter_(1, label, 1.0)
-        mix = mix.unsqueeze(2)
+        mix = mix.to(y1.dtype).unsqueeze(2)
         return [torch.squeeze(torch.bmm(y1, mix), 2), torch.squeeze(torch.bmm(y2, mix), 2)]
 
 

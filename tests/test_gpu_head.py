@@ -1,6 +1,11 @@
-"""The bin-delta head kernels (tcgen05 TF32 GEMM, BatchNorm, fc3 mixing) against torch / the oracle.
-Tolerance for anything that passes through the TF32 tensor-core GEMM: 2e-3 relative to the tensor's
-scale (north_star: "2e-3 relative (bf16 head GEMM)"; TF32 keeps 3 more mantissa bits than bf16).
+"""The bin-delta head kernels (tcgen05 GEMM, BatchNorm, fc3 mixing) against torch / the oracle.
+Tolerances, relative to the tensor's scale (max |reference|):
+  * "fp32" head precision (3xTF32 split accumulation, the default): 1e-5 for a single GEMM and for
+    forward outputs of the whole head; gradients of the whole head 1e-4 (they pass through five GEMMs
+    and two BatchNorm backward reductions; the fp32 reference itself carries ~1e-5 of reordering noise
+    there);
+  * "tf32" head precision (one TF32 MMA per k-step): 2e-3 on single GEMMs and forward outputs
+    (north_star: "2e-3 relative (bf16 head GEMM)"; TF32 keeps 3 more mantissa bits than bf16).
 CUDA-core pieces (BatchNorm, fc3): 1e-5."""
 import numpy as np
 import pytest
@@ -10,14 +15,44 @@ import bdpose_oracle as O
 
 pytestmark = pytest.mark.gpu
 TF32_TOL = 2e-3
+FP32_TOL = 1e-5
+GRAD_TOL = 1e-4
 
 
 def scale_close(a, b, tol, msg=""):
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     err = float((a - b).abs().max())
-    ref = float(b.abs().max()) + 1e-30
+    ref = float(b.abs().max())
+    if ref == 0.0:
+        assert err == 0.0, "%s: reference is exactly zero, got max |x| %.3e" % (msg, err)
+        return
+    print("[rel-err] %-28s %.2e (tol %.1e)" % (msg, err / ref, tol))
     assert err <= tol * ref, "%s: max err %.3e vs scale %.3e (rel %.2e > %.1e)" % (msg, err, ref, err / ref, tol)
+
+
+def flip_close(a, b, msg=""):
+    """Full-size gradients pass through two ReLUs.  Wherever a pre-activation is within fp32 rounding
+    of zero (|h| < ~1e-6 * scale: about 0.5 elements per forward at 24000 x 32 + 12000 x 32
+    activations) the ReLU mask of ANY fp32 evaluation — the reference's own included, measured in
+    scratch/diag_head.py: reference-fp32 vs float64 max 2.5e-4 in one of three trials — can differ
+    from the exact one.  One flipped element moves its sample's row of dX by ~1/sqrt(24000) and,
+    through the BatchNorm batch sums, everything else by ~1/B of that; the flipped unit's own row of
+    dW changes by tens of percent.  So full-size gradients are checked robustly: median error <= 1e-4
+    of the tensor scale and at most 5 % of the elements off by more than 1e-3 of the scale (a flip-free
+    run sits at 1e-7 median / 1e-6 max; the golden-vector test, which has no near-zero
+    pre-activations, checks every gradient element at 1e-4)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    err = (a - b).abs()
+    ref = float(b.abs().max())
+    if ref == 0.0:
+        assert float(err.max()) == 0.0, msg
+        return
+    med, mx = float(err.median()) / ref, float(err.max()) / ref
+    frac = float((err > 1e-3 * ref).double().mean())
+    print("[rel-err] %-28s median %.2e max %.2e frac>1e-3 %.4f" % (msg, med, mx, frac))
+    assert med <= 1e-4 and frac <= 0.05, "%s: median %.2e max %.2e frac %.4f" % (msg, med, mx, frac)
 
 
 def _operand(rows, K, G, major, dev, gen):
@@ -40,7 +75,8 @@ def _operand(rows, K, G, major, dev, gen):
     (200, 96, 100, 2, 0, 0, 1, 1),
     (132, 260, 36, 1, 1, 0, 0, 1),
 ])
-def test_gemm_tf32(cuda, M, N, K, G, am, bm, cl, splits):
+@pytest.mark.parametrize("precise", [True, False])
+def test_gemm_tf32(cuda, M, N, K, G, am, bm, cl, splits, precise):
     from bdpose import head
     gen = torch.Generator(device=cuda).manual_seed(M + N + K)
     A, Al = _operand(M, K, G, am, cuda, gen)
@@ -52,13 +88,13 @@ def test_gemm_tf32(cuda, M, N, K, G, am, bm, cl, splits):
     a_ld = K if am == 0 else M
     b_ld = K if bm == 0 else N
     head.gemm_tf32(A, am, a_ld, M * K, B, bm, b_ld, N * K, C, cl, N if cl == 0 else M, M * N, M, N, K,
-                   G=G, splits=splits, c_ss=G * M * N)
+                   G=G, splits=splits, c_ss=G * M * N, precise=precise)
     out = C.sum(0)
     if cl == 1:
         out = out.transpose(1, 2)
     assert not torch.isnan(out).any()
-    # TF32: error ~ 2^-11 * sqrt(K) * |a||b|; compare against the result scale
-    scale_close(out, ref, TF32_TOL, "gemm")
+    # TF32: error ~ 2^-11 * sqrt(K) * |a||b|; 3xTF32: ~2^-20; compare against the result scale
+    scale_close(out, ref, FP32_TOL if precise else TF32_TOL, "gemm")
 
 
 def test_gemm_shared_operand_and_padding(cuda):
@@ -71,7 +107,7 @@ def test_gemm_shared_operand_and_padding(cuda):
     C = torch.zeros(G, M, ldc, device=cuda)
     head.gemm_tf32(A, 0, K, M * K, B, 0, K, 0, C, 0, ldc, M * ldc, M, N, K, G=G)
     ref = torch.einsum("gmk,nk->gmn", A.double(), B.double())
-    scale_close(C[:, :, :N], ref, TF32_TOL, "shared-B")
+    scale_close(C[:, :, :N], ref, FP32_TOL, "shared-B")
     assert float(C[:, :, N:].abs().max()) == 0.0
 
 
@@ -132,3 +168,189 @@ def test_fc3_mix_vs_torch(cuda, soft):
     torch.testing.assert_close(dw3, w3.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(db3, b3.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(dmix, mix.grad, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the model classes against the reference's golden vectors and the oracle modules
+# ---------------------------------------------------------------------------------------------------
+def _load_sd(model, g, prefix="sd0/"):
+    sd = {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+    model.load_state_dict(sd)
+
+
+def test_one_bin_delta_model_golden(cuda, golden):
+    """binDeltaModels.OneBinDeltaModel (identity trunk) vs the reference run stored in heads.npz:
+    train-mode outputs, every parameter gradient, dX, running statistics; eval-mode outputs."""
+    import binDeltaModels as M
+    g = golden("heads")
+    C, K, N0, N1, N2, nd, B = [int(v) for v in g["dims"]]
+    model = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+    model.feature_model = torch.nn.Identity()
+    assert sorted(model.state_dict().keys()) == sorted(k[4:] for k in g.files if k.startswith("sd0/"))
+    _load_sd(model, g)
+    model.cuda().train()
+    x = torch.from_numpy(g["x"]).to(cuda).requires_grad_(True)
+    label = torch.from_numpy(g["label"]).to(cuda)
+    y1, y2 = model(x, label)
+    scale_close(y1, torch.from_numpy(g["train_y1"]), FP32_TOL, "y1")
+    scale_close(y2, torch.from_numpy(g["train_y2"]), FP32_TOL, "y2")
+    ((y1 * torch.from_numpy(g["w1"]).to(cuda)).sum() + (y2 * torch.from_numpy(g["w2"]).to(cuda)).sum()).backward()
+    scale_close(x.grad, torch.from_numpy(g["train_gx"]), GRAD_TOL, "dx")
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k            # dense (possibly zero) gradients, never None
+        ref = torch.from_numpy(g["train_grad/" + k])
+        if float(ref.abs().max()) == 0:
+            assert float(p.grad.abs().max()) == 0, k
+        else:
+            scale_close(p.grad, ref, GRAD_TOL, k)
+    sd = model.state_dict()
+    for k in g.files:
+        if k.startswith("train_sd/"):
+            name = k[len("train_sd/"):]
+            if "num_batches" in name:
+                assert int(sd[name]) == int(g[k]), name
+            else:
+                scale_close(sd[name], torch.from_numpy(g[k]), FP32_TOL, name)
+    model.eval()
+    with torch.no_grad():
+        e1, e2 = model(x.detach(), label)
+    scale_close(e1, torch.from_numpy(g["eval_y1"]), FP32_TOL, "eval y1")
+    scale_close(e2, torch.from_numpy(g["eval_y2"]), FP32_TOL, "eval y2")
+
+
+def test_pascal_head_vs_oracle_full_size(cuda):
+    """BASELINE config 1: C=12, K=200, 2048-1000-500, B=32 — fused model vs the oracle's module-by-
+    module evaluation, with the two-forwards-one-backward pattern of the training scripts.
+    Everything is checked twice: against the oracle in float64 (the exact value of the reference's
+    formula) and against the oracle in float32 (= the reference as it runs): forward outputs to 1e-5
+    of the tensor scale, gradients with flip_close (isolated ReLU-mask flips, see there)."""
+    import copy
+    import binDeltaModels as M
+    torch.manual_seed(0)
+    C, K, N0, N1, N2, nd, B = 12, 200, 2048, 1000, 500, 3, 32
+    ref = O.OneBinDeltaHeads(C, K, N0, N1, N2, nd)
+    ref64 = copy.deepcopy(ref).double()
+    model = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+    model.feature_model = torch.nn.Identity()
+    model.load_state_dict(ref.state_dict())
+    model.cuda().train()
+    ref.train(); ref64.train()
+    xa, xb = torch.randn(B, N0), torch.randn(B, N0)
+    la, lb = torch.randint(0, C, (B, 1)), torch.randint(0, C, (B, 1))
+    wa, wb = torch.randn(2 * B, K), torch.randn(2 * B, nd)
+
+    def step(m, dev, dt):
+        xs = [t.detach().clone().to(dev, dt).requires_grad_(True) for t in (xa, xb)]
+        call = (lambda x, l: m(x, l)) if dev != "cpu" else (lambda x, l: m(x, label=l))
+        oa = call(xs[0], la.to(dev))
+        ob = call(xs[1], lb.to(dev))
+        y1 = torch.cat([oa[0], ob[0]]); y2 = torch.cat([oa[1], ob[1]])
+        ((y1 * wa.to(dev, dt)).sum() + (y2 * wb.to(dev, dt)).sum()).backward()
+        return y1, y2, xs
+    r1, r2, rx = step(ref, "cpu", torch.float32)
+    d1, d2, dx = step(ref64, "cpu", torch.float64)
+    y1, y2, gx = step(model, cuda, torch.float32)
+    scale_close(y1, d1, FP32_TOL, "y1 vs f64"); scale_close(y2, d2, FP32_TOL, "y2 vs f64")
+    scale_close(y1, r1, FP32_TOL, "y1 vs f32"); scale_close(y2, r2, FP32_TOL, "y2 vs f32")
+    for i, nm in enumerate(("dxa", "dxb")):
+        flip_close(gx[i].grad, dx[i].grad, nm + " vs f64")
+        flip_close(gx[i].grad, rx[i].grad, nm + " vs f32")
+    p32, p64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        flip_close(p.grad, p64[k].grad, k + " vs f64")
+        flip_close(p.grad, p32[k].grad, k + " vs f32")
+    rsd = ref.state_dict()
+    for k, v in model.state_dict().items():
+        if "running" in k:
+            scale_close(v, rsd[k], FP32_TOL, k)
+        elif "num_batches" in k:
+            assert int(v) == int(rsd[k]) == 2
+    # the per-index path (scripts that loop bin_models[i](x) themselves) agrees with the fused path
+    model.eval(); ref.eval()
+    with torch.no_grad():
+        solo = model.bin_models[3](xa.to(cuda))
+        scale_close(solo, ref.bin_models[3](xa), FP32_TOL, "solo head")
+        mix = torch.softmax(torch.randn(B, C), 1)
+        f1, f2 = model.forward_features(xa.to(cuda), mix=mix.to(cuda))
+        q1, q2 = ref(xa, mix=mix)
+        scale_close(f1, q1, FP32_TOL, "soft y1"); scale_close(f2, q2, FP32_TOL, "soft y2")
+
+
+def test_soft_mix_gradient(cuda):
+    """Joint category+pose model: gradient flows into the mixing weights
+    (learnJointCatPoseModel_weighted.py:110-115)."""
+    import binDeltaModels as M
+    torch.manual_seed(3)
+    C, K, N0, N1, N2, nd, B = 4, 24, 64, 48, 32, 3, 12
+    ref = O.OneBinDeltaHeads(C, K, N0, N1, N2, nd)
+    model = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+    model.feature_model = torch.nn.Identity()
+    model.load_state_dict(ref.state_dict())
+    model.cuda().train(); ref.train()
+    x = torch.randn(B, N0); logits = torch.randn(B, C)
+    w1, w2 = torch.randn(B, K), torch.randn(B, nd)
+    outs = []
+    for m, dev in ((ref, "cpu"), (model, cuda)):
+        lg = logits.clone().to(dev).requires_grad_(True)
+        xx = x.clone().to(dev).requires_grad_(True)
+        mix = torch.softmax(lg, 1)
+        y1, y2 = m(xx, mix=mix) if dev == "cpu" else m.forward_features(xx, mix=mix)
+        ((y1 * w1.to(dev)).sum() + (y2 * w2.to(dev)).sum()).backward()
+        outs.append((y1, lg.grad, xx.grad))
+    scale_close(outs[1][0], outs[0][0], FP32_TOL, "y1")
+    scale_close(outs[1][1], outs[0][1], GRAD_TOL, "dlogits")
+    scale_close(outs[1][2], outs[0][2], GRAD_TOL, "dx")
+
+
+def test_state_dict_roundtrip_and_restack(cuda, tmp_path):
+    import binDeltaModels as M
+    import copy
+    torch.manual_seed(5)
+    m = M.OneBinDeltaModel("none", 3, 16, 64, 40, 24, 3)
+    m.feature_model = torch.nn.Identity()
+    m.cuda().eval()
+    x = torch.randn(6, 64, device=cuda); lab = torch.randint(0, 3, (6, 1), device=cuda)
+    with torch.no_grad():
+        y = m(x, lab)
+    torch.save(m.state_dict(), tmp_path / "m.tar")
+    m2 = M.OneBinDeltaModel("none", 3, 16, 64, 40, 24, 3)
+    m2.feature_model = torch.nn.Identity()
+    m2.load_state_dict(torch.load(tmp_path / "m.tar"))
+    m2.cuda().eval()
+    m3 = copy.deepcopy(m).eval()
+    with torch.no_grad():
+        for other in (m2, m3):
+            yo = other(x, lab)
+            assert torch.equal(yo[0], y[0]) and torch.equal(yo[1], y[1])
+    # an optimizer step on the per-module Parameters is seen by the fused path
+    m.train()
+    opt = torch.optim.SGD(list(m.bin_models.parameters()) + list(m.res_models.parameters()), lr=0.1)
+    y1, y2 = m(x, lab)
+    (y1.sum() + y2.sum()).backward()
+    opt.step(); opt.zero_grad()
+    m.eval()
+    with torch.no_grad():
+        y_after = m(x, lab)
+    assert not torch.equal(y_after[0], y[0])
+
+
+def test_tf32_mode_forward(cuda):
+    """The reduced-precision mode: one TF32 MMA per k-step, forward outputs within 2e-3."""
+    import binDeltaModels as M
+    from bdpose import head
+    torch.manual_seed(0)
+    C, K, N0, N1, N2, nd, B = 12, 200, 2048, 1000, 500, 3, 48
+    ref = O.OneBinDeltaHeads(C, K, N0, N1, N2, nd)
+    model = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+    model.feature_model = torch.nn.Identity()
+    model.load_state_dict(ref.state_dict())
+    model.cuda().train(); ref.train()
+    x = torch.randn(B, N0); lab = torch.randint(0, C, (B, 1))
+    head.set_precision("tf32")
+    try:
+        y1, y2 = model(x.to(cuda), lab.to(cuda))
+    finally:
+        head.set_precision("fp32")
+    r1, r2 = ref(x, label=lab)
+    scale_close(y1, r1, TF32_TOL, "y1"); scale_close(y2, r2, TF32_TOL, "y2")
