@@ -193,9 +193,9 @@ int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
  *   OneBinDeltaModel.forward          binDeltaModels.py:112-121 (all C heads on all B, label select)
  *   soft mixing (joint model)         learnJointCatPoseModel_weighted.py:107-115
  *   ObjectNet one-hot-concat heads    objectnetHelperFunctions.py:110-172
- * Activations between the layers are kept FEATURE-MAJOR, [features, ldb] with the batch along the
- * contiguous axis (ldb >= B, a multiple of 4): the GEMM puts features on the 128 TMEM lanes and the
- * batch on the N side (swap-AB), and BatchNorm's batch statistics become a per-row reduction.
+ * Activations are batch-major [B, ld] (ld >= features, a multiple of 4): the GEMM puts the batch
+ * on the 128 TMEM lanes and streams the weights on the N side, 176-256 rows of them per MMA, which is
+ * what lets a small batch still pull the weights at HBM speed.
  * ---------------------------------------------------------------------------------------------- */
 
 /*
@@ -220,44 +220,44 @@ int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t a_gstride, 
 int bdp_gemm_tf32_splits(int64_t K, int splits);
 
 /*
- * BatchNorm1d + ReLU on feature-major activations (nn.BatchNorm1d defaults: eps 1e-5, momentum 0.1,
- * biased variance for normalisation, unbiased for the running estimate; binDeltaModels.py:66-73).
- * h [F, ldb] pre-activation (GEMM output), B valid columns.
+ * BatchNorm1d + ReLU (nn.BatchNorm1d defaults: eps 1e-5, momentum 0.1, biased variance for
+ * normalisation, unbiased for the running estimate; binDeltaModels.py:66-73).
+ * h [B, ld] pre-activation (GEMM output), F valid columns.
  * training != 0: batch statistics; save_mean / save_invstd [F] are written; running_mean / running_var
  *                [F] are updated in place (NULL: skip) — num_batches_tracked is the caller's.
  * training == 0: normalise with running_mean / running_var.
- * a [F, ldb] = relu(gamma * xhat + beta); columns B..ldb-1 are written as zeros.
+ * a [B, ld] = relu(gamma * xhat + beta)   (columns F..ld-1 are not touched)
  */
-int bdp_bn_relu_fwd(const float* h, int64_t F, int64_t B, int64_t ldb, const float* gamma,
+int bdp_bn_relu_fwd(const float* h, int64_t F, int64_t B, int64_t ld, const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float* save_mean,
                     float* save_invstd, float eps, float momentum, int training, float* a,
                     void* stream);
 /*
- * Backward of the above (training statistics): da [F, ldb] gradient w.r.t. the post-ReLU output,
- * a the saved output (ReLU mask), h the saved pre-activation.
- * dh [F, ldb] (pad columns zeroed), dgamma [F], dbeta [F].  training == 0 uses the running
- * statistics (mean = running_mean, invstd = rsqrt(running_var + eps)) passed in save_mean/save_invstd.
+ * Backward of the above: da [B, ld] gradient w.r.t. the post-ReLU output, a the saved output (ReLU
+ * mask), h the saved pre-activation.  dh [B, ld], dgamma [F], dbeta [F].  training == 0 uses the
+ * running statistics (mean = running_mean, invstd = rsqrt(running_var + eps)) passed in
+ * save_mean / save_invstd and drops the batch-coupling terms.
  */
 int bdp_bn_relu_bwd(const float* da, const float* a, const float* h, const float* gamma,
                     const float* save_mean, const float* save_invstd, int64_t F, int64_t B,
-                    int64_t ldb, int training, float* dh, float* dgamma, float* dbeta, void* stream);
+                    int64_t ld, int training, float* dh, float* dgamma, float* dbeta, void* stream);
 
 /*
- * fc3 + category mixing.  a2 [H*N2, ldb] feature-major post-ReLU activations of H heads; w3
+ * fc3 + category mixing.  a2 [B, ld] post-ReLU activations, head h in columns [h*N2, (h+1)*N2); w3
  * [H, O, N2], b3 [H, O]; mix [B, H] mixing weights (one-hot of the class label —
  * binDeltaModels.py:116-119 — or softmax probabilities — learnJointCatPoseModel_weighted.py:110-115).
- *   y[b, o] = sum_h mix[b,h] * (b3[h,o] + sum_j w3[h,o,j] * a2[h*N2 + j, b])          y [B, O]
+ *   y[b, o] = sum_h mix[b,h] * (b3[h,o] + sum_j w3[h,o,j] * a2[b, h*N2 + j])          y [B, O]
  * Heads with mix[b,h] == 0 are skipped (exactly what the bmm with a one-hot produces).
  */
-int bdp_head_fc3_fwd(const float* a2, int64_t ldb, const float* w3, const float* b3,
+int bdp_head_fc3_fwd(const float* a2, int64_t ld, const float* w3, const float* b3,
                      const float* mix, int64_t B, int H, int O, int N2, float* y, void* stream);
 /*
  * Backward of fc3 + mixing, dy [B, O]:
- *   da2 [H*N2, ldb]  = mix[b,h] * sum_o dy[b,o] w3[h,o,j]             (dense, zeros where mix == 0)
- *   dw3 [H, O, N2]   = sum_b mix[b,h] dy[b,o] a2[h*N2+j, b]           db3 [H, O] = sum_b mix[b,h] dy[b,o]
- *   dmix [B, H]      = sum_o dy[b,o] * (b3[h,o] + w3[h,o,:] . a2[h,:,b])   (NULL: skip)
+ *   da2 [B, ld]      = mix[b,h] * sum_o dy[b,o] w3[h,o,j]             (dense, zeros where mix == 0)
+ *   dw3 [H, O, N2]   = sum_b mix[b,h] dy[b,o] a2[b, h*N2+j]           db3 [H, O] = sum_b mix[b,h] dy[b,o]
+ *   dmix [B, H]      = sum_o dy[b,o] * (b3[h,o] + w3[h,o,:] . a2[b,h,:])   (NULL: skip)
  */
-int bdp_head_fc3_bwd(const float* dy, const float* a2, int64_t ldb, const float* w3,
+int bdp_head_fc3_bwd(const float* dy, const float* a2, int64_t ld, const float* w3,
                      const float* b3, const float* mix, int64_t B, int H, int O, int N2,
                      float* da2, float* dw3, float* db3, float* dmix, void* stream);
 

@@ -4,7 +4,7 @@
 fc2 [H,N2,N1], bn2 [H,N2], fc3 [H,O,N2] + bias) and runs all of them on one feature batch:
 
   fc1   one tcgen05 TF32 GEMM over the flattened [H*N1, N0] weights        (bdp_gemm_tf32)
-  bn1   batch statistics + affine + ReLU on feature-major activations       (bdp_bn_relu_fwd)
+  bn1   batch statistics + affine + ReLU on batch-major activations         (bdp_bn_relu_fwd)
   fc2   grouped tcgen05 GEMM, one [N2,N1] weight per head                   (bdp_gemm_tf32, G=H)
   bn2   as bn1
   fc3   label-selected / soft-mixed output layer                            (bdp_head_fc3_fwd)
@@ -27,10 +27,6 @@ from . import _lib as L
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
-
-
-def _pad4(n):
-    return (n + 3) // 4 * 4
 
 
 # Head GEMM precision: "fp32" = 3xTF32 split accumulation (parity mode, default), "tf32" = one TF32
@@ -61,18 +57,18 @@ def gemm_splits(K, splits):
     return L.lib().bdp_gemm_tf32_splits(K, splits)
 
 
-def bn_relu_fwd(h, B, gamma, beta, running_mean, running_var, training, eps=BN_EPS,
+def bn_relu_fwd(h, gamma, beta, running_mean, running_var, training, eps=BN_EPS,
                 momentum=BN_MOMENTUM):
-    """h [F, ldb] -> (a [F, ldb], save_mean [F], save_invstd [F])."""
-    F, ldb = h.shape
-    a = torch.empty_like(h)
+    """h [B, F] batch-major -> (a [B, F], save_mean [F], save_invstd [F])."""
+    B, F = h.shape
+    a = torch.empty_strided(h.shape, h.stride(), dtype=h.dtype, device=h.device)   # same row pitch
     if training:
         mean = torch.empty(F, dtype=torch.float32, device=h.device)
         invstd = torch.empty(F, dtype=torch.float32, device=h.device)
     else:
         mean = invstd = None
     with torch.cuda.device(h.device):
-        st = L.lib().bdp_bn_relu_fwd(L.ptr(h), F, B, ldb, L.ptr(gamma), L.ptr(beta),
+        st = L.lib().bdp_bn_relu_fwd(L.ptr(h), F, B, h.stride(0), L.ptr(gamma), L.ptr(beta),
                                      L.ptr(running_mean), L.ptr(running_var), L.ptr(mean),
                                      L.ptr(invstd), eps, momentum, 1 if training else 0, L.ptr(a),
                                      L.stream_ptr())
@@ -80,37 +76,46 @@ def bn_relu_fwd(h, B, gamma, beta, running_mean, running_var, training, eps=BN_E
     return a, mean, invstd
 
 
-def bn_relu_bwd(da, a, h, gamma, mean, invstd, B, training=True):
-    F, ldb = h.shape
-    dh = torch.empty_like(h)
+def bn_relu_bwd(da, a, h, gamma, mean, invstd, training=True):
+    B, F = h.shape
+    if da.stride() != h.stride() or a.stride() != h.stride():
+        raise RuntimeError("bn_relu_bwd: da, a and h must share the row pitch")
+    dh = torch.empty_strided(h.shape, h.stride(), dtype=h.dtype, device=h.device)
     dgamma = torch.empty(F, dtype=torch.float32, device=h.device)
     dbeta = torch.empty(F, dtype=torch.float32, device=h.device)
     with torch.cuda.device(h.device):
         st = L.lib().bdp_bn_relu_bwd(L.ptr(da), L.ptr(a), L.ptr(h), L.ptr(gamma), L.ptr(mean),
-                                     L.ptr(invstd), F, B, ldb, 1 if training else 0, L.ptr(dh),
-                                     L.ptr(dgamma), L.ptr(dbeta), L.stream_ptr())
+                                     L.ptr(invstd), F, B, h.stride(0), 1 if training else 0,
+                                     L.ptr(dh), L.ptr(dgamma), L.ptr(dbeta), L.stream_ptr())
     L.check(st, "bdp_bn_relu_bwd")
     return dh, dgamma, dbeta
 
 
-def fc3_fwd(a2, w3, b3, mix, B):
+def fc3_fwd(a2, w3, b3, mix):
+    """a2 [B, H*N2] (a column slice of the stacked activations: row pitch a2.stride(0))."""
     H, O, N2 = w3.shape
+    B = a2.shape[0]
     y = torch.empty((B, O), dtype=torch.float32, device=a2.device)
     with torch.cuda.device(a2.device):
-        st = L.lib().bdp_head_fc3_fwd(L.ptr(a2), a2.shape[1], L.ptr(w3), L.ptr(b3), L.ptr(mix), B,
+        st = L.lib().bdp_head_fc3_fwd(L.ptr(a2), a2.stride(0), L.ptr(w3), L.ptr(b3), L.ptr(mix), B,
                                       H, O, N2, L.ptr(y), L.stream_ptr())
     L.check(st, "bdp_head_fc3_fwd")
     return y
 
 
-def fc3_bwd(dy, a2, w3, b3, mix, B, want_dmix):
+def fc3_bwd(dy, a2, w3, b3, mix, want_dmix, da2=None):
+    """da2 (optional) is the column slice of the stacked gradient buffer to fill (same pitch as a2)."""
     H, O, N2 = w3.shape
-    da2 = torch.empty_like(a2)
+    B = a2.shape[0]
+    if da2 is None:
+        da2 = torch.empty_like(a2)
+    if da2.stride(0) != a2.stride(0):
+        raise RuntimeError("fc3_bwd: da2 and a2 must share the row pitch")
     dw3 = torch.empty_like(w3)
     db3 = torch.empty_like(b3)
     dmix = torch.empty((B, H), dtype=torch.float32, device=a2.device) if want_dmix else None
     with torch.cuda.device(a2.device):
-        st = L.lib().bdp_head_fc3_bwd(L.ptr(dy), L.ptr(a2), a2.shape[1], L.ptr(w3), L.ptr(b3),
+        st = L.lib().bdp_head_fc3_bwd(L.ptr(dy), L.ptr(a2), a2.stride(0), L.ptr(w3), L.ptr(b3),
                                       L.ptr(mix), B, H, O, N2, L.ptr(da2), L.ptr(dw3), L.ptr(db3),
                                       L.ptr(dmix), L.stream_ptr())
     L.check(st, "bdp_head_fc3_bwd")
@@ -260,7 +265,7 @@ class _HeadFn(torch.autograd.Function):
         N2 = w2.shape[1]
         B = x.shape[0]
         dev = x.device
-        ldb = _pad4(B)
+        F1, F2 = H * N1, H * N2
         if x.shape[1] != N0:
             raise RuntimeError("head: input has %d features, fc1 expects %d" % (x.shape[1], N0))
         if N0 % 4 or N1 % 4 or N2 % 4:
@@ -270,15 +275,15 @@ class _HeadFn(torch.autograd.Function):
                              "[%d, %d]" % (B, N1))
         x = x.detach().float().contiguous()
         mix = mix.detach().float().contiguous()
-        # fc1: H1^T [H*N1, ldb] = W1 [H*N1, N0] (K-major) x X [B, N0] (K-major)
-        h1 = torch.empty((H * N1, ldb), dtype=torch.float32, device=dev)
-        gemm_tf32(w1, 0, N0, 0, x, 0, N0, 0, h1, 0, ldb, 0, H * N1, B, N0)
-        a1, m1, is1 = bn_relu_fwd(h1, B, buf["g1"].view(-1), buf["be1"].view(-1), buf["rm1"].view(-1),
+        # fc1: H1 [B, H*N1] = X [B, N0] (lanes, K-major) x W1 [H*N1, N0] (streamed, K-major)
+        h1 = torch.empty((B, F1), dtype=torch.float32, device=dev)
+        gemm_tf32(x, 0, N0, 0, w1, 0, N0, 0, h1, 0, F1, 0, B, F1, N0)
+        a1, m1, is1 = bn_relu_fwd(h1, buf["g1"].view(-1), buf["be1"].view(-1), buf["rm1"].view(-1),
                                   buf["rv1"].view(-1), training)
-        # fc2 (grouped): H2^T_g [N2, ldb] = W2_g [N2, N1] (K-major) x A1^T_g [N1, ldb] (MN-major)
-        h2 = torch.empty((H * N2, ldb), dtype=torch.float32, device=dev)
-        gemm_tf32(w2, 0, N1, N2 * N1, a1, 1, ldb, N1 * ldb, h2, 0, ldb, N2 * ldb, N2, B, N1, G=H)
-        a2, m2, is2 = bn_relu_fwd(h2, B, buf["g2"].view(-1), buf["be2"].view(-1), buf["rm2"].view(-1),
+        # fc2 (grouped): H2_g [B, N2] = A1_g [B, N1] (columns g*N1.. of a1) x W2_g [N2, N1]
+        h2 = torch.empty((B, F2), dtype=torch.float32, device=dev)
+        gemm_tf32(a1, 0, F1, N1, w2, 0, N1, N2 * N1, h2, 0, F2, N2, B, N2, N1, G=H)
+        a2, m2, is2 = bn_relu_fwd(h2, buf["g2"].view(-1), buf["be2"].view(-1), buf["rm2"].view(-1),
                                   buf["rv2"].view(-1), training)
         if training:
             buf["nb1"] += 1
@@ -288,12 +293,12 @@ class _HeadFn(torch.autograd.Function):
             Hg = w3.shape[0]
             if mix.shape[1] != Hg:
                 raise RuntimeError("head: mixing weights have %d columns for %d heads" % (mix.shape[1], Hg))
-            ys.append(fc3_fwd(a2[off * N2:(off + Hg) * N2], w3, b3, mix, B))
+            ys.append(fc3_fwd(a2[:, off * N2:(off + Hg) * N2], w3, b3, mix))
             off += Hg
         ctx.stack = stack
         ctx.saved = (x, mix, h1, a1, m1, is1, h2, a2, m2, is2)
         ctx.training = training
-        ctx.dims = (H, N0, N1, N2, B, ldb)
+        ctx.dims = (H, N0, N1, N2, B)
         return tuple(ys)
 
     @staticmethod
@@ -301,7 +306,8 @@ class _HeadFn(torch.autograd.Function):
         stack = ctx.stack
         buf = stack.buf
         x, mix, h1, a1, m1, is1, h2, a2, m2, is2 = ctx.saved
-        H, N0, N1, N2, B, ldb = ctx.dims
+        H, N0, N1, N2, B = ctx.dims
+        F1, F2 = H * N1, H * N2
         training = ctx.training
         dev = x.device
         w1, w2 = buf["w1"], buf["w2"]
@@ -310,7 +316,7 @@ class _HeadFn(torch.autograd.Function):
             m1, is1 = buf["rm1"].view(-1), torch.rsqrt(buf["rv1"].view(-1) + BN_EPS)
             m2, is2 = buf["rm2"].view(-1), torch.rsqrt(buf["rv2"].view(-1) + BN_EPS)
         grads = {}
-        # fc3 backward, group by group
+        # fc3 backward, group by group, each filling its column slice of da2
         da2 = torch.empty_like(a2)
         dmix, off = None, 0
         for gi, (w3, b3) in enumerate(zip(buf["w3"], buf["b3"])):
@@ -318,36 +324,34 @@ class _HeadFn(torch.autograd.Function):
             dy = dys[gi]
             dy = torch.zeros((B, O), device=dev) if dy is None else dy.contiguous().float()
             sl = slice(off * N2, (off + Hg) * N2)
-            d_a, d_w, d_b, d_m = fc3_bwd(dy, a2[sl], w3, b3, mix, B, want_dmix)
-            da2[sl] = d_a
+            _, d_w, d_b, d_m = fc3_bwd(dy, a2[:, sl], w3, b3, mix, want_dmix, da2=da2[:, sl])
             grads["w3_%d" % gi], grads["b3_%d" % gi] = d_w, d_b
             if want_dmix:
                 dmix = d_m if dmix is None else dmix + d_m
             off += Hg
         # bn2 backward
-        dh2, dg2, dbe2 = bn_relu_bwd(da2, a2, h2, buf["g2"].view(-1), m2, is2, B, training)
-        # fc2 wgrad: dW2_g [N2, N1] = dH2^T_g [N2, B] (K-major over the batch) x A1^T_g [N1, B] (K-major)
+        dh2, dg2, dbe2 = bn_relu_bwd(da2, a2, h2, buf["g2"].view(-1), m2, is2, training)
+        # fc2 wgrad: dW2_g [N2, N1] = sum_b dH2_g[b, :]^T A1_g[b, :]   (both MN-major, K = batch)
         dw2 = torch.empty_like(w2)
-        gemm_tf32(dh2, 0, ldb, N2 * ldb, a1, 0, ldb, N1 * ldb, dw2, 0, N1, N2 * N1, N2, N1, B, G=H)
-        # fc2 dgrad: dA1^T_g [N1, ldb] = W2_g^T (MN-major: [N2 rows, N1 contiguous]) x dH2^T_g (MN-major)
+        gemm_tf32(dh2, 1, F2, N2, a1, 1, F1, N1, dw2, 0, N1, N2 * N1, N2, N1, B, G=H)
+        # fc2 dgrad: dA1_g [B, N1] = dH2_g [B, N2] (K-major) x W2_g ([k = N2 rows, n = N1 contiguous]: MN-major)
         da1 = torch.empty_like(a1)
-        gemm_tf32(w2, 1, N1, N2 * N1, dh2, 1, ldb, N2 * ldb, da1, 0, ldb, N1 * ldb, N1, B, N2, G=H)
+        gemm_tf32(dh2, 0, F2, N2, w2, 1, N1, N2 * N1, da1, 0, F1, N1, B, N1, N2, G=H)
         # bn1 backward
-        dh1, dg1, dbe1 = bn_relu_bwd(da1, a1, h1, buf["g1"].view(-1), m1, is1, B, training)
-        # fc1 wgrad: dW1 [H*N1, N0] = dH1^T [H*N1, B] (K-major) x X [B, N0] (MN-major: batch rows)
+        dh1, dg1, dbe1 = bn_relu_bwd(da1, a1, h1, buf["g1"].view(-1), m1, is1, training)
+        # fc1 wgrad: dW1 [H*N1, N0] = dH1^T X   (both MN-major, K = batch)
         dw1 = torch.empty_like(w1)
-        gemm_tf32(dh1, 0, ldb, 0, x, 1, N0, 0, dw1, 0, N0, 0, H * N1, N0, B)
+        gemm_tf32(dh1, 1, F1, 0, x, 1, N0, 0, dw1, 0, N0, 0, F1, N0, B)
         grads.update(w1=dw1, g1=dg1.view(H, N1), be1=dbe1.view(H, N1), w2=dw2, g2=dg2.view(H, N2),
                      be2=dbe2.view(H, N2))
         stack.deposit(grads)
         dx = None
         if ctx.needs_input_grad[0]:
-            # fc1 dgrad: dX [B, N0]: D[m = feature, n = sample] = sum_k W1[k, m] dH1^T[k, n], split-K
-            KK = H * N1
-            m_tiles = (N0 + 127) // 128
-            splits = gemm_splits(KK, max(1, min(64, L.lib().bdp_sm_count() // m_tiles)))
+            # fc1 dgrad: dX [B, N0] = dH1 [B, H*N1] (K-major) x W1 ([k = H*N1 rows, n = N0]: MN-major), split-K
+            n_tiles = (N0 + 255) // 256
+            splits = gemm_splits(F1, max(1, min(64, L.lib().bdp_sm_count() // n_tiles)))
             parts = torch.empty((splits, B, N0), dtype=torch.float32, device=dev)
-            gemm_tf32(w1, 1, N0, 0, dh1, 1, ldb, 0, parts, 1, N0, 0, N0, B, KK, splits=splits,
+            gemm_tf32(dh1, 0, F1, 0, w1, 1, N0, 0, parts, 0, N0, 0, B, N0, F1, splits=splits,
                       c_ss=B * N0)
             dx = torch.empty((B, N0), dtype=torch.float32, device=dev)
             sum_slabs(parts, B * N0, splits, B * N0, dx)
@@ -366,3 +370,156 @@ def onehot(label, num_classes):
     it on the CPU and copies it back every forward: binDeltaModels.py:116-117)."""
     label = label.reshape(-1, 1).long()
     return torch.zeros(label.shape[0], num_classes, device=label.device).scatter_(1, label, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# driver hooks: smoke test, benchmark legs, profiling target
+# ------------------------------------------------------------------------------------------------
+def _pascal_model(C=12, K=200, N0=2048, N1=1000, N2=500, nd=3, seed=0):
+    import binDeltaModels as M
+    torch.manual_seed(seed)
+    m = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+    m.feature_model = torch.nn.Identity()
+    return m.cuda()
+
+
+def smoke(dev):
+    """One small train-mode forward+backward of a 3-category head against the oracle modules."""
+    import bdpose_oracle as O
+    import binDeltaModels as M
+    torch.manual_seed(0)
+    C, K, N0, N1, N2, nd, B = 3, 16, 64, 40, 24, 3, 10
+    ref = O.OneBinDeltaHeads(C, K, N0, N1, N2, nd)
+    m = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+    m.feature_model = torch.nn.Identity()
+    m.load_state_dict(ref.state_dict())
+    m.cuda().train(); ref.train()
+    x = torch.randn(B, N0); lab = torch.randint(0, C, (B, 1))
+    xr = x.clone().requires_grad_(True)
+    r1, r2 = ref(xr, label=lab)
+    (r1.sum() + r2.pow(2).sum()).backward()
+    xg = x.clone().to(dev).requires_grad_(True)
+    y1, y2 = m(xg, lab.to(dev))
+    (y1.sum() + y2.pow(2).sum()).backward()
+    assert torch.allclose(y1.cpu(), r1, rtol=1e-4, atol=1e-5), "head y1 differs from the oracle"
+    assert torch.allclose(y2.cpu(), r2, rtol=1e-4, atol=1e-5), "head y2 differs from the oracle"
+    assert torch.allclose(xg.grad.cpu(), xr.grad, rtol=1e-3, atol=1e-5), "head dx differs from the oracle"
+    g = m.bin_models[0].fc1.weight.grad
+    assert g is not None and torch.allclose(g.cpu(), ref.bin_models[0].fc1.weight.grad, rtol=1e-3, atol=1e-5)
+
+
+def _time(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench(dev, peaks):
+    """BASELINE configs 1 and 4: head + fused loss, forward+backward, samples/s."""
+    import binDeltaLosses  # noqa: F401  (the fused loss mirrors)
+    from . import ops
+    out = {}
+    hbm = peaks["hbm_gbs"]
+    C, K = 12, 200
+    m = _pascal_model(C, K).train()
+    keys = torch.randn(K, 3, device=dev)
+    n_params = sum(p.numel() for p in m.bin_models.parameters()) + sum(p.numel() for p in m.res_models.parameters())
+    for B in (32, 96):
+        x = torch.randn(B, 2048, device=dev, requires_grad=True)
+        lab = torch.randint(0, C, (B, 1), device=dev)
+        bins = torch.randint(0, K, (B,), device=dev)
+        tgt = torch.randn(B, 3, device=dev)
+
+        def fwd():
+            with torch.no_grad():
+                m(x, lab)
+
+        def step():
+            for p in m.parameters():
+                p.grad = None
+            y1, y2 = m(x, lab)
+            lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
+            (lc + lr).backward()
+        for mode in ("fp32", "tf32"):
+            set_precision(mode)
+            try:
+                ms_f = _time(fwd, 20, 5)
+                ms = _time(step, 20, 5)
+            finally:
+                set_precision("fp32")
+            wbytes = n_params * 4
+            out["pascal_head_B%d_%s" % (B, mode)] = {
+                "samples_per_s_fwd_bwd": B / (ms * 1e-3), "ms_fwd_bwd": ms, "ms_fwd": ms_f,
+                "fwd_weight_stream_gbs": wbytes / (ms_f * 1e-3) / 1e9,
+                "fwd_hbm_frac": wbytes / (ms_f * 1e-3) / 1e9 / hbm,
+                "fwd_bwd_hbm_frac": 3 * wbytes / (ms * 1e-3) / 1e9 / hbm,
+                "weight_bytes": wbytes}
+    # raw fc1 GEMM: the dominant kernel of the head (197 MB of weights streamed once)
+    H, N1, N0, B = 24, 1000, 2048, 32
+    w1 = m._heads().ensure()["w1"]
+    xb = torch.randn(B, N0, device=dev)
+    h1 = torch.empty(B, H * N1, device=dev)
+    for precise in (True, False):
+        ms = _time(lambda: gemm_tf32(xb, 0, N0, 0, w1, 0, N0, 0, h1, 0, H * N1, 0, B, H * N1, N0, precise=precise), 30, 5)
+        by = w1.numel() * 4 + xb.numel() * 4 + h1.numel() * 4
+        out["fc1_gemm_B32_%s" % ("3xtf32" if precise else "tf32")] = {
+            "ms": ms, "achieved_gbs": by / (ms * 1e-3) / 1e9, "hbm_frac": by / (ms * 1e-3) / 1e9 / hbm,
+            "tflops": 2.0 * H * N1 * N0 * B / (ms * 1e-3) / 1e12}
+    del m
+    # config 4: ObjectNet one-hot-concat heads, C=100, B=256
+    import objectnetHelperFunctions as OH
+    torch.manual_seed(0)
+    om = OH.OneBinDeltaModel.__new__(OH.OneBinDeltaModel)
+    torch.nn.Module.__init__(om)
+    om.num_classes, om.num_clusters = 100, 200
+    om.feature_model = torch.nn.Identity()
+    om.bin_model = OH.bin_3layer(2148, 1000, 500, 200).cuda()
+    om.res_model = OH.res_3layer(2148, 1000, 500, 3).cuda()
+    object.__setattr__(om, "_stack", None)
+    om.train()
+    B = 256
+    x = torch.randn(B, 2048, device=dev, requires_grad=True)
+    lab = torch.randint(0, 100, (B, 1), device=dev)
+    bins = torch.randint(0, 200, (B,), device=dev)
+    tgt = torch.randn(B, 3, device=dev)
+    keys = torch.randn(200, 3, device=dev)
+
+    def ostep():
+        for p in om.parameters():
+            p.grad = None
+        y1, y2 = om.forward_features(x, lab)
+        lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
+        (lc + 10 * lr).backward()
+    for mode in ("fp32", "tf32"):
+        set_precision(mode)
+        try:
+            ms = _time(ostep, 20, 5)
+        finally:
+            set_precision("fp32")
+        out["objectnet_head_B256_%s" % mode] = {"samples_per_s_fwd_bwd": B / (ms * 1e-3), "ms_fwd_bwd": ms}
+    return out
+
+
+def profile(dev):
+    """A few head steps for ncu (profiles/prof_targets.py head)."""
+    from . import ops
+    m = _pascal_model().train()
+    B, K = 32, 200
+    x = torch.randn(B, 2048, device=dev, requires_grad=True)
+    lab = torch.randint(0, 12, (B, 1), device=dev)
+    bins = torch.randint(0, K, (B,), device=dev)
+    tgt = torch.randn(B, 3, device=dev)
+    keys = torch.randn(K, 3, device=dev)
+    for _ in range(3):
+        for p in m.parameters():
+            p.grad = None
+        y1, y2 = m(x, lab)
+        lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
+        (lc + lr).backward()

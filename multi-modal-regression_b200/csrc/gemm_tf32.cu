@@ -10,15 +10,16 @@
 //   rows of D (m)  -> the 128 TMEM lanes  (always the "feature" side: swap-AB, batch is the N side)
 //   cols of D (n)  -> TMEM columns, BN <= 256 per tile
 //
-// Warp roles (384 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer
+// Warp roles (512 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> global),
-// warps 8-11 = operand splitters (precise mode only).  mbarrier pipelines: smem full/empty
+// warps 8-15 = operand splitters (precise mode only).  mbarrier pipelines: smem full/empty
 // (TMA <-> MMA), split-ready (splitters -> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator
 // stages so the epilogue of tile i overlaps the mainloop of tile i+1).
 //
 // Precision.  precise = 0: one TF32 MMA per k-step (operands truncated to 10 mantissa bits by the
 // tensor core, ~1e-3 relative).  precise = 1 ("3xTF32"): every fp32 operand tile is split in shared
-// memory into hi = tf32(x) and lo = tf32(x - hi), and D += Ahi*Bhi + Ahi*Blo + Alo*Bhi; the dropped
+// memory into hi = tf32(x) (the raw fp32 itself: the tensor core ignores the low 13 mantissa bits)
+// and lo = tf32(x - hi), and D += Ahi*Bhi + Ahi*Blo + Alo*Bhi; the dropped
 // terms are ~2^-20 relative, i.e. fp32-class results (needed for parity: at 1e-3 a few ReLU masks
 // flip and gradients drift by percents).  The weights still stream from HBM exactly once.
 //
@@ -29,6 +30,7 @@
 // go to the remaining ones (where ulp is ~2^-11 smaller), and the epilogue adds the chains in
 // registers with round-to-nearest.  BN = 32 -> 8 chains, 64 -> 4, 128 -> 2, 256 -> 1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -37,8 +39,8 @@ namespace {
 constexpr int kBM = 128;            // tile rows = TMEM lanes
 constexpr int kBK = 32;             // fp32 per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;           // K of one tcgen05.mma.kind::tf32
-constexpr int kGemmThreads = 384;
-constexpr int kSplitThreads = 128;   // warps 8-11
+constexpr int kGemmThreads = 512;
+constexpr int kSplitThreads = 256;   // warps 8-15
 constexpr int kABytes = kBM * kBK * 4;     // 16 KB per stage
 constexpr int kMaxStages = 10;
 
@@ -53,6 +55,11 @@ struct GemmParams {
   int c_nm;                         // 0: C[m*ldc + n], 1: C[n*ldc + m]
   int precise;                      // 1: 3xTF32 split-operand accumulation
   int chains, chains_hi;            // TMEM accumulator chains per tile (see below)
+  int cstride;                      // TMEM columns between accumulator chains (BN rounded up to 32)
+  int k_rotate;                     // 1: stagger the K walk of the tiles
+  int a_rows;                       // A rows actually fetched per stage (small-M problems)
+  int a_bytes;                      // smem reserved for the A tile of one stage (1 KB multiple)
+  int acc_stages;                   // TMEM accumulator stages (2 only when a CTA runs >1 tile)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -126,6 +133,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 columns, or the 16-column tail of a tile whose width is an odd multiple of 16
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[32], bool full) {
+  if (full) {
+    tmem_ld32(taddr, v);
+  } else {
+    tmem_ld16(taddr, v);
+#pragma unroll
+    for (int i = 16; i < 32; ++i) v[i] = 0u;
+  }
+}
+
 // UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1).
 //   K-major : rows are 128 B apart inside an 8-row group, groups SBO = 1024 B apart; the K
 //             position inside the 128 B row is selected by advancing the start address.
@@ -151,7 +179,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // 1024-byte aligned operand ring (swizzle-128B atoms are 1 KB), barriers after it
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = static_cast<uint32_t>(P.BN) * kBK * 4;
-  const uint32_t tile_bytes = kABytes + b_bytes;                 // what TMA delivers per stage
+  const uint32_t a_bytes = static_cast<uint32_t>(P.a_bytes);
+  const uint32_t tile_bytes = a_bytes + b_bytes;                 // operand footprint of one stage
+  const uint32_t a_tx = static_cast<uint32_t>(P.a_rows) * kBK * 4;   // A bytes TMA really delivers
   const uint32_t stage_bytes = P.precise ? 2u * tile_bytes : tile_bytes;   // + the lo copies
   const uint32_t bar_base = base + P.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -162,7 +192,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint32_t s_tmem_base;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int need_cols = 2 * P.chains * P.BN;
+  const int need_cols = P.acc_stages * P.chains * P.cstride;
   const int tmem_cols = (need_cols <= 32) ? 32 : (need_cols <= 64) ? 64 : (need_cols <= 128) ? 128
                         : (need_cols <= 256) ? 256 : 512;
   const int chains_x = P.chains - P.chains_hi;       // chains reserved for the cross terms
@@ -201,17 +231,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int kb0 = sp * P.kb_per_split;
       const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
       const int m0 = mt * kBM, n0 = nt * P.BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      // Each tile walks its K range from a different starting block (the sum is order-free): with
+      // a power-of-two row pitch (2048 floats) all CTAs would otherwise request the same column
+      // block of 148 x BN different rows at the same time — addresses 8 KB apart, which pile onto a
+      // few DRAM channels.
+      const int nkb = kb1 - kb0;
+      const int rot = P.k_rotate ? static_cast<int>((static_cast<unsigned>(t) * 13u) % static_cast<unsigned>(nkb)) : 0;
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb0 + (i + rot) % nkb;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = base + stage * stage_bytes;
-        const uint32_t sb = sa + kABytes;
-        mbar_expect_tx(full_bar(stage), tile_bytes);
+        const uint32_t sb = sa + a_bytes;
+        mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
         const int k0 = kb * kBK;
         if (!P.a_mn) {
-          tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, g * P.a_g);
+          tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, g * P.a_g);    // box = a_rows x 32
         } else {
-#pragma unroll
-          for (int j = 0; j < kBM / 32; ++j)
+          for (int j = 0; j < P.a_rows / 32; ++j)
             tma_load_3d(sa + j * 4096, &tmA, full_bar(stage), m0 + 32 * j, k0, g * P.a_g);
         }
         if (!P.b_mn) {
@@ -244,14 +280,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
-      const uint32_t tmem_t = tmem_base + static_cast<uint32_t>(as * P.chains * P.BN);
+      const uint32_t tmem_t = tmem_base + static_cast<uint32_t>(as * P.chains * P.cstride);
       uint32_t started = 0;                            // chains that already hold a partial sum
       int step = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(P.precise ? split_bar(stage) : full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + stage * stage_bytes;
-        const uint32_t sb = sa + kABytes;
+        const uint32_t sb = sa + a_bytes;
         const uint32_t a_sbo = P.a_mn ? 512u : 1024u, a_lt = P.a_mn ? 1u : 2u;
         const uint32_t b_sbo = P.b_mn ? 512u : 1024u, b_lt = P.b_mn ? 1u : 2u;
 #pragma unroll
@@ -259,10 +295,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t ad = umma_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
           const uint64_t bd = umma_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
           const int ch = step % P.chains_hi;
-          const uint32_t d_hi = tmem_t + static_cast<uint32_t>(ch * P.BN);
+          const uint32_t d_hi = tmem_t + static_cast<uint32_t>(ch * P.cstride);
           if (P.precise) {
             const int cx = chains_x > 0 ? P.chains_hi + step % chains_x : ch;
-            const uint32_t d_x = tmem_t + static_cast<uint32_t>(cx * P.BN);
+            const uint32_t d_x = tmem_t + static_cast<uint32_t>(cx * P.cstride);
             const uint64_t adl = umma_desc(sa + tile_bytes + k * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t bdl = umma_desc(sb + tile_bytes + k * b_kstep, b_lbo, b_sbo, b_lt);
             umma_tf32(d_x, adl, bd, idesc, (started >> cx) & 1u);
@@ -280,7 +316,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (kb == kb1 - 1) umma_commit(tfull_bar(as)); // accumulator complete -> epilogue
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == P.acc_stages) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= 8) {
     // ===== operand splitters (precise mode): x -> hi = tf32(x) in place, lo = tf32(x - hi) =====
@@ -288,7 +324,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int tid = threadIdx.x - 8 * 32;
       int stage = 0;
       uint32_t phase = 0;
-      const int nvec = static_cast<int>(tile_bytes / 16);
+      // A rows beyond a_rows are never fetched (their D rows are discarded), so only the fetched
+      // part of A and the B tile are split; K-major A: the first a_rows*128 bytes, MN-major A: whole
+      const int a_vec = static_cast<int>((P.a_mn ? a_bytes : a_tx) / 16);
+      const int b_vec = static_cast<int>(b_bytes / 16);
+      const int nvec = a_vec + b_vec;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int sp = (t % tiles_per_group) % P.splits;
         const int kb0 = sp * P.kb_per_split;
@@ -296,18 +336,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           const uint32_t sa = base + stage * stage_bytes;
-          for (int i = tid; i < nvec; i += kSplitThreads) {
+          for (int ii = tid; ii < nvec; ii += kSplitThreads) {
+            const int i = ii < a_vec ? ii : ii - a_vec + static_cast<int>(a_bytes / 16);
             uint32_t x0, x1, x2, x3;
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sa + 16u * i));
+            // the tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32
+            // left in place IS the hi part; only lo = tf32(x - hi) is written
             const uint32_t h0 = x0 & 0xFFFFE000u, h1 = x1 & 0xFFFFE000u, h2 = x2 & 0xFFFFE000u,
                            h3 = x3 & 0xFFFFE000u;
             const uint32_t l0 = __float_as_uint(__uint_as_float(x0) - __uint_as_float(h0)) & 0xFFFFE000u;
             const uint32_t l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1)) & 0xFFFFE000u;
             const uint32_t l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2)) & 0xFFFFE000u;
             const uint32_t l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3)) & 0xFFFFE000u;
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 16u * i), "r"(h0),
-                         "r"(h1), "r"(h2), "r"(h3) : "memory");
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + tile_bytes + 16u * i),
                          "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
           }
@@ -336,52 +377,56 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       float* Cg = P.C + sp * P.c_sstride + g * P.c_gstride;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                            static_cast<uint32_t>(as * P.chains * P.BN);
+                            static_cast<uint32_t>(as * P.chains * P.cstride);
       // chains that received at least one k-step of this tile
       const int nsteps = (min(P.kb_total, sp * P.kb_per_split + P.kb_per_split) - sp * P.kb_per_split) *
                          (kBK / kUmmaK);
       const int used_hi = min(P.chains_hi, nsteps);
       const int used_x = (P.precise && chains_x > 0) ? min(chains_x, nsteps) : 0;
-      for (int c = 0; c < P.BN / 32; ++c) {
+      for (int c = 0; c * 32 < P.BN; ++c) {
         if (n0 + c * 32 >= P.N) break;                 // warp-uniform
+        const bool full = c * 32 + 32 <= P.BN;         // else: 16-column tail (BN = odd multiple of 16)
         uint32_t v[32];
-        tmem_ld32(trow + c * 32, v);
+        tmem_ld_cols(trow + c * 32, v, full);
         for (int chn = 1; chn < used_hi + used_x; ++chn) {
           const int cc = chn < used_hi ? chn : P.chains_hi + (chn - used_hi);
           uint32_t w[32];
-          tmem_ld32(trow + cc * P.BN + c * 32, w);
+          tmem_ld_cols(trow + cc * P.cstride + c * 32, w, full);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
         }
         const int nb = n0 + c * 32;
+        const int wcols = full ? 32 : 16;
         if (!P.c_nm) {
           if (m < P.M) {
             float* dst = Cg + static_cast<long long>(m) * P.ldc + nb;
-            const bool vec = (nb + 32 <= P.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+            const bool vec = (nb + wcols <= P.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
             if (vec) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dst + i) =
-                    make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                if (i < wcols)
+                  *reinterpret_cast<float4*>(dst + i) =
+                      make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                  __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (nb + i < P.N) dst[i] = __uint_as_float(v[i]);
+                if (i < wcols && nb + i < P.N) dst[i] = __uint_as_float(v[i]);
             }
           }
         } else {
           if (m < P.M) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (nb + i < P.N) Cg[static_cast<long long>(nb + i) * P.ldc + m] = __uint_as_float(v[i]);
+              if (i < wcols && nb + i < P.N)
+                Cg[static_cast<long long>(nb + i) * P.ldc + m] = __uint_as_float(v[i]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == P.acc_stages) { as = 0; aphase ^= 1u; }
     }
   }
 
@@ -459,38 +504,75 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   GemmParams P = {};
   P.M = (int)M; P.N = (int)N; P.K = (int)K; P.G = G;
   P.a_mn = a_major; P.b_mn = b_major;
-  int bn = (int)((N + 31) / 32 * 32);
-  if (bn > 256) bn = 256;
-  P.BN = bn;
   P.m_tiles = (int)((M + kBM - 1) / kBM);
-  P.n_tiles = (int)((N + bn - 1) / bn);
   P.kb_total = (int)((K + kBK - 1) / kBK);
   if (splits > P.kb_total) splits = P.kb_total;
   P.kb_per_split = (P.kb_total + splits - 1) / splits;
   P.splits = (P.kb_total + P.kb_per_split - 1) / P.kb_per_split;   // no empty split
-  BDP_REQUIRE(P.splits == splits || c_sstride == 0 || true, "gemm_tf32: internal");
+  // Tile width: the B operand carries the big matrix (the weights) in fprop / dgrad, and every CTA
+  // streams its BN rows of it exactly once, so the best width is the one that keeps the most SMs
+  // streaming for the fewest waves: minimise ceil(tiles / SMs) * (BN + 16) (ties: wider tile).
+  const int sms = bdp_num_sms();
+  const int bn_step = b_major ? 32 : 16;              // MN-major B arrives in 32-wide TMA boxes
+  // Precise mode bounds the number of k-steps one TMEM accumulator chain absorbs (each MMA adds its
+  // partial sum with truncation: ~64 steps keep the drift near 3e-6 of the result scale), which caps
+  // the tile width: `need` chains of roundup32(BN) columns must fit the 512 TMEM columns.
+  const int steps = P.kb_per_split * (kBK / kUmmaK);
+  int need = 1;
+  if (precise) {
+    int need_hi = (steps + 63) / 64;
+    if (need_hi > 6) need_hi = 6;
+    need = need_hi + 1;                               // + one chain for the hi*lo cross terms
+  }
+  int bn = 0;
+  long long best_cost = 0;
+  for (int cand = 256; cand >= bn_step; cand -= bn_step) {
+    if (cand > (int)((N + bn_step - 1) / bn_step * bn_step)) continue;
+    if (((cand + 31) / 32 * 32) * need > 512 && cand > bn_step) continue;
+    const long long tiles = (long long)G * P.m_tiles * ((N + cand - 1) / cand) * P.splits;
+    const long long cost = ((tiles + sms - 1) / sms) * (cand + 16);
+    if (bn == 0 || cost < best_cost) { bn = cand; best_cost = cost; }
+  }
+  P.BN = bn;
+  P.n_tiles = (int)((N + bn - 1) / bn);
   P.a_g = (a_gstride != 0 || G == 1) ? 1 : 0;
   P.b_g = (b_gstride != 0 || G == 1) ? 1 : 0;
   P.C = C; P.ldc = ldc; P.c_gstride = c_gstride; P.c_sstride = c_sstride; P.c_nm = c_layout;
-
   P.precise = precise ? 1 : 0;
-  P.chains = 256 / bn;                               // 2 accumulator stages * chains * BN <= 512 columns
+  { const char* e = getenv("BDP_GEMM_NO_ROTATE"); P.k_rotate = (e && e[0] == '1') ? 0 : 1; }
+  // small-M problems (M = batch) fetch only the rows that exist
+  if (P.m_tiles == 1) P.a_rows = a_major ? (int)((M + 31) / 32 * 32) : (int)((M + 7) / 8 * 8);
+  else P.a_rows = kBM;
+  P.a_bytes = a_major ? (P.a_rows / 32) * 4096 : (P.a_rows * kBK * 4 + 1023) / 1024 * 1024;
+  const long long total = (long long)G * P.m_tiles * P.n_tiles * P.splits;
+  long long grid = sms;
+  if (grid > total) grid = total;
+  P.cstride = (bn + 31) / 32 * 32;
+  // two accumulator stages (epilogue of tile i overlaps the mainloop of tile i+1) when a CTA runs
+  // several tiles and the chains still fit
+  P.acc_stages = (total > grid && 2 * need * P.cstride <= 512) ? 2 : 1;
+  P.chains = 512 / (P.acc_stages * P.cstride);
   if (P.chains < 1) P.chains = 1;
   if (P.chains > 8) P.chains = 8;
   P.chains_hi = (precise && P.chains >= 2) ? P.chains - (P.chains >= 4 ? P.chains / 4 : 1) : P.chains;
-  const size_t stage_bytes = ((size_t)kABytes + (size_t)bn * kBK * 4) * (precise ? 2 : 1);
-  int stages = (int)((208 * 1024) / stage_bytes);
+
+  const size_t stage_bytes = ((size_t)P.a_bytes + (size_t)bn * kBK * 4) * (precise ? 2 : 1);
+  // The MMA always reads 128 A rows from shared memory (rows >= a_rows produce discarded D rows), so
+  // a shrunk A reservation is followed by `slack` bytes that keep those reads inside the allocation.
+  const size_t slack = (size_t)(kABytes - P.a_bytes);
+  const size_t fixed = 1024 + 8 * (3 * kMaxStages + 4) + slack;
+  int stages = (int)((224 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   P.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024 + 8 * (3 * kMaxStages + 4);
+  const size_t smem = stages * stage_bytes + fixed;
 
   CUtensorMap tmA, tmB;
   const uint64_t ga = P.a_g ? (uint64_t)G : 1, gb = P.b_g ? (uint64_t)G : 1;
   const uint64_t a_gs = a_gstride ? (uint64_t)a_gstride : (uint64_t)a_ld * (uint64_t)(a_major ? K : M);
   const uint64_t b_gs = b_gstride ? (uint64_t)b_gstride : (uint64_t)b_ld * (uint64_t)(b_major ? K : N);
   int st;
-  if (!a_major) st = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, ga, (uint64_t)a_ld, a_gs, kBK, kBM, false);
+  if (!a_major) st = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, ga, (uint64_t)a_ld, a_gs, kBK, (uint32_t)P.a_rows, false);
   else st = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, ga, (uint64_t)a_ld, a_gs, 32, kBK, true);
   if (st != BDP_OK) return st;
   if (!b_major) st = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, gb, (uint64_t)b_ld, b_gs, kBK, (uint32_t)bn, false);
@@ -506,9 +588,6 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
                                        227 * 1024 - (int)fa.sharedSizeBytes));
     attr_set = true;
   }
-  const long long total = (long long)G * P.m_tiles * P.n_tiles * P.splits;
-  long long grid = bdp_num_sms();
-  if (grid > total) grid = total;
   gemm_tf32_kernel<<<(unsigned)grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       tmA, tmB, P);
   BDP_CUDA_CHECK_LAUNCH("gemm_tf32_kernel");

@@ -1,7 +1,8 @@
 // (a) The CUDA-core pieces around the tcgen05 GEMMs of the bin-delta heads: BatchNorm1d+ReLU
-// forward/backward on feature-major activations, the label-selected / soft-mixed fc3, and the
-// split-K slab sum.  Activation tensors are [features, ldb] with the batch contiguous, so every
-// BatchNorm reduction is a reduction along one short row (B <= a few hundred): one warp per feature.
+// forward/backward, the label-selected / soft-mixed fc3, and the split-K slab sum.  Activations are
+// batch-major [B, F] (the torch layout; the GEMM puts the batch on the TMEM lanes and streams the
+// weights on the N side): a BatchNorm block owns 32 adjacent features (coalesced 128-byte rows) and
+// its 8 warps split the batch.
 //
 // Reference: binDeltaModels.py:62-91 (layers), 112-121 (stack + one-hot bmm select),
 // learnJointCatPoseModel_weighted.py:107-115 (softmax mixing); nn.BatchNorm1d defaults.
@@ -9,36 +10,46 @@
 
 namespace {
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kBnWarps = 8;
+
+// sum over the 8 warps of a block of per-thread partials; result broadcast to every warp
+__device__ __forceinline__ double block_col_sum(double v, double (*s)[32], int wy, int lane) {
+  __syncthreads();
+  s[wy][lane] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kBnWarps; ++w) t += s[w][lane];
+  return t;
+}
 
 // ---- BatchNorm + ReLU ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-bn_relu_fwd_kernel(const float* __restrict__ h, int64_t F, int B, int64_t ldb,
+__global__ void __launch_bounds__(kBnWarps * 32)
+bn_relu_fwd_kernel(const float* __restrict__ h, int64_t F, int B, int64_t ld,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ running_mean, float* __restrict__ running_var,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd, float eps,
                    float momentum, int training, float* __restrict__ a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (f >= F) return;
-  const float* row = h + f * ldb;
-  double mean, invstd;
+  __shared__ double s_red[kBnWarps][32];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int64_t f = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = f < F;
+  double mean = 0.0, invstd = 1.0;
   if (training) {
     // statistics in double (what torch's CPU kernel accumulates in; its CUDA kernel's Welford in
     // float agrees to ~1e-7)
-    double s = 0.0;
-    for (int b = lane; b < B; b += 32) s += (double)row[b];
-    s = warp_sum(s);
-    mean = s / (double)B;
-    double v = 0.0;
-    for (int b = lane; b < B; b += 32) {
-      const double d = (double)row[b] - mean;
-      v += d * d;
+    double sacc = 0.0;
+    if (ok) for (int b = wy; b < B; b += kBnWarps) sacc += (double)h[(int64_t)b * ld + f];
+    mean = block_col_sum(sacc, s_red, wy, lane) / (double)B;
+    double vacc = 0.0;
+    if (ok) for (int b = wy; b < B; b += kBnWarps) {
+      const double d = (double)h[(int64_t)b * ld + f] - mean;
+      vacc += d * d;
     }
-    v = warp_sum(v);
+    const double v = block_col_sum(vacc, s_red, wy, lane);
     const double var = v / (double)B;
     invstd = 1.0 / sqrt(var + (double)eps);
-    if (lane == 0) {
+    if (ok && wy == 0) {
       if (save_mean) save_mean[f] = (float)mean;
       if (save_invstd) save_invstd[f] = (float)invstd;
       if (running_mean) running_mean[f] = (1.f - momentum) * running_mean[f] + momentum * (float)mean;
@@ -47,67 +58,63 @@ bn_relu_fwd_kernel(const float* __restrict__ h, int64_t F, int B, int64_t ldb,
         running_var[f] = (1.f - momentum) * running_var[f] + momentum * (float)unbiased;
       }
     }
-  } else {
+  } else if (ok) {
     mean = (double)running_mean[f];
     invstd = 1.0 / sqrt((double)running_var[f] + (double)eps);
   }
+  if (!ok) return;
   const float m = (float)mean, is = (float)invstd, g = gamma[f], bt = beta[f];
-  float* out = a + f * ldb;
-  for (int b = lane; b < (int)ldb; b += 32) {
-    float y = 0.f;
-    if (b < B) y = fmaxf((row[b] - m) * is * g + bt, 0.f);
-    out[b] = y;
+  for (int b = wy; b < B; b += kBnWarps) {
+    const int64_t i = (int64_t)b * ld + f;
+    a[i] = fmaxf((h[i] - m) * is * g + bt, 0.f);
   }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kBnWarps * 32)
 bn_relu_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a,
                    const float* __restrict__ h, const float* __restrict__ gamma,
                    const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
-                   int64_t F, int B, int64_t ldb, int training, float* __restrict__ dh,
+                   int64_t F, int B, int64_t ld, int training, float* __restrict__ dh,
                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int lane = threadIdx.x & 31;
-  const int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (f >= F) return;
-  const float* dar = da + f * ldb;
-  const float* ar = a + f * ldb;
-  const float* hr = h + f * ldb;
-  const float m = save_mean[f], is = save_invstd[f], g = gamma[f];
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = lane; b < B; b += 32) {
-    const float dy = ar[b] > 0.f ? dar[b] : 0.f;      // relu'(x) = 1[x > 0]
-    const float xh = (hr[b] - m) * is;
-    s1 += (double)dy;
-    s2 += (double)dy * (double)xh;
+  __shared__ double s_red[kBnWarps][32];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int64_t f = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = f < F;
+  const float m = ok ? save_mean[f] : 0.f, is = ok ? save_invstd[f] : 1.f, g = ok ? gamma[f] : 0.f;
+  double a1 = 0.0, a2 = 0.0;
+  if (ok) for (int b = wy; b < B; b += kBnWarps) {
+    const int64_t i = (int64_t)b * ld + f;
+    const float dy = a[i] > 0.f ? da[i] : 0.f;        // relu'(x) = 1[x > 0]
+    const float xh = (h[i] - m) * is;
+    a1 += (double)dy;
+    a2 += (double)dy * (double)xh;
   }
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if (lane == 0) {
+  const double s1 = block_col_sum(a1, s_red, wy, lane);
+  const double s2 = block_col_sum(a2, s_red, wy, lane);
+  if (!ok) return;
+  if (wy == 0) {
     if (dgamma) dgamma[f] = (float)s2;
     if (dbeta) dbeta[f] = (float)s1;
   }
   const float k1 = training ? (float)(s1 / (double)B) : 0.f;
   const float k2 = training ? (float)(s2 / (double)B) : 0.f;
-  float* out = dh + f * ldb;
-  for (int b = lane; b < (int)ldb; b += 32) {
-    float v = 0.f;
-    if (b < B) {
-      const float dy = ar[b] > 0.f ? dar[b] : 0.f;
-      const float xh = (hr[b] - m) * is;
-      v = g * is * (dy - k1 - xh * k2);
-    }
-    out[b] = v;
+  for (int b = wy; b < B; b += kBnWarps) {
+    const int64_t i = (int64_t)b * ld + f;
+    const float dy = a[i] > 0.f ? da[i] : 0.f;
+    const float xh = (h[i] - m) * is;
+    dh[i] = g * is * (dy - k1 - xh * k2);
   }
 }
 
 // ---- fc3 + mixing ---------------------------------------------------------------------------------
+// a2 is [B, ld] batch-major; the activations of head hd are columns [col0 + hd*N2, col0 + (hd+1)*N2)
 constexpr int kFc3OutPerBlock = 32;
 
 __global__ void __launch_bounds__(256)
-fc3_fwd_kernel(const float* __restrict__ a2, int64_t ldb, const float* __restrict__ w3,
+fc3_fwd_kernel(const float* __restrict__ a2, int64_t ld, const float* __restrict__ w3,
                const float* __restrict__ b3, const float* __restrict__ mix, int H, int O, int N2,
                float* __restrict__ y) {
-  extern __shared__ float s_col[];                    // [N2] activation column of (head, sample)
+  extern __shared__ float s_col[];                    // [N2] activations of (sample, head)
   const int b = blockIdx.y;
   const int o0 = blockIdx.x * kFc3OutPerBlock;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,7 +124,7 @@ fc3_fwd_kernel(const float* __restrict__ a2, int64_t ldb, const float* __restric
     if (p == 0.f) continue;                           // block-uniform
     __syncthreads();
     for (int j = threadIdx.x; j < N2; j += blockDim.x)
-      s_col[j] = a2[((int64_t)hd * N2 + j) * ldb + b];
+      s_col[j] = a2[(int64_t)b * ld + (int64_t)hd * N2 + j];
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kFc3OutPerBlock / 8; ++i) {
@@ -139,29 +146,33 @@ fc3_fwd_kernel(const float* __restrict__ a2, int64_t ldb, const float* __restric
   }
 }
 
-// da2 column of every (head, sample) pair with a non-zero mixing weight (da2 is pre-zeroed)
+// da2[b, hd*N2 + j] = mix[b,hd] * sum_o dy[b,o] w3[hd,o,j]   (zeros where the mixing weight is 0)
 __global__ void __launch_bounds__(256)
 fc3_bwd_act_kernel(const float* __restrict__ dy, const float* __restrict__ w3,
-                   const float* __restrict__ mix, int64_t ldb, int H, int O, int N2,
+                   const float* __restrict__ mix, int64_t ld, int H, int O, int N2,
                    float* __restrict__ da2) {
   extern __shared__ float s_dy[];                     // [O]
   const int hd = blockIdx.x, b = blockIdx.y;
   const float p = mix[(int64_t)b * H + hd];
-  if (p == 0.f) return;
+  float* out = da2 + (int64_t)b * ld + (int64_t)hd * N2;
+  if (p == 0.f) {
+    for (int j = threadIdx.x; j < N2; j += blockDim.x) out[j] = 0.f;
+    return;
+  }
   for (int o = threadIdx.x; o < O; o += blockDim.x) s_dy[o] = p * dy[(int64_t)b * O + o];
   __syncthreads();
   for (int j = threadIdx.x; j < N2; j += blockDim.x) {
     const float* w = w3 + (int64_t)hd * O * N2 + j;
     float d = 0.f;
     for (int o = 0; o < O; ++o) d = fmaf(s_dy[o], w[(int64_t)o * N2], d);
-    da2[((int64_t)hd * N2 + j) * ldb + b] = d;
+    out[j] = d;
   }
 }
 
 constexpr int kFc3WOut = 8;   // outputs per block in the weight-gradient kernel
 
 __global__ void __launch_bounds__(256)
-fc3_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int64_t ldb,
+fc3_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int64_t ld,
                  const float* __restrict__ mix, int B, int H, int O, int N2,
                  float* __restrict__ dw3, float* __restrict__ db3) {
   extern __shared__ float s_pd[];                     // [B][kFc3WOut] mix * dy
@@ -174,12 +185,12 @@ fc3_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int
   }
   __syncthreads();
   for (int j = threadIdx.x; j < N2; j += blockDim.x) {
-    const float* ar = a2 + ((int64_t)hd * N2 + j) * ldb;
+    const float* ac = a2 + (int64_t)hd * N2 + j;
     float acc[kFc3WOut];
 #pragma unroll
     for (int oo = 0; oo < kFc3WOut; ++oo) acc[oo] = 0.f;
     for (int b = 0; b < B; ++b) {
-      const float av = ar[b];
+      const float av = ac[(int64_t)b * ld];           // coalesced over j
 #pragma unroll
       for (int oo = 0; oo < kFc3WOut; ++oo) acc[oo] = fmaf(s_pd[b * kFc3WOut + oo], av, acc[oo]);
     }
@@ -194,16 +205,17 @@ fc3_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int
   }
 }
 
-// dmix[b, h] = sum_o dy[b,o] * (b3[h,o] + w3[h,o,:] . a2[h,:,b])
+// dmix[b, h] = sum_o dy[b,o] * (b3[h,o] + w3[h,o,:] . a2[b, h*N2 : (h+1)*N2])
 __global__ void __launch_bounds__(256)
-fc3_bwd_mix_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int64_t ldb,
+fc3_bwd_mix_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int64_t ld,
                    const float* __restrict__ w3, const float* __restrict__ b3, int H, int O, int N2,
                    float* __restrict__ dmix) {
   extern __shared__ float s_col[];                    // [N2]
   __shared__ float s_part[8];
   const int hd = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = threadIdx.x; j < N2; j += blockDim.x) s_col[j] = a2[((int64_t)hd * N2 + j) * ldb + b];
+  for (int j = threadIdx.x; j < N2; j += blockDim.x)
+    s_col[j] = a2[(int64_t)b * ld + (int64_t)hd * N2 + j];
   __syncthreads();
   float acc = 0.f;
   for (int o = warp; o < O; o += 8) {
@@ -235,17 +247,17 @@ sum_slabs_kernel(const float* __restrict__ parts, int64_t n, int S, int64_t stri
 
 }  // namespace
 
-extern "C" int bdp_bn_relu_fwd(const float* h, int64_t F, int64_t B, int64_t ldb,
+extern "C" int bdp_bn_relu_fwd(const float* h, int64_t F, int64_t B, int64_t ld,
                                const float* gamma, const float* beta, float* running_mean,
                                float* running_var, float* save_mean, float* save_invstd, float eps,
                                float momentum, int training, float* a, void* stream) {
   BDP_REQUIRE(h && gamma && beta && a, "bn_relu_fwd: NULL buffer");
-  BDP_REQUIRE(F > 0 && B > 0 && ldb >= B, "bn_relu_fwd: bad sizes F=%lld B=%lld ldb=%lld",
-              (long long)F, (long long)B, (long long)ldb);
+  BDP_REQUIRE(F > 0 && B > 0 && ld >= F, "bn_relu_fwd: bad sizes F=%lld B=%lld ld=%lld",
+              (long long)F, (long long)B, (long long)ld);
   BDP_REQUIRE(training || (running_mean && running_var), "bn_relu_fwd: eval mode needs running stats");
-  const unsigned blocks = (unsigned)ceil_div64(F, kWarpsPerBlock);
-  bn_relu_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      h, F, (int)B, ldb, gamma, beta, running_mean, running_var, save_mean, save_invstd, eps,
+  const unsigned blocks = (unsigned)ceil_div64(F, 32);
+  bn_relu_fwd_kernel<<<blocks, kBnWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      h, F, (int)B, ld, gamma, beta, running_mean, running_var, save_mean, save_invstd, eps,
       momentum, training, a);
   BDP_CUDA_CHECK_LAUNCH("bn_relu_fwd_kernel");
   return BDP_OK;
@@ -253,18 +265,18 @@ extern "C" int bdp_bn_relu_fwd(const float* h, int64_t F, int64_t B, int64_t ldb
 
 extern "C" int bdp_bn_relu_bwd(const float* da, const float* a, const float* h, const float* gamma,
                                const float* save_mean, const float* save_invstd, int64_t F,
-                               int64_t B, int64_t ldb, int training, float* dh, float* dgamma,
+                               int64_t B, int64_t ld, int training, float* dh, float* dgamma,
                                float* dbeta, void* stream) {
   BDP_REQUIRE(da && a && h && gamma && save_mean && save_invstd && dh, "bn_relu_bwd: NULL buffer");
-  BDP_REQUIRE(F > 0 && B > 0 && ldb >= B, "bn_relu_bwd: bad sizes");
-  const unsigned blocks = (unsigned)ceil_div64(F, kWarpsPerBlock);
-  bn_relu_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      da, a, h, gamma, save_mean, save_invstd, F, (int)B, ldb, training, dh, dgamma, dbeta);
+  BDP_REQUIRE(F > 0 && B > 0 && ld >= F, "bn_relu_bwd: bad sizes");
+  const unsigned blocks = (unsigned)ceil_div64(F, 32);
+  bn_relu_bwd_kernel<<<blocks, kBnWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      da, a, h, gamma, save_mean, save_invstd, F, (int)B, ld, training, dh, dgamma, dbeta);
   BDP_CUDA_CHECK_LAUNCH("bn_relu_bwd_kernel");
   return BDP_OK;
 }
 
-extern "C" int bdp_head_fc3_fwd(const float* a2, int64_t ldb, const float* w3, const float* b3,
+extern "C" int bdp_head_fc3_fwd(const float* a2, int64_t ld, const float* w3, const float* b3,
                                 const float* mix, int64_t B, int H, int O, int N2, float* y,
                                 void* stream) {
   BDP_REQUIRE(a2 && w3 && b3 && mix && y, "head_fc3_fwd: NULL buffer");
@@ -272,12 +284,12 @@ extern "C" int bdp_head_fc3_fwd(const float* a2, int64_t ldb, const float* w3, c
               "head_fc3_fwd: bad sizes B=%lld H=%d O=%d N2=%d", (long long)B, H, O, N2);
   dim3 grid((unsigned)((O + kFc3OutPerBlock - 1) / kFc3OutPerBlock), (unsigned)B);
   fc3_fwd_kernel<<<grid, 256, N2 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
-      a2, ldb, w3, b3, mix, H, O, N2, y);
+      a2, ld, w3, b3, mix, H, O, N2, y);
   BDP_CUDA_CHECK_LAUNCH("fc3_fwd_kernel");
   return BDP_OK;
 }
 
-extern "C" int bdp_head_fc3_bwd(const float* dy, const float* a2, int64_t ldb, const float* w3,
+extern "C" int bdp_head_fc3_bwd(const float* dy, const float* a2, int64_t ld, const float* w3,
                                 const float* b3, const float* mix, int64_t B, int H, int O, int N2,
                                 float* da2, float* dw3, float* db3, float* dmix, void* stream) {
   BDP_REQUIRE(dy && a2 && w3 && b3 && mix, "head_fc3_bwd: NULL buffer");
@@ -286,20 +298,19 @@ extern "C" int bdp_head_fc3_bwd(const float* dy, const float* a2, int64_t ldb, c
   BDP_REQUIRE((size_t)B * kFc3WOut * 4 <= 48 * 1024, "head_fc3_bwd: batch too large (%lld)", (long long)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (da2) {
-    BDP_CUDA_CALL(cudaMemsetAsync(da2, 0, (size_t)H * N2 * ldb * sizeof(float), st));
-    fc3_bwd_act_kernel<<<dim3(H, (unsigned)B), 256, O * sizeof(float), st>>>(dy, w3, mix, ldb, H, O,
+    fc3_bwd_act_kernel<<<dim3(H, (unsigned)B), 256, O * sizeof(float), st>>>(dy, w3, mix, ld, H, O,
                                                                             N2, da2);
     BDP_CUDA_CHECK_LAUNCH("fc3_bwd_act_kernel");
   }
   if (dw3) {
     BDP_REQUIRE(db3 != nullptr, "head_fc3_bwd: db3 is NULL");
     fc3_bwd_w_kernel<<<dim3(H, (unsigned)((O + kFc3WOut - 1) / kFc3WOut)), 256,
-                       (size_t)B * kFc3WOut * sizeof(float), st>>>(dy, a2, ldb, mix, (int)B, H, O,
+                       (size_t)B * kFc3WOut * sizeof(float), st>>>(dy, a2, ld, mix, (int)B, H, O,
                                                                    N2, dw3, db3);
     BDP_CUDA_CHECK_LAUNCH("fc3_bwd_w_kernel");
   }
   if (dmix) {
-    fc3_bwd_mix_kernel<<<dim3(H, (unsigned)B), 256, N2 * sizeof(float), st>>>(dy, a2, ldb, w3, b3, H,
+    fc3_bwd_mix_kernel<<<dim3(H, (unsigned)B), 256, N2 * sizeof(float), st>>>(dy, a2, ld, w3, b3, H,
                                                                              O, N2, dmix);
     BDP_CUDA_CHECK_LAUNCH("fc3_bwd_mix_kernel");
   }

@@ -1,0 +1,99 @@
+# -*- coding: utf-8 -*-
+"""Drop-in for the MODEL classes of the reference's objectnetHelperFunctions module
+(objectnetHelperFunctions.py:110-231): ObjectNet3D heads take cat(features, onehot(label)) as input
+and use ONE bin / res MLP pair for all 100 categories.  The pair runs as a two-head stack on the
+tcgen05 head kernels.  The dataset classes of that module (TrainImages / TestImages: disk I/O) stay
+the reference's own."""
+import numpy as np
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from bdpose import head as _head
+from binDeltaModels import bin_3layer, res_3layer, res_2layer, _feature_model   # noqa: F401
+
+
+def _cat_onehot(feat, label, num_classes):
+    return torch.cat((feat, _head.onehot(label, num_classes)), dim=1)
+
+
+class OneBinDeltaModel(nn.Module):
+    """objectnetHelperFunctions.py:155-172"""
+
+    def __init__(self, num_classes, dict_size=200, n0=2048, n1=1000, n2=500, dim=3):
+        super().__init__()
+        self.num_classes = num_classes
+        self.num_clusters = dict_size
+        fm = _feature_model('resnet')
+        if fm is not None:
+            self.feature_model = fm
+        self.bin_model = bin_3layer(n0 + num_classes, n1, n2, self.num_clusters).cuda()
+        self.res_model = res_3layer(n0 + num_classes, n1, n2, dim).cuda()
+        object.__setattr__(self, '_stack', None)
+
+    def forward_features(self, feat, label):
+        st = self.__dict__.get('_stack')
+        if st is None or st.heads[0] is not self.bin_model or st.heads[1] is not self.res_model:
+            st = _head.HeadStack([[self.bin_model], [self.res_model]])
+            object.__setattr__(self, '_stack', st)
+        x = _cat_onehot(feat, label, self.num_classes)
+        ones = torch.ones(x.shape[0], 1, device=x.device)
+        y1, y2 = _head.run_heads(st, x, ones, self.training)
+        return [y1, y2]
+
+    def forward(self, x, label):
+        return self.forward_features(self.feature_model(x), label)
+
+
+class RegressionModel(nn.Module):
+    """objectnetHelperFunctions.py:201-215: pi * tanh(res_3layer(cat(features, onehot)))"""
+
+    def __init__(self, num_classes, n0=2048, n1=1000, n2=500, dim=3):
+        super().__init__()
+        self.num_classes = num_classes
+        fm = _feature_model('resnet')
+        if fm is not None:
+            self.feature_model = fm
+        self.pose_model = res_3layer(n0 + num_classes, n1, n2, dim).cuda()
+
+    def forward(self, x, label):
+        x = _cat_onehot(self.feature_model(x), label, self.num_classes)
+        return np.pi * torch.tanh(self.pose_model(x))
+
+
+class ClassificationModel(nn.Module):
+    """objectnetHelperFunctions.py:218-231"""
+
+    def __init__(self, num_classes, dict_size=16, n0=2048, n1=1000, n2=500):
+        super().__init__()
+        self.num_classes = num_classes
+        fm = _feature_model('resnet')
+        if fm is not None:
+            self.feature_model = fm
+        self.pose_model = bin_3layer(n0 + num_classes, n1, n2, dict_size).cuda()
+
+    def forward(self, x, label):
+        return self.pose_model(_cat_onehot(self.feature_model(x), label, self.num_classes))
+
+
+class OneDeltaPerBinModel(nn.Module):
+    """objectnetHelperFunctions.py:175-198: one bin head + dict_size res_2layer heads, delta picked by
+    the argmax bin (the small per-bin heads stay on stock torch layers)."""
+
+    def __init__(self, num_classes, dict_size=16, n0=2048, n1=1000, n2=500, n3=100, dim=3):
+        super().__init__()
+        self.ndim = dim
+        self.num_classes = num_classes
+        self.num_clusters = dict_size
+        fm = _feature_model('resnet')
+        if fm is not None:
+            self.feature_model = fm
+        self.bin_model = bin_3layer(n0 + num_classes, n1, n2, self.num_clusters).cuda()
+        self.res_models = nn.ModuleList([res_2layer(n0 + num_classes, n3, dim) for i in range(self.num_clusters)]).cuda()
+
+    def forward(self, x, label):
+        x = _cat_onehot(self.feature_model(x), label, self.num_classes)
+        y1 = self.bin_model(x)
+        y2 = torch.stack([m(x) for m in self.res_models]).permute(1, 2, 0)        # [B, dim, K]
+        pose = _head.onehot(torch.argmax(y1, dim=1, keepdim=True), self.num_clusters).unsqueeze(2)
+        return [y1, torch.squeeze(torch.bmm(y2, pose), 2)]

@@ -74,6 +74,15 @@ def _operand(rows, K, G, major, dev, gen):
     (2048, 48, 3000, 1, 1, 1, 1, 5),         # fc1 dgrad: split-K partials, transposed store
     (200, 96, 100, 2, 0, 0, 1, 1),
     (132, 260, 36, 1, 1, 0, 0, 1),
+    # batch-major shape classes: the batch on the lanes (small M), the weights streamed on the N side
+    (32, 3000, 2048, 1, 0, 0, 0, 1),         # fc1
+    (37, 24000, 256, 1, 0, 0, 0, 1),         # fc1, one wave of wide tiles over all SMs, ragged M
+    (96, 500, 1000, 3, 0, 0, 0, 1),          # fc2 grouped
+    (32, 1000, 500, 2, 0, 1, 0, 1),          # fc2 dgrad (weights MN-major)
+    (500, 1000, 37, 2, 1, 1, 0, 1),          # fc2 wgrad (both MN-major, K = ragged batch)
+    (3000, 2048, 32, 1, 1, 1, 0, 1),         # fc1 wgrad
+    (48, 2048, 3000, 1, 0, 1, 0, 5),         # fc1 dgrad, split-K
+    (200, 1000, 256, 1, 0, 0, 0, 1),         # batch > 128: two lane tiles
 ])
 @pytest.mark.parametrize("precise", [True, False])
 def test_gemm_tf32(cuda, M, N, K, G, am, bm, cl, splits, precise):
@@ -111,10 +120,32 @@ def test_gemm_shared_operand_and_padding(cuda):
     assert float(C[:, :, N:].abs().max()) == 0.0
 
 
+def test_gemm_column_window_groups(cuda):
+    """Grouped GEMM whose A and C groups are column windows of one batch-major buffer (group stride
+    smaller than the row pitch): the fc2 layout, H2[:, g*N2:(g+1)*N2] = A1[:, g*N1:(g+1)*N1] W2_g^T."""
+    from bdpose import head
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    G, Bt, N1, N2 = 4, 37, 200, 100
+    a1 = torch.randn(Bt, G * N1, device=cuda, generator=gen)
+    w2 = torch.randn(G, N2, N1, device=cuda, generator=gen)
+    ref = torch.einsum("bgk,gnk->bgn", a1.view(Bt, G, N1).double(), w2.double()).reshape(Bt, G * N2)
+    for precise in (True, False):
+        h2 = torch.full((Bt, G * N2), float("nan"), device=cuda)
+        head.gemm_tf32(a1, 0, G * N1, N1, w2, 0, N1, N2 * N1, h2, 0, G * N2, N2, Bt, N2, N1, G=G,
+                       precise=precise)
+        scale_close(h2, ref, FP32_TOL if precise else TF32_TOL, "fc2 windows")
+    # wgrad over the same windows: dW2_g = dH2_g^T A1_g (both MN-major, K = batch)
+    dh2 = torch.randn(Bt, G * N2, device=cuda, generator=gen)
+    dw = torch.full((G, N2, N1), float("nan"), device=cuda)
+    head.gemm_tf32(dh2, 1, G * N2, N2, a1, 1, G * N1, N1, dw, 0, N1, N2 * N1, N2, N1, Bt, G=G)
+    refw = torch.einsum("bgn,bgk->gnk", dh2.view(Bt, G, N2).double(), a1.view(Bt, G, N1).double())
+    scale_close(dw, refw, FP32_TOL, "fc2 wgrad windows")
+
+
 def test_bn_relu_vs_torch(cuda):
     from bdpose import head
     torch.manual_seed(0)
-    F, B, ldb = 300, 37, 40
+    F, B, ld = 300, 37, 320                       # a column window of a wider [B, ld] buffer
     h = torch.randn(B, F, device=cuda, dtype=torch.float32) * 2 + 0.5
     bn = torch.nn.BatchNorm1d(F).to(cuda)
     bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.uniform_(-0.5, 0.5)
@@ -123,31 +154,30 @@ def test_bn_relu_vs_torch(cuda):
     y = torch.relu(bn(hx))
     w = torch.randn_like(y)
     (y * w).sum().backward()
-    hT = torch.zeros(F, ldb, device=cuda); hT[:, :B] = h.t()
+    hp = torch.zeros(B, ld, device=cuda)[:, :F]; hp.copy_(h)
     rm, rv = rm0.clone(), rv0.clone()
-    a, mean, invstd = head.bn_relu_fwd(hT, B, bn.weight.data, bn.bias.data, rm, rv, True)
-    torch.testing.assert_close(a[:, :B].t(), y.detach(), rtol=1e-5, atol=1e-6)
-    assert float(a[:, B:].abs().max()) == 0
+    a, mean, invstd = head.bn_relu_fwd(hp, bn.weight.data, bn.bias.data, rm, rv, True)
+    torch.testing.assert_close(a, y.detach(), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(rm, bn.running_mean, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(rv, bn.running_var, rtol=1e-6, atol=1e-7)
-    daT = torch.zeros(F, ldb, device=cuda); daT[:, :B] = w.t()
-    dh, dg, db = head.bn_relu_bwd(daT, a, hT, bn.weight.data, mean, invstd, B, True)
-    torch.testing.assert_close(dh[:, :B].t(), hx.grad, rtol=1e-4, atol=1e-5 * float(hx.grad.abs().max()))
+    dap = torch.zeros(B, ld, device=cuda)[:, :F]; dap.copy_(w)
+    dh, dg, db = head.bn_relu_bwd(dap, a, hp, bn.weight.data, mean, invstd, True)
+    torch.testing.assert_close(dh, hx.grad, rtol=1e-4, atol=1e-5 * float(hx.grad.abs().max()))
     torch.testing.assert_close(dg, bn.weight.grad, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(db, bn.bias.grad, rtol=1e-4, atol=1e-5)
     # eval mode
     bn.eval()
     ye = torch.relu(bn(h))
-    ae, _, _ = head.bn_relu_fwd(hT, B, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, False)
-    torch.testing.assert_close(ae[:, :B].t(), ye, rtol=1e-5, atol=1e-6)
+    ae, _, _ = head.bn_relu_fwd(hp, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, False)
+    torch.testing.assert_close(ae, ye, rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("soft", [False, True])
 def test_fc3_mix_vs_torch(cuda, soft):
     from bdpose import head
     torch.manual_seed(1)
-    H, O, N2, B, ldb = 5, 37, 52, 9, 12
-    a2 = torch.rand(H, N2, B, device=cuda)
+    H, O, N2, B = 5, 37, 52, 9
+    a2 = torch.rand(B, H, N2, device=cuda)
     w3 = (torch.randn(H, O, N2, device=cuda) * 0.2).requires_grad_(True)
     b3 = torch.randn(H, O, device=cuda).requires_grad_(True)
     if soft:
@@ -156,18 +186,23 @@ def test_fc3_mix_vs_torch(cuda, soft):
         mix = torch.zeros(B, H, device=cuda).scatter_(1, torch.randint(0, H, (B, 1), device=cuda), 1.0)
     mix.requires_grad_(True)
     a2r = a2.clone().requires_grad_(True)
-    yh = torch.einsum("hoj,hjb->bho", w3, a2r) + b3[None]
+    yh = torch.einsum("hoj,bhj->bho", w3, a2r) + b3[None]
     y = (yh * mix[:, :, None]).sum(1)
     dy = torch.randn_like(y)
     (y * dy).sum().backward()
-    a2p = torch.zeros(H * N2, ldb, device=cuda); a2p[:, :B] = a2.reshape(H * N2, B)
-    yg = head.fc3_fwd(a2p, w3.detach(), b3.detach(), mix.detach(), B)
+    # the H heads are a column window [8, 8 + H*N2) of a wider stacked buffer
+    wide = torch.zeros(B, H * N2 + 20, device=cuda)
+    a2p = wide[:, 8:8 + H * N2]; a2p.copy_(a2.reshape(B, H * N2))
+    yg = head.fc3_fwd(a2p, w3.detach(), b3.detach(), mix.detach())
     torch.testing.assert_close(yg, y.detach(), rtol=1e-5, atol=1e-5)
-    da2, dw3, db3, dmix = head.fc3_bwd(dy, a2p, w3.detach(), b3.detach(), mix.detach(), B, True)
-    torch.testing.assert_close(da2[:, :B].reshape(H, N2, B), a2r.grad, rtol=1e-5, atol=1e-5)
+    dwide = torch.zeros_like(wide)
+    da2, dw3, db3, dmix = head.fc3_bwd(dy, a2p, w3.detach(), b3.detach(), mix.detach(), True,
+                                       da2=dwide[:, 8:8 + H * N2])
+    torch.testing.assert_close(da2.reshape(B, H, N2), a2r.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(dw3, w3.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(db3, b3.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(dmix, mix.grad, rtol=1e-5, atol=1e-5)
+    assert float(dwide[:, :8].abs().max()) == 0 and float(dwide[:, 8 + H * N2:].abs().max()) == 0
 
 
 # ---------------------------------------------------------------------------------------------------
