@@ -237,8 +237,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // few DRAM channels.
       const int nkb = kb1 - kb0;
       const int rot = P.k_rotate ? static_cast<int>((static_cast<unsigned>(t) * 13u) % static_cast<unsigned>(nkb)) : 0;
-      for (int i = 0; i < nkb; ++i) {
-        const int kb = kb0 + (i + rot) % nkb;
+      int kb = kb0 + rot;
+      for (int i = 0; i < nkb; ++i, ++kb) {
+        if (kb == kb1) kb = kb0;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = base + stage * stage_bytes;
         const uint32_t sb = sa + a_bytes;
@@ -268,9 +269,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                            (static_cast<uint32_t>(P.b_mn) << 16) |
                            (static_cast<uint32_t>(P.BN >> 3) << 17) |
                            (static_cast<uint32_t>(kBM >> 4) << 24);
-    const uint32_t a_lbo = P.a_mn ? 4096u : 16u, b_lbo = P.b_mn ? 4096u : 16u;
-    const uint32_t a_kstep = P.a_mn ? 1024u : kUmmaK * 4u;
-    const uint32_t b_kstep = P.b_mn ? 1024u : kUmmaK * 4u;
+    // Everything that does not change per k-step is hoisted: this single thread issues up to 12 MMAs
+    // per k-block and its scalar instruction stream is the pacing item in precise mode (runtime
+    // modulos and 64-bit descriptor assembly per MMA cost ~2500 cycles per k-block).
+    const uint64_t a_desc0 = umma_desc(0, P.a_mn ? 4096u : 16u, P.a_mn ? 512u : 1024u, P.a_mn ? 1u : 2u);
+    const uint64_t b_desc0 = umma_desc(0, P.b_mn ? 4096u : 16u, P.b_mn ? 512u : 1024u, P.b_mn ? 1u : 2u);
+    const uint32_t a_kstep16 = (P.a_mn ? 1024u : kUmmaK * 4u) >> 4;   // descriptor address units
+    const uint32_t b_kstep16 = (P.b_mn ? 1024u : kUmmaK * 4u) >> 4;
+    const uint32_t lo16 = tile_bytes >> 4;               // hi -> lo copy of the same operand
+    const uint32_t cstride = static_cast<uint32_t>(P.cstride);
+    const uint32_t hi_span = static_cast<uint32_t>(P.chains_hi) * cstride;
+    const uint32_t x_span = static_cast<uint32_t>(chains_x) * cstride;
+    const int precise = P.precise;
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -280,37 +290,41 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
-      const uint32_t tmem_t = tmem_base + static_cast<uint32_t>(as * P.chains * P.cstride);
-      uint32_t started = 0;                            // chains that already hold a partial sum
-      int step = 0;
+      const uint32_t tmem_t = tmem_base + static_cast<uint32_t>(as * P.chains) * cstride;
+      // chains are visited round-robin; a chain accumulates from its second visit on
+      uint32_t hi_col = 0, x_col = 0;
+      int hi_fresh = P.chains_hi, x_fresh = chains_x;   // chains not yet written in this tile
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(P.precise ? split_bar(stage) : full_bar(stage), phase);
+        mbar_wait(precise ? split_bar(stage) : full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + stage * stage_bytes;
-        const uint32_t sb = sa + a_bytes;
-        const uint32_t a_sbo = P.a_mn ? 512u : 1024u, a_lt = P.a_mn ? 1u : 2u;
-        const uint32_t b_sbo = P.b_mn ? 512u : 1024u, b_lt = P.b_mn ? 1u : 2u;
+        uint64_t ad = a_desc0 | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
+        uint64_t bd = b_desc0 | static_cast<uint64_t>(((sa + a_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
         for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t ad = umma_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
-          const uint64_t bd = umma_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
-          const int ch = step % P.chains_hi;
-          const uint32_t d_hi = tmem_t + static_cast<uint32_t>(ch * P.cstride);
-          if (P.precise) {
-            const int cx = chains_x > 0 ? P.chains_hi + step % chains_x : ch;
-            const uint32_t d_x = tmem_t + static_cast<uint32_t>(cx * P.cstride);
-            const uint64_t adl = umma_desc(sa + tile_bytes + k * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t bdl = umma_desc(sb + tile_bytes + k * b_kstep, b_lbo, b_sbo, b_lt);
-            umma_tf32(d_x, adl, bd, idesc, (started >> cx) & 1u);
-            started |= 1u << cx;
-            umma_tf32(d_x, ad, bdl, idesc, 1u);
-            umma_tf32(d_hi, ad, bd, idesc, (started >> ch) & 1u);
-            started |= 1u << ch;
+          const uint32_t d_hi = tmem_t + hi_col;
+          if (precise) {
+            if (x_span != 0) {
+              const uint32_t d_x = tmem_t + hi_span + x_col;
+              umma_tf32(d_x, ad + lo16, bd, idesc, x_fresh <= 0);
+              umma_tf32(d_x, ad, bd + lo16, idesc, 1u);
+              umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0);
+              --x_fresh;
+              x_col += cstride;
+              if (x_col == x_span) x_col = 0;
+            } else {                                     // a single chain takes everything
+              umma_tf32(d_hi, ad + lo16, bd, idesc, hi_fresh <= 0);
+              umma_tf32(d_hi, ad, bd + lo16, idesc, 1u);
+              umma_tf32(d_hi, ad, bd, idesc, 1u);
+            }
           } else {
-            umma_tf32(d_hi, ad, bd, idesc, (started >> ch) & 1u);
-            started |= 1u << ch;
+            umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0);
           }
-          ++step;
+          --hi_fresh;
+          hi_col += cstride;
+          if (hi_col == hi_span) hi_col = 0;
+          ad += a_kstep16;
+          bd += b_kstep16;
         }
         umma_commit(empty_bar(stage));                 // frees the smem slot when the MMAs retire
         if (kb == kb1 - 1) umma_commit(tfull_bar(as)); // accumulator complete -> epilogue
