@@ -178,6 +178,31 @@ int bdp_kmeans_lloyd_step(const double* x, int64_t N, int d, const double* cente
                           double* inertia, int update, void* stream);
 
 /*
+ * Key grid: candidate pruning for the nearest-key query (same labels as the brute-force entry points,
+ * ~5 candidate keys per rotation instead of K).  A uniform grid over the dictionary's bounding box
+ * stores, per cell, the ascending list of keys that can be nearest to some point of the cell; points
+ * outside the grid and cells with overflowing lists take the brute-force path inside the kernel.
+ *   bdp_keygrid_bytes(K, d)       device bytes the caller allocates for the grid (-1: unsupported;
+ *                                 supported: d = 3|4, 1 <= K <= 4096)
+ *   bdp_keygrid_build(...)        (re)builds the grid for `centers` [K, d] fp64 — three small
+ *                                 launches, no host synchronisation; rebuild whenever centers change
+ *   bdp_assign_nearest_grid       bdp_assign_nearest with a prebuilt grid (16-byte aligned)
+ *   bdp_kmeans_lloyd_step_grid    bdp_kmeans_lloyd_step with a prebuilt grid
+ * Replaces the same reference call sites as the brute-force forms (binDeltaGenerators.py:27-30,
+ * learnKmeansDictionary.py:41-42).
+ */
+int64_t bdp_keygrid_bytes(int K, int d);
+int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
+                      void* stream);
+int bdp_assign_nearest_grid(const void* x, int x_dtype, int64_t N, int d, const double* centers,
+                            int K, const void* grid, int64_t grid_bytes, int32_t* labels32,
+                            int64_t* labels64, float* residual, double* min_sqdist, void* stream);
+int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, const double* centers, int K,
+                               const void* grid, int64_t grid_bytes, int32_t* labels, int64_t* acc,
+                               int fix_hi_bits, int64_t* stats, double* inertia, int update,
+                               void* stream);
+
+/*
  * M-step finalisation on the device (no host round trip): centers_new = sum / count from the
  * fixed-point accumulators (exactly rounded sum, then one division), empty clusters take the
  * centre of the heaviest cluster (sklearn _average_centers), shift2[0] = sum ||new - old||^2,

@@ -39,14 +39,25 @@ class LloydState:
         self.n_empty = torch.zeros(1, dtype=torch.int64, device=dev)
 
 
-def lloyd_step(x, centers, state, fix_hi_bits, update=True):
-    """One E(+M-accumulate) step on this rank's shard.  Adds into state.acc / stats / inertia."""
+def lloyd_step(x, centers, state, fix_hi_bits, update=True, grid=None):
+    """One E(+M-accumulate) step on this rank's shard.  Adds into state.acc / stats / inertia.
+    grid: an ops.KeyGrid buffer to rebuild for `centers` and query through (candidate pruning), or
+    None for the brute-force scan — the labels are the same either way."""
     N, d = x.shape
     with torch.cuda.device(x.device):
-        st = L.lib().bdp_kmeans_lloyd_step(L.ptr(x), N, d, L.ptr(centers), centers.shape[0],
-                                           L.ptr(state.labels), L.ptr(state.acc), fix_hi_bits,
-                                           L.ptr(state.stats), L.ptr(state.inertia),
-                                           1 if update else 0, L.stream_ptr())
+        if grid is None:
+            st = L.lib().bdp_kmeans_lloyd_step(L.ptr(x), N, d, L.ptr(centers), centers.shape[0],
+                                               L.ptr(state.labels), L.ptr(state.acc), fix_hi_bits,
+                                               L.ptr(state.stats), L.ptr(state.inertia),
+                                               1 if update else 0, L.stream_ptr())
+        else:
+            grid.rebuild(centers)
+            st = L.lib().bdp_kmeans_lloyd_step_grid(L.ptr(x), N, d, L.ptr(grid.centers),
+                                                    centers.shape[0], L.ptr(grid.buf), grid.nbytes,
+                                                    L.ptr(state.labels), L.ptr(state.acc),
+                                                    fix_hi_bits, L.ptr(state.stats),
+                                                    L.ptr(state.inertia), 1 if update else 0,
+                                                    L.stream_ptr())
     L.check(st, "bdp_kmeans_lloyd_step")
 
 
@@ -117,7 +128,8 @@ def _relocate_empty(x, centers_old, state, fix_hi_bits, group):
         acc[new_id, 2 * d] = 1
 
 
-def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, center=True):
+def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, center=True,
+                 use_grid="auto"):
     """Lloyd k-means on this rank's shard `x` [N_local, d] fp64 (CUDA) from explicit centres.
 
     Returns dict(centers [K,d] fp64, labels [N_local] int32, inertia float, n_iter int).
@@ -152,12 +164,15 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
 
     state = LloydState(N, K, d, dev)
     centers_new = torch.empty_like(centers)
+    grid = None
+    if use_grid is True or (use_grid == "auto" and ops.KeyGrid.supported(K, d, N)):
+        grid = ops.KeyGrid(centers)
     strict = False
     n_iter = 0
     iters = fixed_iters if fixed_iters is not None else max_iter
     for it in range(iters):
         state.acc_stats.zero_()
-        lloyd_step(x, centers, state, hb, update=True)
+        lloyd_step(x, centers, state, hb, update=True, grid=grid)
         allreduce(state.acc_stats)
         finalize(state, centers, centers_new, hb)
         if fixed_iters is None:
@@ -181,7 +196,7 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     state.acc_stats.zero_()
     state.inertia.zero_()
     if not strict:
-        lloyd_step(x, centers, state, hb, update=False)
+        lloyd_step(x, centers, state, hb, update=False, grid=grid)
         inertia = allreduce(state.inertia.clone())
     else:
         lab = state.labels.long()

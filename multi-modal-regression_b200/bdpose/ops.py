@@ -217,10 +217,62 @@ def error_stats(err_deg, labels=None, num_classes=1):
 # ------------------------------------------------------------------------------------------------
 # (c) assignment
 # ------------------------------------------------------------------------------------------------
-def assign_nearest(x, centers, want_residual=True, want_sqdist=False, label_dtype=torch.int64):
+# Nearest-key queries go through the key grid (candidate pruning, include/bdpose.h) when the
+# dictionary and the batch are big enough for the three small build launches to pay off.
+GRID_MIN_K = 8
+GRID_MIN_N = 1 << 15
+_grid_ws = {}     # (device index, stream, bytes) -> grid buffer, reused (rebuilt on every call)
+
+
+class KeyGrid:
+    """Device buffer holding the key grid of one dictionary (bdp_keygrid_build)."""
+
+    def __init__(self, centers, buf=None):
+        _need_cuda(centers)
+        self.centers = centers.double().contiguous()
+        self.K, self.d = self.centers.shape
+        self.nbytes = L.lib().bdp_keygrid_bytes(self.K, self.d)
+        if self.nbytes < 0:
+            raise RuntimeError("key grid: unsupported dictionary shape [%d, %d]" % (self.K, self.d))
+        dev = self.centers.device
+        if buf is None or buf.numel() < self.nbytes or buf.device != dev:
+            buf = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)
+        self.buf = buf
+        self.rebuild()
+
+    def rebuild(self, centers=None):
+        """(Re)build for the current / new centre values (same shape); no host synchronisation."""
+        if centers is not None:
+            self.centers = centers.double().contiguous()
+        with torch.cuda.device(self.buf.device):
+            st = L.lib().bdp_keygrid_build(L.ptr(self.centers), self.K, self.d, L.ptr(self.buf),
+                                           self.nbytes, L.stream_ptr())
+        L.check(st, "bdp_keygrid_build")
+        return self
+
+    @staticmethod
+    def supported(K, d, N):
+        return d in (3, 4) and GRID_MIN_K <= K <= 4096 and N >= GRID_MIN_N
+
+
+def _scratch_grid(centers):
+    dev = centers.device
+    nbytes = L.lib().bdp_keygrid_bytes(centers.shape[0], centers.shape[1])
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _grid_ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _grid_ws[key] = buf
+    return KeyGrid(centers, buf)
+
+
+def assign_nearest(x, centers, want_residual=True, want_sqdist=False, label_dtype=torch.int64,
+                   grid="auto"):
     """kmeans.predict + residual (binDeltaGenerators.py:27-30).  x [N,d] fp32|fp64, centers [K,d].
 
-    Returns (labels [N] label_dtype, residual [N,d] fp32 | None, sqdist [N] fp64 | None)."""
+    grid: "auto" (build a key grid when it pays off), None (brute-force scan) or a KeyGrid built for
+    exactly these centres.  Returns (labels [N] label_dtype, residual [N,d] fp32 | None,
+    sqdist [N] fp64 | None)."""
     _need_cuda(x, centers)
     if x.dtype not in (torch.float32, torch.float64):
         x = x.double()
@@ -235,10 +287,21 @@ def assign_nearest(x, centers, want_residual=True, want_sqdist=False, label_dtyp
     lab64 = torch.empty(N, dtype=torch.int64, device=dev) if label_dtype != torch.int32 else None
     res = torch.empty((N, d), dtype=torch.float32, device=dev) if want_residual else None
     sq = torch.empty(N, dtype=torch.float64, device=dev) if want_sqdist else None
+    if isinstance(grid, str):
+        if grid != "auto":
+            raise NameError("Unknown grid mode passed")
+        grid = _scratch_grid(centers) if KeyGrid.supported(K, d, N) else None
     with torch.cuda.device(dev):
-        st = L.lib().bdp_assign_nearest(L.ptr(x), _dtype_code(x), N, d, L.ptr(centers), K,
-                                        L.ptr(lab32), L.ptr(lab64), L.ptr(res), L.ptr(sq),
-                                        L.stream_ptr())
+        if grid is None:
+            st = L.lib().bdp_assign_nearest(L.ptr(x), _dtype_code(x), N, d, L.ptr(centers), K,
+                                            L.ptr(lab32), L.ptr(lab64), L.ptr(res), L.ptr(sq),
+                                            L.stream_ptr())
+        else:
+            if grid.K != K or grid.d != d:
+                raise ValueError("assign_nearest: key grid was built for a [%d, %d] dictionary" % (grid.K, grid.d))
+            st = L.lib().bdp_assign_nearest_grid(L.ptr(x), _dtype_code(x), N, d, L.ptr(centers), K,
+                                                 L.ptr(grid.buf), grid.nbytes, L.ptr(lab32),
+                                                 L.ptr(lab64), L.ptr(res), L.ptr(sq), L.stream_ptr())
     L.check(st, "bdp_assign_nearest")
     return (lab32 if lab32 is not None else lab64), res, sq
 

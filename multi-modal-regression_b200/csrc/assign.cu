@@ -42,6 +42,7 @@ __device__ __forceinline__ void to_limbs(double x, double scale_hi, long long& h
   lo = (long long)((xs - f) * 4294967296.0);  // (xs-f) in [0,1) exact; product exact; trunc
 }
 
+struct GridHdr;
 struct AssignParams {
   const void* x;
   int64_t N;
@@ -58,6 +59,9 @@ struct AssignParams {
   double* inertia;
   int update;
   float err_coef;          // 2^-24 * 2(D+5) * safety
+  // key grid (candidate pruning); NULL for the brute-force kernel
+  const struct GridHdr* ghdr;
+  const unsigned short* gfine;
 };
 
 template <typename T, int D>
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(const AssignParams P) 
         const int oi = __shfl_xor_sync(BDP_FULL_MASK, bi, o);
         if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
       }
+      if (bi == 0x7fffffff) bi = 0;                      // all distances NaN: argmin gives 0
       if (lane == 0) emit_point<D, LLOYD>(P, i, xe, bi, s_acc, acc_in_smem, changed, inertia);
     }
     // next tile's first __syncthreads() (chunk loop) orders the list reuse
@@ -319,6 +324,578 @@ int dispatch_assign(AssignParams& P, int x_dtype, int d, cudaStream_t st) {
   }
   if (d == 3) return launch_assign<double, 3, LLOYD>(P, st);
   return launch_assign<double, 4, LLOYD>(P, st);
+}
+
+// ---- key grid: candidate pruning for the nearest-key query -------------------------------------
+// The brute-force scan costs N*K pair evaluations (10^10 at the benchmark size) although a point
+// can only be nearest to the handful of keys around it.  The key grid is a uniform grid over the
+// bounding box of the dictionary (plus a margin); every cell stores the ascending list of keys that
+// can be nearest to SOME point of the cell:
+//     U(cell)    = min_k maxdist^2(cell, c_k)          (an upper bound on the nearest distance)
+//     cand(cell) = { k : mindist^2(cell, c_k) <= U }   (the true nearest key of any point is in it)
+// built in two levels (coarse cells of 4^d fine cells filter the dictionary once, fine cells filter
+// their parent's list), ~3*10^7 box tests for K=1000 instead of 5*10^8.  A query then evaluates
+// ~5 candidates per point instead of K — exactly the same fp32-screen / fp64-exact arithmetic as the
+// brute-force kernel, on a superset of the keys that matter, so the labels are identical.  Points
+// outside the grid and cells whose list overflows the 64-byte record take the brute-force slow path.
+constexpr int kGridCap = 31;                 // ids per fine record  (u16 count + 31 u16 ids = 64 B)
+constexpr int kCoarseCap = 255;              // ids per coarse record (512 B)
+constexpr int kGridMaxK = 4096;              // fp32 screening records of the whole dictionary in smem
+constexpr unsigned kGridOverflow = 0xFFFFu;
+
+struct GridHdr {
+  double origin[4];
+  double cell[4];
+  double inv_cell[4];
+  int G;            // fine cells per dimension (multiple of 4)
+  int enabled;      // 0: degenerate dictionary -> every point takes the slow path
+  int pad[6];
+};
+static_assert(sizeof(GridHdr) == 128, "GridHdr layout");
+
+__host__ __device__ inline int64_t ipow64(int64_t b, int e) {
+  int64_t r = 1;
+  for (int i = 0; i < e; ++i) r *= b;
+  return r;
+}
+
+int keygrid_G(int K, int d) {
+  const double r = pow((double)K, 1.0 / d);
+  int gc = (int)ceil((d == 3 ? 1.6 : 1.0) * r);
+  const int hi = d == 3 ? 16 : 6;
+  if (gc < 2) gc = 2;
+  if (gc > hi) gc = hi;
+  return 4 * gc;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) keygrid_header_kernel(const double* __restrict__ centers,
+                                                             int K, int G, double margin_frac,
+                                                             GridHdr* __restrict__ hdr) {
+  __shared__ double s_lo[8][D], s_hi[8][D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double lo[D], hi[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+  bool finite = true;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double c = centers[(int64_t)j * D + k];
+      finite = finite && isfinite(c);
+      lo[k] = fmin(lo[k], c);
+      hi[k] = fmax(hi[k], c);
+    }
+  }
+  const int all_finite = __syncthreads_and(finite ? 1 : 0);
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(BDP_FULL_MASK, lo[k], o));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(BDP_FULL_MASK, hi[k], o));
+    }
+    if (lane == 0) { s_lo[warp][k] = lo[k]; s_hi[warp][k] = hi[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ext = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      for (int w = 1; w < 8; ++w) { s_lo[0][k] = fmin(s_lo[0][k], s_lo[w][k]); s_hi[0][k] = fmax(s_hi[0][k], s_hi[w][k]); }
+      ext = fmax(ext, s_hi[0][k] - s_lo[0][k]);
+    }
+    const bool ok = all_finite && ext > 0.0 && isfinite(ext);
+    const double margin = ext * margin_frac;
+    for (int k = 0; k < 4; ++k) {
+      double o = 0.0, c = 1.0;
+      if (k < D && ok) {
+        o = s_lo[0][k] - margin;
+        c = (s_hi[0][k] - s_lo[0][k] + 2.0 * margin) / (double)G;
+      }
+      hdr->origin[k] = o; hdr->cell[k] = c; hdr->inv_cell[k] = 1.0 / c;
+    }
+    hdr->G = G;
+    hdr->enabled = ok ? 1 : 0;
+  }
+}
+
+// squared distance bounds between key c and the box [lo, hi]
+template <int D>
+__device__ __forceinline__ void box_bounds(const double* __restrict__ c, const double lo[D],
+                                           const double hi[D], double& mind2, double& maxd2) {
+  mind2 = 0.0; maxd2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double ck = __ldg(c + k);
+    const double a = ck - lo[k], b = hi[k] - ck;      // >= 0 when inside along this axis
+    const double far = fmax(fabs(a), fabs(b));
+    const double near = fmax(fmax(-a, -b), 0.0);
+    maxd2 += far * far;
+    mind2 += near * near;
+  }
+}
+
+// One warp filters a key list against one box.  src == nullptr: the whole dictionary.
+template <int D>
+__device__ __forceinline__ void filter_box(const double* __restrict__ centers, int K,
+                                           const unsigned short* __restrict__ src, int n_src,
+                                           const double lo[D], const double hi[D],
+                                           unsigned short* __restrict__ rec, int cap, int lane) {
+  double u = INFINITY;
+  for (int j = lane; j < n_src; j += 32) {
+    const int k = src ? (int)src[j] : j;
+    double mn, mx;
+    box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
+    u = fmin(u, mx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) u = fmin(u, __shfl_xor_sync(BDP_FULL_MASK, u, o));
+  const double thr = u * (1.0 + 1e-9) + 1e-300;
+  int cnt = 0;
+  for (int j0 = 0; j0 < n_src; j0 += 32) {
+    const int j = j0 + lane;
+    bool keep = false;
+    int k = 0;
+    if (j < n_src) {
+      k = src ? (int)src[j] : j;
+      double mn, mx;
+      box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
+      keep = mn <= thr;
+    }
+    const unsigned m = __ballot_sync(BDP_FULL_MASK, keep);
+    if (keep) {
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (pos < cap) rec[1 + pos] = (unsigned short)k;      // ascending key order
+    }
+    cnt += __popc(m);
+  }
+  if (lane == 0) rec[0] = (unsigned short)(cnt > cap ? kGridOverflow : (unsigned)cnt);
+}
+
+// Coarse cells (4 fine cells per side): one warp filters the whole dictionary against one cell.
+template <int D>
+__global__ void __launch_bounds__(256) keygrid_coarse_kernel(const double* __restrict__ centers,
+                                                             int K, const GridHdr* __restrict__ hdr,
+                                                             unsigned short* __restrict__ coarse) {
+  const int lane = threadIdx.x & 31;
+  const int Gc = hdr->G / 4;
+  const int64_t n_cells = ipow64(Gc, D);
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t cell = warp0; cell < n_cells; cell += n_warps) {
+    double lo[D], hi[D];
+    int64_t r = cell;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const int ck = (int)(r % Gc);
+      r /= Gc;
+      const double eps = 1e-9 * hdr->cell[k];
+      lo[k] = hdr->origin[k] + (double)(4 * ck) * hdr->cell[k] - eps;
+      hi[k] = hdr->origin[k] + (double)(4 * ck + 4) * hdr->cell[k] + eps;
+    }
+    filter_box<D>(centers, K, nullptr, K, lo, hi, coarse + cell * (kCoarseCap + 1), kCoarseCap, lane);
+  }
+}
+
+// Fine cells: one THREAD per cell, the 4^D children of a coarse cell on adjacent threads, so the
+// parent's key list and the keys themselves are warp-uniform (broadcast) loads.
+template <int D>
+__global__ void __launch_bounds__(256) keygrid_fine_kernel(const double* __restrict__ centers, int K,
+                                                           const GridHdr* __restrict__ hdr,
+                                                           const unsigned short* __restrict__ coarse,
+                                                           unsigned short* __restrict__ fine) {
+  constexpr int kChildren = D == 3 ? 64 : 256;
+  const int G = hdr->G, Gc = G / 4;
+  const int64_t n_fine = ipow64(G, D);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_fine) return;
+  const int64_t parent = t / kChildren;
+  int child = (int)(t % kChildren);
+  double lo[D], hi[D];
+  int64_t pr = parent, cell = 0, mul = 1;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const int ck = 4 * (int)(pr % Gc) + (child & 3);
+    pr /= Gc;
+    child >>= 2;
+    const double eps = 1e-9 * hdr->cell[k];
+    lo[k] = hdr->origin[k] + (double)ck * hdr->cell[k] - eps;
+    hi[k] = hdr->origin[k] + (double)(ck + 1) * hdr->cell[k] + eps;
+    cell += (int64_t)ck * mul;
+    mul *= G;
+  }
+  const unsigned short* prec = coarse + parent * (kCoarseCap + 1);
+  const unsigned pc = prec[0];
+  const bool all = pc == kGridOverflow;
+  const int n_src = all ? K : (int)pc;
+  double u = INFINITY;
+  for (int j = 0; j < n_src; ++j) {
+    const int k = all ? j : (int)prec[1 + j];
+    double mn, mx;
+    box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
+    u = fmin(u, mx);
+  }
+  const double thr = u * (1.0 + 1e-9) + 1e-300;
+  unsigned short* rec = fine + cell * (kGridCap + 1);
+  int cnt = 0;
+  for (int j = 0; j < n_src; ++j) {
+    const int k = all ? j : (int)prec[1 + j];
+    double mn, mx;
+    box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
+    if (mn <= thr) {
+      if (cnt < kGridCap) rec[1 + cnt] = (unsigned short)k;        // ascending key order
+      ++cnt;
+    }
+  }
+  rec[0] = (unsigned short)(cnt > kGridCap ? kGridOverflow : (unsigned)cnt);
+}
+
+// Query.  Every warp owns 32*kGPts consecutive points of a block tile: the points come in and the
+// residuals go out through a warp-private shared-memory stage so that global traffic is full 128-byte
+// lines (a 12-byte point per lane would touch every line three times).  Lloyd sums go to shared
+// memory as NATIVE 32-bit atomics on 16-bit chunks of the two fixed-point limbs (a 64-bit shared
+// atomicAdd is a compare-and-swap loop); a block folds its chunk counters into the global int64
+// accumulators every 2^16 points, before a counter can overflow.
+constexpr int kGThreads = 512;
+constexpr int kGWarps = kGThreads / 32;
+constexpr int kGPts = 2;
+constexpr int kGTile = kGThreads * kGPts;
+constexpr int kFlushTiles = 65536 / kGTile;
+
+template <int D>
+__device__ __forceinline__ void flush_acc32(unsigned* s_acc32, int K, unsigned long long* acc) {
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < K * (D + 1); idx += kGThreads) {
+    const int j = idx / (D + 1), k = idx % (D + 1);
+    const unsigned* a = s_acc32 + (size_t)j * (4 * D + 1);
+    const unsigned cnt = a[4 * D];
+    if (cnt == 0u) continue;
+    unsigned long long* g = acc + (size_t)j * (2 * D + 1);
+    if (k == D) {
+      atomicAdd(g + 2 * D, (unsigned long long)cnt);
+    } else {
+      const long long hi = (long long)a[4 * k] + ((long long)a[4 * k + 1] << 16) -
+                           (long long)cnt * 2147483648LL;          // remove the +2^31 bias
+      const unsigned long long lo = (unsigned long long)a[4 * k + 2] +
+                                    ((unsigned long long)a[4 * k + 3] << 16);
+      if (hi) atomicAdd(g + 2 * k, (unsigned long long)hi);
+      if (lo) atomicAdd(g + 2 * k + 1, lo);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * (4 * D + 1); i += kGThreads) s_acc32[i] = 0u;
+  __syncthreads();
+}
+
+template <typename T, int D, bool LLOYD>
+__global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [K float4 recs][K float norms (D==4)][warp stages][chunk accumulators (lloyd)]
+  float4* s_rec = reinterpret_cast<float4*>(smem_raw);
+  float* s_cn = reinterpret_cast<float*>(s_rec + P.K);
+  double* s_stage_all = reinterpret_cast<double*>(s_cn + (D == 4 ? ((P.K + 3) & ~3) : 0));
+  unsigned* s_acc32 = reinterpret_cast<unsigned*>(s_stage_all + kGWarps * kGPts * 32 * D);
+  __shared__ double s_red[2][kGWarps];
+  __shared__ float s_cmax[kGWarps];
+  const bool acc_in_smem = LLOYD && P.update && P.K <= kMaxSmemAccK;
+
+  const T* __restrict__ x = reinterpret_cast<const T*>(P.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_tiles = (P.N + kGTile - 1) / kGTile;
+  T* stage = reinterpret_cast<T*>(s_stage_all + warp * (kGPts * 32 * D));
+  float* rstage = reinterpret_cast<float*>(stage);
+
+  if (acc_in_smem) {
+    for (int i = threadIdx.x; i < P.K * (4 * D + 1); i += kGThreads) s_acc32[i] = 0u;
+  }
+  // stage the fp32 screening records of the whole dictionary + max ||c|| for the error bound
+  float cmax = 0.f;
+  for (int j = threadIdx.x; j < P.K; j += kGThreads) {
+    const double* c = P.centers + (int64_t)j * D;
+    double cn = 0.0;
+    float m2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double ck = __ldg(c + k);
+      cn += ck * ck;
+      m2[k] = (float)(-2.0 * ck);
+    }
+    if (D == 3) s_rec[j] = make_float4(m2[0], m2[1], m2[2], (float)cn);
+    else { s_rec[j] = make_float4(m2[0], m2[1], m2[2], m2[3]); s_cn[j] = (float)cn; }
+    cmax = fmaxf(cmax, (float)sqrt(cn) * 1.000001f);
+  }
+  cmax = warp_max(cmax);
+  if (lane == 0) s_cmax[warp] = cmax;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kGWarps; ++w) cmax = fmaxf(cmax, s_cmax[w]);
+
+  double g_org[D], g_inv[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) { g_org[k] = P.ghdr->origin[k]; g_inv[k] = P.ghdr->inv_cell[k]; }
+  const int G = P.ghdr->G;
+  const bool g_on = P.ghdr->enabled != 0;
+  const double Gd = (double)G;
+
+  int changed = 0, tiles_since_flush = 0;
+  double inertia = 0.0;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t wbase = tile * kGTile + (int64_t)warp * (32 * kGPts);
+    const int64_t nrem = P.N - wbase;
+    const int nval = nrem <= 0 ? 0 : (nrem < 32 * kGPts ? (int)nrem : 32 * kGPts);
+    // coalesced load of this warp's points
+#pragma unroll
+    for (int j = 0; j < kGPts * D; ++j) {
+      const int idx = j * 32 + lane;
+      if (idx < nval * D) stage[idx] = x[wbase * D + idx];
+    }
+    __syncwarp();
+    double xd[kGPts][D];
+    const uint4* recp[kGPts];
+    uint4 first[kGPts];
+    bool in_grid[kGPts], valid[kGPts];
+    // phase 1: points -> cells -> first 16 bytes of every record (all loads in flight together)
+#pragma unroll
+    for (int p = 0; p < kGPts; ++p) {
+      const int li = p * 32 + lane;
+      valid[p] = li < nval;
+      bool ok = g_on && valid[p];
+      int64_t cidx = 0, mul = 1;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        xd[p][k] = valid[p] ? (double)stage[li * D + k] : 0.0;
+        const double t = (xd[p][k] - g_org[k]) * g_inv[k];
+        ok = ok && (t >= 0.0) && (t < Gd);             // false for NaN as well
+        const int ck = ok ? (int)t : 0;                 // t >= 0: truncation == floor
+        cidx += (int64_t)ck * mul;
+        mul *= G;
+      }
+      in_grid[p] = ok;
+      recp[p] = reinterpret_cast<const uint4*>(P.gfine + (ok ? cidx : 0) * (kGridCap + 1));
+      first[p] = __ldg(recp[p]);
+    }
+    __syncwarp();                                       // stage is reused for the residuals
+    // phase 2: fp32 screen over the candidates, fp64 exact pass on near ties
+    int label[kGPts];
+    bool slow[kGPts];
+#pragma unroll
+    for (int p = 0; p < kGPts; ++p) {
+      label[p] = 0;
+      const unsigned cnt = first[p].x & 0xFFFFu;
+      slow[p] = valid[p] && (!in_grid[p] || cnt == kGridOverflow);
+      if (!valid[p] || slow[p]) continue;
+      float xf[D];
+      float n2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) { xf[k] = (float)xd[p][k]; n2 += xf[k] * xf[k]; }
+      const float sN = sqrtf(n2) * 1.0000002f + cmax;
+      const float tau = P.err_coef * sN * sN;
+      float best = INFINITY, second = INFINITY;
+      int bidx = 0;
+      uint4 ch = first[p];
+      for (unsigned c = 0; c * 8u <= cnt; ++c) {
+        if (c > 0) ch = __ldg(recp[p] + c);
+        const unsigned w[4] = {ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const unsigned e = c * 8u + h;
+          if (e == 0u || e > cnt) continue;
+          const int id = (int)((w[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu);
+          const float4 cr = s_rec[id];
+          const float cn = (D == 4) ? s_cn[id] : 0.f;
+          const float d = screen_dist<D>(xf, cr, cn);
+          const bool lt = d < best;
+          second = fminf(second, lt ? best : d);
+          bidx = lt ? id : bidx;
+          best = fminf(best, d);
+        }
+      }
+      if (!(second - best > tau) && cnt > 1u) {
+        // near tie: exact fp64 pass over the same candidates (ascending ids: lowest index wins)
+        double bd = INFINITY;
+        const unsigned short* ids = reinterpret_cast<const unsigned short*>(recp[p]);
+        for (unsigned e = 1; e <= cnt; ++e) {
+          const int id = (int)__ldg(ids + e);
+          const double* c = P.centers + (int64_t)id * D;
+          double sq = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            const double df = xd[p][k] - __ldg(c + k);
+            sq += df * df;
+          }
+          if (sq < bd) { bd = sq; bidx = id; }
+        }
+      }
+      label[p] = bidx;
+    }
+    // slow path: points outside the grid / in overflowed cells, the whole warp scans the dictionary
+#pragma unroll
+    for (int p = 0; p < kGPts; ++p) {
+      unsigned m = __ballot_sync(BDP_FULL_MASK, slow[p]);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        double xe[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) xe[k] = __shfl_sync(BDP_FULL_MASK, xd[p][k], src);
+        double bd = INFINITY;
+        int bi = 0x7fffffff;
+        for (int j = lane; j < P.K; j += 32) {
+          const double* c = P.centers + (int64_t)j * D;
+          double sq = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            const double df = xe[k] - __ldg(c + k);
+            sq += df * df;
+          }
+          if (sq < bd) { bd = sq; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(BDP_FULL_MASK, bd, o);
+          const int oi = __shfl_xor_sync(BDP_FULL_MASK, bi, o);
+          if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (bi == 0x7fffffff) bi = 0;                    // all distances NaN: argmin gives 0
+        if (lane == src) label[p] = bi;
+      }
+    }
+    // emit
+#pragma unroll
+    for (int p = 0; p < kGPts; ++p) {
+      if (!valid[p]) continue;
+      const int li = p * 32 + lane;
+      const int64_t i = wbase + li;
+      const double* c = P.centers + (int64_t)label[p] * D;
+      double diff[D], sq = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        diff[k] = xd[p][k] - __ldg(c + k);
+        sq += diff[k] * diff[k];
+      }
+      if (LLOYD) {
+        changed += (P.labels32[i] != label[p]);
+        P.labels32[i] = label[p];
+        inertia += sq;
+        if (P.update) {
+          if (acc_in_smem) {
+            unsigned* a = s_acc32 + (size_t)label[p] * (4 * D + 1);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              long long hi, lo;
+              to_limbs(xd[p][k], P.scale_hi, hi, lo);
+              const unsigned ub = (unsigned)(hi + 2147483648LL);      // hi in [-2^31, 2^31)
+              const unsigned ul = (unsigned)lo;
+              atomicAdd(a + 4 * k, ub & 0xFFFFu);
+              atomicAdd(a + 4 * k + 1, ub >> 16);
+              atomicAdd(a + 4 * k + 2, ul & 0xFFFFu);
+              atomicAdd(a + 4 * k + 3, ul >> 16);
+            }
+            atomicAdd(a + 4 * D, 1u);
+          } else {
+            unsigned long long* a = P.acc + (size_t)label[p] * (2 * D + 1);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              long long hi, lo;
+              to_limbs(xd[p][k], P.scale_hi, hi, lo);
+              atomicAdd(a + 2 * k, (unsigned long long)hi);
+              atomicAdd(a + 2 * k + 1, (unsigned long long)lo);
+            }
+            atomicAdd(a + 2 * D, 1ull);
+          }
+        }
+      } else {
+        if (P.labels32) P.labels32[i] = label[p];
+        if (P.labels64) P.labels64[i] = (int64_t)label[p];
+        if (P.min_sqdist) P.min_sqdist[i] = sq;
+        if (P.residual) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) rstage[li * D + k] = (float)diff[k];
+        }
+      }
+    }
+    if (!LLOYD && P.residual) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kGPts * D; ++j) {
+        const int idx = j * 32 + lane;
+        if (idx < nval * D) P.residual[wbase * D + idx] = rstage[idx];
+      }
+      __syncwarp();
+    }
+    if (acc_in_smem && ++tiles_since_flush == kFlushTiles) {
+      flush_acc32<D>(s_acc32, P.K, P.acc);
+      tiles_since_flush = 0;
+    }
+  }
+
+  if (LLOYD) {
+    if (acc_in_smem) flush_acc32<D>(s_acc32, P.K, P.acc);
+    changed = warp_sum(changed);
+    inertia = warp_sum(inertia);
+    if (lane == 0) { s_red[0][warp] = (double)changed; s_red[1][warp] = inertia; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double ch = 0.0, in = 0.0;
+      for (int w = 0; w < kGWarps; ++w) { ch += s_red[0][w]; in += s_red[1][w]; }
+      if (ch != 0.0) atomicAdd(P.stats, (unsigned long long)ch);
+      if (P.inertia) atomicAdd(P.inertia, in);
+    }
+  }
+}
+
+template <typename T, int D, bool LLOYD>
+int launch_assign_grid(const AssignParams& P, cudaStream_t st) {
+  const bool smem_acc = LLOYD && P.update && P.K <= kMaxSmemAccK;
+  size_t smem = (size_t)P.K * 16 + (D == 4 ? (size_t)((P.K + 3) & ~3) * 4 : 0);
+  smem += (size_t)kGWarps * kGPts * 32 * D * 8;
+  if (smem_acc) smem += (size_t)P.K * (4 * D + 1) * 4;
+  auto kern = assign_grid_kernel<T, D, LLOYD>;
+  if (smem > 48 * 1024) {
+    BDP_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  int per_sm = 0;
+  BDP_CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t n_tiles = ceil_div64(P.N, (int64_t)kGTile);
+  int64_t blocks = (int64_t)bdp_num_sms() * per_sm;
+  if (blocks > n_tiles) blocks = n_tiles;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, kGThreads, smem, st>>>(P);
+  BDP_CUDA_CHECK_LAUNCH("assign_grid_kernel");
+  return BDP_OK;
+}
+
+template <bool LLOYD>
+int dispatch_assign_grid(AssignParams& P, int x_dtype, int d, cudaStream_t st) {
+  P.err_coef = screen_err_coef(d);
+  if (x_dtype == BDP_F32) {
+    if (d == 3) return launch_assign_grid<float, 3, LLOYD>(P, st);
+    return launch_assign_grid<float, 4, LLOYD>(P, st);
+  }
+  if (d == 3) return launch_assign_grid<double, 3, LLOYD>(P, st);
+  return launch_assign_grid<double, 4, LLOYD>(P, st);
+}
+
+int keygrid_check(const void* grid, int64_t grid_bytes, int K, int d, const char* who) {
+  BDP_REQUIRE(grid != nullptr, "%s: grid is NULL", who);
+  BDP_REQUIRE(K >= 1 && K <= kGridMaxK, "%s: the key grid supports 1 <= K <= %d (got %d)", who, kGridMaxK, K);
+  BDP_REQUIRE(grid_bytes >= bdp_keygrid_bytes(K, d), "%s: grid buffer too small (%lld < %lld)", who,
+              (long long)grid_bytes, (long long)bdp_keygrid_bytes(K, d));
+  BDP_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 15) == 0, "%s: grid must be 16-byte aligned", who);
+  return BDP_OK;
+}
+
+void keygrid_pointers(const void* grid, int K, int d, const GridHdr** hdr,
+                      const unsigned short** coarse, const unsigned short** fine) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(grid);
+  const int G = keygrid_G(K, d);
+  const int64_t n_coarse = ipow64(G / 4, d);
+  *hdr = reinterpret_cast<const GridHdr*>(b);
+  *coarse = reinterpret_cast<const unsigned short*>(b + sizeof(GridHdr));
+  *fine = *coarse + n_coarse * (kCoarseCap + 1);
 }
 
 // ---- argmax |<key, q>| -----------------------------------------------------------------------
@@ -670,4 +1247,91 @@ extern "C" int bdp_convert_axis_angle(const double* aa, int64_t N, double* rotma
   convert_aa_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, st>>>(aa, N, rotmat, quat);
   BDP_CUDA_CHECK_LAUNCH("convert_aa_kernel");
   return BDP_OK;
+}
+
+extern "C" int64_t bdp_keygrid_bytes(int K, int d) {
+  if ((d != 3 && d != 4) || K < 1 || K > kGridMaxK) return -1;
+  const int G = keygrid_G(K, d);
+  const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
+  return (int64_t)sizeof(GridHdr) + n_coarse * (kCoarseCap + 1) * 2 + n_fine * (kGridCap + 1) * 2;
+}
+
+extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
+                                 void* stream) {
+  BDP_REQUIRE(centers != nullptr, "keygrid_build: NULL centers");
+  BDP_REQUIRE(d == 3 || d == 4, "keygrid_build: d must be 3 or 4 (got %d)", d);
+  int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_build");
+  if (rc != BDP_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const GridHdr* hdr; const unsigned short *coarse, *fine;
+  keygrid_pointers(grid, K, d, &hdr, &coarse, &fine);
+  GridHdr* h = const_cast<GridHdr*>(hdr);
+  unsigned short* co = const_cast<unsigned short*>(coarse);
+  unsigned short* fi = const_cast<unsigned short*>(fine);
+  const int G = keygrid_G(K, d);
+  const double r = pow((double)K, 1.0 / d);
+  const double margin_frac = r > 2.0 ? 1.0 / r : 0.5;
+  const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
+  const int sms = bdp_num_sms();
+  auto blocks_for = [&](int64_t cells) {
+    int64_t b = ceil_div64(cells, 8);                  // 8 warps per block, one cell per warp
+    const int64_t cap = (int64_t)sms * 8;
+    return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
+  };
+  const unsigned fine_blocks = (unsigned)ceil_div64(n_fine, 256);
+  if (d == 3) {
+    keygrid_header_kernel<3><<<1, 256, 0, st>>>(centers, K, G, margin_frac, h);
+    keygrid_coarse_kernel<3><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, co);
+    keygrid_fine_kernel<3><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi);
+  } else {
+    keygrid_header_kernel<4><<<1, 256, 0, st>>>(centers, K, G, margin_frac, h);
+    keygrid_coarse_kernel<4><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, co);
+    keygrid_fine_kernel<4><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi);
+  }
+  BDP_CUDA_CHECK_LAUNCH("keygrid kernels");
+  return BDP_OK;
+}
+
+extern "C" int bdp_assign_nearest_grid(const void* x, int x_dtype, int64_t N, int d,
+                                       const double* centers, int K, const void* grid,
+                                       int64_t grid_bytes, int32_t* labels32, int64_t* labels64,
+                                       float* residual, double* min_sqdist, void* stream) {
+  BDP_REQUIRE(N >= 0, "assign_nearest_grid: N < 0");
+  if (N == 0) return BDP_OK;
+  BDP_REQUIRE(x && centers, "assign_nearest_grid: NULL input");
+  BDP_REQUIRE(d == 3 || d == 4, "assign_nearest_grid: d must be 3 or 4 (got %d)", d);
+  BDP_REQUIRE(x_dtype == BDP_F32 || x_dtype == BDP_F64, "assign_nearest_grid: x_dtype %d", x_dtype);
+  int rc = keygrid_check(grid, grid_bytes, K, d, "assign_nearest_grid");
+  if (rc != BDP_OK) return rc;
+  AssignParams P = {};
+  P.x = x; P.N = N; P.centers = centers; P.K = K;
+  P.labels32 = labels32; P.labels64 = labels64; P.residual = residual; P.min_sqdist = min_sqdist;
+  const unsigned short* coarse;
+  keygrid_pointers(grid, K, d, &P.ghdr, &coarse, &P.gfine);
+  return dispatch_assign_grid<false>(P, x_dtype, d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, const double* centers,
+                                          int K, const void* grid, int64_t grid_bytes,
+                                          int32_t* labels, int64_t* acc, int fix_hi_bits,
+                                          int64_t* stats, double* inertia, int update,
+                                          void* stream) {
+  BDP_REQUIRE(N >= 0 && N < (1ll << 30), "kmeans_lloyd_step_grid: N out of range");
+  if (N == 0) return BDP_OK;
+  BDP_REQUIRE(x && centers && labels && stats, "kmeans_lloyd_step_grid: NULL buffer");
+  BDP_REQUIRE(d == 3 || d == 4, "kmeans_lloyd_step_grid: d must be 3 or 4 (got %d)", d);
+  BDP_REQUIRE(!update || acc, "kmeans_lloyd_step_grid: acc is NULL with update=1");
+  BDP_REQUIRE(fix_hi_bits >= 0 && fix_hi_bits <= 30, "kmeans_lloyd_step_grid: fix_hi_bits %d",
+              fix_hi_bits);
+  int rc = keygrid_check(grid, grid_bytes, K, d, "kmeans_lloyd_step_grid");
+  if (rc != BDP_OK) return rc;
+  AssignParams P = {};
+  P.x = x; P.N = N; P.centers = centers; P.K = K; P.labels32 = labels;
+  P.acc = reinterpret_cast<unsigned long long*>(acc);
+  P.scale_hi = ldexp(1.0, fix_hi_bits);
+  P.stats = reinterpret_cast<unsigned long long*>(stats);
+  P.inertia = inertia; P.update = update;
+  const unsigned short* coarse;
+  keygrid_pointers(grid, K, d, &P.ghdr, &coarse, &P.gfine);
+  return dispatch_assign_grid<true>(P, BDP_F64, d, reinterpret_cast<cudaStream_t>(stream));
 }
