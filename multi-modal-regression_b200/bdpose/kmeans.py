@@ -39,16 +39,18 @@ class LloydState:
         self.n_empty = torch.zeros(1, dtype=torch.int64, device=dev)
 
 
-def lloyd_step(x, centers, state, fix_hi_bits, update=True, grid=None):
+def lloyd_step(x, centers, state, fix_hi_bits, update=True, grid=None, want_inertia=False):
     """One E(+M-accumulate) step on this rank's shard.  Adds into state.acc / stats / inertia.
     grid: an ops.KeyGrid buffer to rebuild for `centers` and query through (candidate pruning), or
     None for the brute-force scan — the labels are the same either way."""
     N, d = x.shape
+    # the inertia is only read after the final E-step (update=False); M-steps skip it
+    inertia = None if (update and not want_inertia) else state.inertia
     with torch.cuda.device(x.device):
         if grid is None:
             st = L.lib().bdp_kmeans_lloyd_step(L.ptr(x), N, d, L.ptr(centers), centers.shape[0],
                                                L.ptr(state.labels), L.ptr(state.acc), fix_hi_bits,
-                                               L.ptr(state.stats), L.ptr(state.inertia),
+                                               L.ptr(state.stats), L.ptr(inertia),
                                                1 if update else 0, L.stream_ptr())
         else:
             grid.rebuild(centers)
@@ -56,7 +58,7 @@ def lloyd_step(x, centers, state, fix_hi_bits, update=True, grid=None):
                                                     centers.shape[0], L.ptr(grid.buf), grid.nbytes,
                                                     L.ptr(state.labels), L.ptr(state.acc),
                                                     fix_hi_bits, L.ptr(state.stats),
-                                                    L.ptr(state.inertia), 1 if update else 0,
+                                                    L.ptr(inertia), 1 if update else 0,
                                                     L.stream_ptr())
     L.check(st, "bdp_kmeans_lloyd_step")
 

@@ -331,8 +331,11 @@ int dispatch_assign(AssignParams& P, int x_dtype, int d, cudaStream_t st) {
 // can only be nearest to the handful of keys around it.  The key grid is a uniform grid over the
 // bounding box of the dictionary (plus a margin); every cell stores the ascending list of keys that
 // can be nearest to SOME point of the cell:
-//     U(cell)    = min_k maxdist^2(cell, c_k)          (an upper bound on the nearest distance)
-//     cand(cell) = { k : mindist^2(cell, c_k) <= U }   (the true nearest key of any point is in it)
+//     U(cell)    = min_k maxdist^2(cell, c_k)          (an upper bound on the nearest distance),
+//     p(cell)    = the key attaining it (the pivot)
+//     cand(cell) = { k : mindist^2(cell, c_k) <= U  and  k beats the pivot SOMEWHERE in the cell }
+// (the second test is exact: |x-c_k|^2 - |x-c_p|^2 is linear in x, its minimum over the box sits at
+// a corner).  The true nearest key of any point of the cell — and every key tied with it — is in it,
 // built in two levels (coarse cells of 4^d fine cells filter the dictionary once, fine cells filter
 // their parent's list), ~3*10^7 box tests for K=1000 instead of 5*10^8.  A query then evaluates
 // ~5 candidates per point instead of K — exactly the same fp32-screen / fp64-exact arithmetic as the
@@ -342,6 +345,10 @@ constexpr int kGridCap = 31;                 // ids per fine record  (u16 count 
 constexpr int kCoarseCap = 255;              // ids per coarse record (512 B)
 constexpr int kGridMaxK = 4096;              // fp32 screening records of the whole dictionary in smem
 constexpr unsigned kGridOverflow = 0xFFFFu;
+// Cell boxes are grown by this fraction of a cell on every side before the bounds are taken, which
+// covers the rounding of the point -> cell mapping in the query (fp32 for fp32 rotations: the cell
+// coordinate is off by < 3e-5 cells; fp64: < 1e-13).
+constexpr double kBoxEps = 1e-3;
 
 struct GridHdr {
   double origin[4];
@@ -350,8 +357,10 @@ struct GridHdr {
   int G;            // fine cells per dimension (multiple of 4)
   int enabled;      // 0: degenerate dictionary -> every point takes the slow path
   int pad[6];
+  float origin32[4];
+  float inv_cell32[4];
 };
-static_assert(sizeof(GridHdr) == 128, "GridHdr layout");
+static_assert(sizeof(GridHdr) == 160, "GridHdr layout");
 
 __host__ __device__ inline int64_t ipow64(int64_t b, int e) {
   int64_t r = 1;
@@ -414,6 +423,7 @@ __global__ void __launch_bounds__(256) keygrid_header_kernel(const double* __res
         c = (s_hi[0][k] - s_lo[0][k] + 2.0 * margin) / (double)G;
       }
       hdr->origin[k] = o; hdr->cell[k] = c; hdr->inv_cell[k] = 1.0 / c;
+      hdr->origin32[k] = (float)o; hdr->inv_cell32[k] = (float)(1.0 / c);
     }
     hdr->G = G;
     hdr->enabled = ok ? 1 : 0;
@@ -436,6 +446,24 @@ __device__ __forceinline__ void box_bounds(const double* __restrict__ c, const d
   }
 }
 
+// min over the box of |x - c_k|^2 - |x - c_p|^2 (linear in x: attained at a corner).  Positive means
+// key k loses to the pivot key p everywhere in the box, so k can never be the nearest key there.
+template <int D>
+__device__ __forceinline__ double bisector_min(const double* __restrict__ ck, const double cp[D],
+                                               const double lo[D], const double hi[D], double& scale) {
+  double f = 0.0, nk = 0.0, np = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double c = __ldg(ck + k);
+    const double dlt = c - cp[k];
+    f -= 2.0 * dlt * (dlt > 0.0 ? hi[k] : lo[k]);
+    nk += c * c;
+    np += cp[k] * cp[k];
+  }
+  scale = 1.0 + nk + np;
+  return f + (nk - np);
+}
+
 // One warp filters a key list against one box.  src == nullptr: the whole dictionary.
 template <int D>
 __device__ __forceinline__ void filter_box(const double* __restrict__ centers, int K,
@@ -443,15 +471,23 @@ __device__ __forceinline__ void filter_box(const double* __restrict__ centers, i
                                            const double lo[D], const double hi[D],
                                            unsigned short* __restrict__ rec, int cap, int lane) {
   double u = INFINITY;
+  int piv = 0;
   for (int j = lane; j < n_src; j += 32) {
     const int k = src ? (int)src[j] : j;
     double mn, mx;
     box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-    u = fmin(u, mx);
+    if (mx < u) { u = mx; piv = k; }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) u = fmin(u, __shfl_xor_sync(BDP_FULL_MASK, u, o));
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ou = __shfl_xor_sync(BDP_FULL_MASK, u, o);
+    const int op = __shfl_xor_sync(BDP_FULL_MASK, piv, o);
+    if (ou < u || (ou == u && op < piv)) { u = ou; piv = op; }
+  }
   const double thr = u * (1.0 + 1e-9) + 1e-300;
+  double cp[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) cp[k] = __ldg(centers + (int64_t)piv * D + k);
   int cnt = 0;
   for (int j0 = 0; j0 < n_src; j0 += 32) {
     const int j = j0 + lane;
@@ -459,9 +495,10 @@ __device__ __forceinline__ void filter_box(const double* __restrict__ centers, i
     int k = 0;
     if (j < n_src) {
       k = src ? (int)src[j] : j;
-      double mn, mx;
+      double mn, mx, sc;
       box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-      keep = mn <= thr;
+      const double bm = bisector_min<D>(centers + (int64_t)k * D, cp, lo, hi, sc);
+      keep = mn <= thr && bm <= 1e-9 * sc;
     }
     const unsigned m = __ballot_sync(BDP_FULL_MASK, keep);
     if (keep) {
@@ -490,7 +527,7 @@ __global__ void __launch_bounds__(256) keygrid_coarse_kernel(const double* __res
     for (int k = 0; k < D; ++k) {
       const int ck = (int)(r % Gc);
       r /= Gc;
-      const double eps = 1e-9 * hdr->cell[k];
+      const double eps = kBoxEps * hdr->cell[k];
       lo[k] = hdr->origin[k] + (double)(4 * ck) * hdr->cell[k] - eps;
       hi[k] = hdr->origin[k] + (double)(4 * ck + 4) * hdr->cell[k] + eps;
     }
@@ -519,7 +556,7 @@ __global__ void __launch_bounds__(256) keygrid_fine_kernel(const double* __restr
     const int ck = 4 * (int)(pr % Gc) + (child & 3);
     pr /= Gc;
     child >>= 2;
-    const double eps = 1e-9 * hdr->cell[k];
+    const double eps = kBoxEps * hdr->cell[k];
     lo[k] = hdr->origin[k] + (double)ck * hdr->cell[k] - eps;
     hi[k] = hdr->origin[k] + (double)(ck + 1) * hdr->cell[k] + eps;
     cell += (int64_t)ck * mul;
@@ -530,20 +567,25 @@ __global__ void __launch_bounds__(256) keygrid_fine_kernel(const double* __restr
   const bool all = pc == kGridOverflow;
   const int n_src = all ? K : (int)pc;
   double u = INFINITY;
+  int piv = 0;
   for (int j = 0; j < n_src; ++j) {
     const int k = all ? j : (int)prec[1 + j];
     double mn, mx;
     box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-    u = fmin(u, mx);
+    if (mx < u) { u = mx; piv = k; }
   }
   const double thr = u * (1.0 + 1e-9) + 1e-300;
+  double cp[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) cp[k] = __ldg(centers + (int64_t)piv * D + k);
   unsigned short* rec = fine + cell * (kGridCap + 1);
   int cnt = 0;
   for (int j = 0; j < n_src; ++j) {
     const int k = all ? j : (int)prec[1 + j];
-    double mn, mx;
+    double mn, mx, sc;
     box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-    if (mn <= thr) {
+    const double bm = bisector_min<D>(centers + (int64_t)k * D, cp, lo, hi, sc);
+    if (mn <= thr && bm <= 1e-9 * sc) {
       if (cnt < kGridCap) rec[1 + cnt] = (unsigned short)k;        // ascending key order
       ++cnt;
     }
@@ -631,12 +673,17 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
 #pragma unroll
   for (int w = 0; w < kGWarps; ++w) cmax = fmaxf(cmax, s_cmax[w]);
 
-  double g_org[D], g_inv[D];
+  // point -> cell in the arithmetic of the input type (see kBoxEps)
+  T g_org[D], g_inv[D];
 #pragma unroll
-  for (int k = 0; k < D; ++k) { g_org[k] = P.ghdr->origin[k]; g_inv[k] = P.ghdr->inv_cell[k]; }
+  for (int k = 0; k < D; ++k) {
+    if (sizeof(T) == 4) { g_org[k] = (T)P.ghdr->origin32[k]; g_inv[k] = (T)P.ghdr->inv_cell32[k]; }
+    else { g_org[k] = (T)P.ghdr->origin[k]; g_inv[k] = (T)P.ghdr->inv_cell[k]; }
+  }
   const int G = P.ghdr->G;
   const bool g_on = P.ghdr->enabled != 0;
-  const double Gd = (double)G;
+  const T Gt = (T)G;
+  const bool want_sq = LLOYD ? (P.inertia != nullptr) : (P.min_sqdist != nullptr);
 
   int changed = 0, tiles_since_flush = 0;
   double inertia = 0.0;
@@ -649,7 +696,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
 #pragma unroll
     for (int j = 0; j < kGPts * D; ++j) {
       const int idx = j * 32 + lane;
-      if (idx < nval * D) stage[idx] = x[wbase * D + idx];
+      if (idx < nval * D) stage[idx] = __ldcs(x + wbase * D + idx);   // touched once: keep L1 for the keys
     }
     __syncwarp();
     double xd[kGPts][D];
@@ -665,9 +712,10 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
       int64_t cidx = 0, mul = 1;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
-        xd[p][k] = valid[p] ? (double)stage[li * D + k] : 0.0;
-        const double t = (xd[p][k] - g_org[k]) * g_inv[k];
-        ok = ok && (t >= 0.0) && (t < Gd);             // false for NaN as well
+        const T xv = valid[p] ? stage[li * D + k] : (T)0;
+        xd[p][k] = (double)xv;
+        const T t = (xv - g_org[k]) * g_inv[k];
+        ok = ok && (t >= (T)0) && (t < Gt);             // false for NaN as well
         const int ck = ok ? (int)t : 0;                 // t >= 0: truncation == floor
         cidx += (int64_t)ck * mul;
         mul *= G;
@@ -694,23 +742,30 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
       const float tau = P.err_coef * sN * sN;
       float best = INFINITY, second = INFINITY;
       int bidx = 0;
-      uint4 ch = first[p];
-      for (unsigned c = 0; c * 8u <= cnt; ++c) {
-        if (c > 0) ch = __ldg(recp[p] + c);
-        const unsigned w[4] = {ch.x, ch.y, ch.z, ch.w};
-#pragma unroll
-        for (int h = 0; h < 8; ++h) {
-          const unsigned e = c * 8u + h;
-          if (e == 0u || e > cnt) continue;
-          const int id = (int)((w[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu);
-          const float4 cr = s_rec[id];
-          const float cn = (D == 4) ? s_cn[id] : 0.f;
-          const float d = screen_dist<D>(xf, cr, cn);
-          const bool lt = d < best;
-          second = fminf(second, lt ? best : d);
-          bidx = lt ? id : bidx;
-          best = fminf(best, d);
+      // the record is a stream of 16-bit ids after the count; 128 bits (8 entries) are resident
+      unsigned long long w0 = ((unsigned long long)first[p].y << 32) | first[p].x;
+      unsigned long long w1 = ((unsigned long long)first[p].w << 32) | first[p].z;
+      int left = 7;                                     // ids left in the resident 128 bits
+      w0 = (w0 >> 16) | (w1 << 48);
+      w1 >>= 16;
+      for (unsigned e = 1; e <= cnt; ++e) {
+        if (left == 0) {
+          const uint4 ch = __ldg(recp[p] + (e >> 3));
+          w0 = ((unsigned long long)ch.y << 32) | ch.x;
+          w1 = ((unsigned long long)ch.w << 32) | ch.z;
+          left = 8;
         }
+        const int id = (int)(w0 & 0xFFFFull);
+        w0 = (w0 >> 16) | (w1 << 48);
+        w1 >>= 16;
+        --left;
+        const float4 cr = s_rec[id];
+        const float cn = (D == 4) ? s_cn[id] : 0.f;
+        const float d = screen_dist<D>(xf, cr, cn);
+        const bool lt = d < best;
+        second = fminf(second, lt ? best : d);
+        bidx = lt ? id : bidx;
+        best = fminf(best, d);
       }
       if (!(second - best > tau) && cnt > 1u) {
         // near tie: exact fp64 pass over the same candidates (ascending ids: lowest index wins)
@@ -768,16 +823,18 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
       if (!valid[p]) continue;
       const int li = p * 32 + lane;
       const int64_t i = wbase + li;
-      const double* c = P.centers + (int64_t)label[p] * D;
       double diff[D], sq = 0.0;
+      if (!LLOYD || want_sq) {
+        const double* c = P.centers + (int64_t)label[p] * D;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        diff[k] = xd[p][k] - __ldg(c + k);
-        sq += diff[k] * diff[k];
+        for (int k = 0; k < D; ++k) {
+          diff[k] = xd[p][k] - __ldg(c + k);
+          sq += diff[k] * diff[k];
+        }
       }
       if (LLOYD) {
-        changed += (P.labels32[i] != label[p]);
-        P.labels32[i] = label[p];
+        changed += (__ldcs(P.labels32 + i) != label[p]);
+        __stcs(P.labels32 + i, label[p]);
         inertia += sq;
         if (P.update) {
           if (acc_in_smem) {
@@ -807,9 +864,9 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
           }
         }
       } else {
-        if (P.labels32) P.labels32[i] = label[p];
-        if (P.labels64) P.labels64[i] = (int64_t)label[p];
-        if (P.min_sqdist) P.min_sqdist[i] = sq;
+        if (P.labels32) __stcs(P.labels32 + i, label[p]);
+        if (P.labels64) __stcs(reinterpret_cast<long long*>(P.labels64) + i, (long long)label[p]);
+        if (P.min_sqdist) __stcs(P.min_sqdist + i, sq);
         if (P.residual) {
 #pragma unroll
           for (int k = 0; k < D; ++k) rstage[li * D + k] = (float)diff[k];
@@ -821,7 +878,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
 #pragma unroll
       for (int j = 0; j < kGPts * D; ++j) {
         const int idx = j * 32 + lane;
-        if (idx < nval * D) P.residual[wbase * D + idx] = rstage[idx];
+        if (idx < nval * D) __stcs(P.residual + wbase * D + idx, rstage[idx]);
       }
       __syncwarp();
     }

@@ -109,7 +109,7 @@ def test_grid_lloyd_step_bit_identical(cuda, K, d):
     outs = []
     for grid in (None, ops.KeyGrid(c)):
         st = kmeans.LloydState(X.shape[0], K, d, cuda)
-        kmeans.lloyd_step(X, c, st, hb, update=True, grid=grid)
+        kmeans.lloyd_step(X, c, st, hb, update=True, grid=grid, want_inertia=True)
         outs.append((st.labels.clone(), st.acc_stats.clone(), float(st.inertia)))
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
