@@ -358,6 +358,38 @@ class _HeadFn(torch.autograd.Function):
         return dx, dmix, None, None, None
 
 
+def allreduce_stack_grads(stack, group=None, average=True):
+    """Data-parallel step of the head: all-reduce the STACKED gradient buffers of a
+    HeadStack in place — a handful of large contiguous tensors (fc1 alone is 197 MB for the Pascal
+    head) instead of 336 per-module ones; the modules' `.grad` views see the reduced values.  Each
+    rank ran its own batch (per-GPU BatchNorm statistics, DDP semantics)."""
+    import torch.distributed as dist
+    if stack.grad is None or not (dist.is_available() and dist.is_initialized()):
+        return
+    ws = dist.get_world_size(group)
+    if ws == 1:
+        return
+    works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True)
+             for _, g in sorted(stack.grad.items())]
+    for w in works:
+        w.wait()
+    if average:
+        for g in stack.grad.values():
+            g.div_(ws)
+
+
+def sync_head_gradients(model, group=None):
+    """All-reduce(mean) the head gradients of every fused stack found under `model` (the
+    OneBinDeltaModel-style containers keep theirs in `_stack`)."""
+    seen = set()
+    for m in model.modules():
+        for name in ("_stack", "_solo"):
+            st = m.__dict__.get(name)
+            if st is not None and id(st) not in seen and st.grad is not None:
+                seen.add(id(st))
+                allreduce_stack_grads(st, group)
+
+
 def run_heads(stack, x, mix, training):
     """All heads of `stack` on features x [B, N0] with mixing weights mix [B, heads per group].
     Returns one [B, O_g] tensor per fc3 group."""

@@ -131,7 +131,7 @@ def _relocate_empty(x, centers_old, state, fix_hi_bits, group):
 
 
 def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, center=True,
-                 use_grid="auto"):
+                 use_grid="auto", _backend=None):
     """Lloyd k-means on this rank's shard `x` [N_local, d] fp64 (CUDA) from explicit centres.
 
     Returns dict(centers [K,d] fp64, labels [N_local] int32, inertia float, n_iter int).
@@ -139,7 +139,14 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     benchmark's fixed-work mode); otherwise sklearn's stopping rules apply.
     """
     import torch.distributed as dist
-    ops._need_cuda(x, init)
+    # _backend: (lloyd_step, finalize) callables standing in for the CUDA entry points — used by the
+    # CPU/gloo tests of this host loop (tests/test_dist_gloo.py); the product path never sets it.
+    if _backend is None:
+        ops._need_cuda(x, init)
+        step_fn, finalize_fn = lloyd_step, finalize
+    else:
+        step_fn, finalize_fn = _backend
+        use_grid = False
     x = x.double().contiguous()
     dev = x.device
     N, d = x.shape
@@ -174,16 +181,16 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     iters = fixed_iters if fixed_iters is not None else max_iter
     for it in range(iters):
         state.acc_stats.zero_()
-        lloyd_step(x, centers, state, hb, update=True, grid=grid)
+        step_fn(x, centers, state, hb, update=True, grid=grid)
         allreduce(state.acc_stats)
-        finalize(state, centers, centers_new, hb)
+        finalize_fn(state, centers, centers_new, hb)
         if fixed_iters is None:
             # one small D2H read per iteration: {changed, n_empty} and the centre shift
             host = torch.cat([state.stats[:1].double(), state.n_empty.double(), state.shift2]).tolist()
             changed, n_empty, shift2 = int(host[0]), int(host[1]), host[2]
             if n_empty > 0:
                 _relocate_empty(x, centers, state, hb, group)
-                finalize(state, centers, centers_new, hb)
+                finalize_fn(state, centers, centers_new, hb)
                 shift2 = float(state.shift2)
         else:
             changed, shift2 = 1, float("inf")
@@ -198,7 +205,7 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     state.acc_stats.zero_()
     state.inertia.zero_()
     if not strict:
-        lloyd_step(x, centers, state, hb, update=False, grid=grid)
+        step_fn(x, centers, state, hb, update=False, grid=grid)
         inertia = allreduce(state.inertia.clone())
     else:
         lab = state.labels.long()
