@@ -341,10 +341,8 @@ def main():
     res_host = torch.empty(N_ROT, 3, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        yd = y_host.to(dev, non_blocking=True)
-        b, r = G.assign_labels(yd, centers)
-        bin_host.copy_(b, non_blocking=True)
-        res_host.copy_(r, non_blocking=True)
+        # public host-to-host API: chunked H2D -> pruned query -> D2H over three streams
+        G.assign_labels_host(y_host, centers, out_bin=bin_host, out_res=res_host)
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()

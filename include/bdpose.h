@@ -250,7 +250,8 @@ int bdp_gemm_tf32_splits(int64_t K, int splits);
  * h [B, ld] pre-activation (GEMM output), F valid columns.
  * training != 0: batch statistics; save_mean / save_invstd [F] are written; running_mean / running_var
  *                [F] are updated in place (NULL: skip) — num_batches_tracked is the caller's.
- * training == 0: normalise with running_mean / running_var.
+ * training == 0: normalise with running_mean / running_var (save_mean / save_invstd, when given,
+ *                receive running_mean and rsqrt(running_var + eps)).
  * a [B, ld] = relu(gamma * xhat + beta)   (columns F..ld-1 are not touched)
  */
 int bdp_bn_relu_fwd(const float* h, int64_t F, int64_t B, int64_t ld, const float* gamma,
@@ -288,6 +289,39 @@ int bdp_head_fc3_bwd(const float* dy, const float* a2, int64_t ld, const float* 
 
 /* out[i] = sum_s parts[s*stride + i], i < n  (split-K reduction, fixed order) */
 int bdp_sum_slabs(const float* parts, int64_t n, int S, int64_t stride, float* out, void* stream);
+/*
+ * Whole-head launch sequences: one call runs every kernel of the forward / backward pass of a stack
+ * of H three-layer heads (OneBinDeltaModel.forward, binDeltaModels.py:112-121, and its autograd
+ * backward).  The heads are split into fc3 groups (OneBinDeltaModel: bin heads with K outputs, res
+ * heads with ndim outputs) that share the mixing weights mix [B, heads per group].
+ */
+#define BDP_HEAD_MAX_GROUPS 4
+typedef struct bdp_head_desc {
+  int32_t H, N0, N1, N2;              /* heads, fc1 in, fc1 out, fc2 out (multiples of 4) */
+  int32_t n_groups, training, precise, reserved;
+  int32_t group_heads[BDP_HEAD_MAX_GROUPS], group_out[BDP_HEAD_MAX_GROUPS];
+  const float *w1, *g1, *be1;         /* [H,N1,N0], [H,N1], [H,N1] */
+  const float *w2, *g2, *be2;         /* [H,N2,N1], [H,N2], [H,N2] */
+  float *rm1, *rv1, *rm2, *rv2;       /* BatchNorm running statistics (updated when training) */
+  const float* w3[BDP_HEAD_MAX_GROUPS];   /* [Hg, O_g, N2] */
+  const float* b3[BDP_HEAD_MAX_GROUPS];   /* [Hg, O_g] */
+  float eps, momentum;
+} bdp_head_desc;
+
+/* floats of the per-call saved-activation buffer: h1|a1 [B,H*N1], h2|a2 [B,H*N2], mean/invstd */
+int64_t bdp_head_saved_floats(const bdp_head_desc* d, int64_t B);
+/* floats of the backward scratch buffer (reusable across calls on one stream) */
+int64_t bdp_head_bwd_workspace_floats(const bdp_head_desc* d, int64_t B);
+/* x [B,N0], mix [B,Hg] -> y[g] [B,O_g]; `saved` is kept by the caller for the backward pass */
+int bdp_head_forward(const bdp_head_desc* d, const float* x, const float* mix, int64_t B,
+                     float* saved, float* const* y, void* stream);
+/* dy[g] [B,O_g] -> stacked parameter gradients (dense, zeros included), dmix [B,Hg] (NULL: skip),
+ * dx [B,N0] (NULL: skip) */
+int bdp_head_backward(const bdp_head_desc* d, const float* x, const float* mix, int64_t B,
+                      const float* saved, const float* const* dy, float* ws, float* dw1, float* dg1,
+                      float* dbe1, float* dw2, float* dg2, float* dbe2, float* const* dw3,
+                      float* const* db3, float* dmix, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

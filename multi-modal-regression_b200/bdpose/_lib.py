@@ -55,7 +55,26 @@ SIGNATURES = {
     "bdp_head_fc3_bwd": (_int, [_p, _p, _i64, _p, _p, _p, _i64, _int, _int, _int, _p, _p, _p, _p,
                                 _p]),
     "bdp_sum_slabs": (_int, [_p, _i64, _int, _i64, _p, _p]),
+    "bdp_head_saved_floats": (_i64, [_p, _i64]),
+    "bdp_head_bwd_workspace_floats": (_i64, [_p, _i64]),
+    "bdp_head_forward": (_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "bdp_head_backward": (_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                 _p]),
 }
+
+HEAD_MAX_GROUPS = 4
+
+
+class HeadDesc(C.Structure):
+    """struct bdp_head_desc (include/bdpose.h)"""
+    _fields_ = [("H", C.c_int32), ("N0", C.c_int32), ("N1", C.c_int32), ("N2", C.c_int32),
+                ("n_groups", C.c_int32), ("training", C.c_int32), ("precise", C.c_int32),
+                ("reserved", C.c_int32),
+                ("group_heads", C.c_int32 * HEAD_MAX_GROUPS), ("group_out", C.c_int32 * HEAD_MAX_GROUPS),
+                ("w1", _p), ("g1", _p), ("be1", _p), ("w2", _p), ("g2", _p), ("be2", _p),
+                ("rm1", _p), ("rv1", _p), ("rm2", _p), ("rv2", _p),
+                ("w3", _p * HEAD_MAX_GROUPS), ("b3", _p * HEAD_MAX_GROUPS),
+                ("eps", C.c_float), ("momentum", C.c_float)]
 
 _lib = None
 

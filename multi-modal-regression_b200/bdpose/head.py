@@ -19,6 +19,7 @@ Precision: the GEMMs run on the tensor cores straight from the fp32 master weigh
 tolerance 1e-5 of the tensor scale in the tests); "tf32" issues one MMA per k-step — the
 reduced-precision head GEMM of the north star (tolerance 2e-3), tighter than bf16.
 """
+import ctypes as C
 import os
 
 import torch
@@ -139,6 +140,10 @@ _BUFS = (("rm1", "bn1", "running_mean"), ("rv1", "bn1", "running_var"),
          ("nb1", "bn1", "num_batches_tracked"), ("nb2", "bn2", "num_batches_tracked"))
 
 
+def _no_stack():
+    return None
+
+
 class HeadStack:
     """Keeps the parameters of a list of identical 3-layer MLP modules (fc1, bn1, fc2, bn2, fc3) in
     STACKED device buffers that the grouped kernels consume, while every module keeps its own
@@ -155,25 +160,35 @@ class HeadStack:
         self.buf = None
         self.grad = None
         self.anchor = None
+        self.plists = None
+        self.descs = {}
+        self.ws = None
+        self._expected = None
+        self.gviews = None       # key -> tuple of per-module views into the stacked gradient buffers
+        self.stacked = None      # key -> nn.Parameter over the stacked weights (opt-in fast path)
+
+    # A stack is a cache over its modules (device buffers, ctypes descriptors): copies and pickles
+    # of a model drop it and rebuild lazily on the next forward.
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_no_stack, ())
 
     # -- storage ---------------------------------------------------------------------------------
+    def _probe(self):
+        """data_ptr of three tensors per head, read through the module dicts (nn.Module.__getattr__
+        costs ~1 us per hop; this runs on every forward)."""
+        out = []
+        for m in self.heads:
+            mods = m._modules
+            out.append(mods["fc1"]._parameters["weight"].data_ptr())
+            out.append(mods["bn1"]._buffers["running_mean"].data_ptr())
+            out.append(mods["fc3"]._parameters["weight"].data_ptr())
+        return out
+
     def _is_current(self):
-        if self.buf is None:
-            return False
-        w1 = self.buf["w1"]
-        for i, m in enumerate(self.heads):
-            p = m.fc1.weight
-            if p.device != w1.device or p.data_ptr() != w1[i].data_ptr():
-                return False
-            if m.bn1.running_mean.data_ptr() != self.buf["rm1"][i].data_ptr():
-                return False
-        off = 0
-        for gi, g in enumerate(self.groups):
-            w3 = self.buf["w3"][gi]
-            for i, m in enumerate(g):
-                if m.fc3.weight.data_ptr() != w3[i].data_ptr():
-                    return False
-        return True
+        return self.buf is not None and self._probe() == self._expected
 
     def ensure(self):
         if self._is_current():
@@ -182,6 +197,8 @@ class HeadStack:
         dev = heads[0].fc1.weight.device
         if dev.type != "cuda":
             raise RuntimeError("bdpose heads run on CUDA only (parameters are on %s); call .cuda()" % dev)
+        if len(self.groups) > L.HEAD_MAX_GROUPS or len({len(g) for g in self.groups}) != 1:
+            raise RuntimeError("head stack: 1..%d fc3 groups with the same number of heads each" % L.HEAD_MAX_GROUPS)
         buf = {}
         with torch.no_grad():
             for key, sub, name in _SLOTS:
@@ -207,9 +224,40 @@ class HeadStack:
                 buf["b3"].append(b)
         self.buf = buf
         self.grad = None
+        self.gviews = None
+        self.stacked = None
+        self.plists = self._param_lists()
+        self.descs = {}
+        self.ws = None
+        self._expected = self._probe()
         if self.anchor is None or self.anchor.device != dev:
             self.anchor = torch.zeros(1, device=dev, requires_grad=True)
         return buf
+
+    def desc(self, training, precise):
+        """struct bdp_head_desc for the current storage (cached per (training, precise))."""
+        key = (bool(training), bool(precise))
+        d = self.descs.get(key)
+        if d is None:
+            buf = self.buf
+            H, N1, N0 = buf["w1"].shape
+            d = L.HeadDesc()
+            d.H, d.N0, d.N1, d.N2 = H, N0, N1, buf["w2"].shape[1]
+            d.n_groups = len(self.groups)
+            d.training, d.precise = int(key[0]), int(key[1])
+            for g, (w3, b3) in enumerate(zip(buf["w3"], buf["b3"])):
+                d.group_heads[g], d.group_out[g] = w3.shape[0], w3.shape[1]
+                d.w3[g], d.b3[g] = w3.data_ptr(), b3.data_ptr()
+            for f in ("w1", "g1", "be1", "w2", "g2", "be2", "rm1", "rv1", "rm2", "rv2"):
+                setattr(d, f, buf[f].data_ptr())
+            d.eps, d.momentum = BN_EPS, BN_MOMENTUM
+            self.descs[key] = d
+        return d
+
+    def workspace(self, n_floats, dev):
+        if self.ws is None or self.ws.numel() < n_floats or self.ws.device != dev:
+            self.ws = torch.empty(n_floats, dtype=torch.float32, device=dev)
+        return self.ws
 
     # -- gradients ---------------------------------------------------------------------------------
     def _param_lists(self):
@@ -219,34 +267,87 @@ class HeadStack:
             out["b3_%d" % gi] = [m.fc3.bias for m in g]
         return out
 
-    def deposit(self, grads):
-        """Hand the stacked gradients of one backward call to the per-module Parameters: `.grad`
-        becomes a view into the stacked gradient (no copies); a second backward before the next
-        zero_grad accumulates (two forwards, one backward: learnGeodesicBDModel.py:116-120, 183).
-        Every head gets a dense gradient, zeros included, as in the reference."""
-        plists = self._param_lists()
-        first = self.heads[0].fc1.weight.grad
-        if first is None:
-            for key, plist in plists.items():
-                gk = grads[key]
-                for i, p in enumerate(plist):
-                    p.grad = gk[i]
-            self.grad = grads
+    def _keys(self):
+        keys = ["w1", "g1", "be1", "w2", "g2", "be2"]
+        for g in range(len(self.groups)):
+            keys += ["w3_%d" % g, "b3_%d" % g]
+        return keys
+
+    def _stacked_tensor(self, key):
+        if key.startswith("w3_"):
+            return self.buf["w3"][int(key[3:])]
+        if key.startswith("b3_"):
+            return self.buf["b3"][int(key[3:])]
+        return self.buf[key]
+
+    def grad_buffers(self):
+        """The persistent stacked gradient buffers (one per stacked parameter tensor) and the
+        per-module views into them, created once per storage generation."""
+        if self.grad is None:
+            self.grad = {k: torch.empty_like(self._stacked_tensor(k)) for k in self._keys()}
+            self.gviews = {k: g.unbind(0) for k, g in self.grad.items()}
+        return self.grad
+
+    def stacked_parameters(self):
+        """Opt-in fast path for new training code: ONE nn.Parameter per stacked tensor (10 for
+        OneBinDeltaModel instead of 336 per-module ones) sharing memory with the per-module
+        Parameters.  After this call backward() leaves its gradients on these (and only these), so an
+        optimizer built over them steps the same weights with 30x fewer tensors to visit."""
+        self.ensure()
+        if self.stacked is None:
+            self.stacked = {k: torch.nn.Parameter(self._stacked_tensor(k)) for k in self._keys()}
+        return [self.stacked[k] for k in self._keys()]
+
+    def grads_are_fresh(self):
+        """True when no gradient is currently held (first backward after zero_grad(set_to_none))."""
+        if self.stacked is not None:
+            return self.stacked["w1"].grad is None
+        return self.plists["w1"][0].grad is None and self.plists["w1"][-1].grad is None
+
+    def grads_are_mine(self):
+        if self.grad is None:
+            return False
+        if self.stacked is not None:
+            g = self.stacked["w1"].grad
+            return g is not None and g.data_ptr() == self.grad["w1"].data_ptr()
+        first, last = self.plists["w1"][0].grad, self.plists["w1"][-1].grad
+        return first is not None and last is not None and \
+            first.data_ptr() == self.grad["w1"].data_ptr() and \
+            last.data_ptr() == self.grad["w1"][-1].data_ptr()
+
+    def publish(self):
+        """Point every Parameter's .grad at its view of the persistent stacked gradient buffers
+        (which backward() has just filled).  Every head gets a dense gradient, zeros included, as in
+        the reference.  NOTE: the buffers are reused by the next fresh backward, so a
+        reference to an old `.grad` kept across zero_grad(set_to_none=True) sees the new values."""
+        if self.stacked is not None:
+            for k, p in self.stacked.items():
+                p.grad = self.grad[k]
             return
-        mine = self.grad is not None and first.data_ptr() == self.grad["w1"][0].data_ptr() and \
-            self.heads[-1].fc1.weight.grad is not None and \
-            self.heads[-1].fc1.weight.grad.data_ptr() == self.grad["w1"][-1].data_ptr()
-        if mine:
-            for key in plists:
+        for key, plist in self.plists.items():
+            for p, v in zip(plist, self.gviews[key]):
+                p.grad = v
+
+    def accumulate(self, grads):
+        """Second backward before the next zero_grad (two forwards, one backward:
+        learnGeodesicBDModel.py:116-120, 183), or foreign gradients already present."""
+        if self.grads_are_mine():
+            for key in self.grad:
                 self.grad[key].add_(grads[key])
-        else:
-            for key, plist in plists.items():
-                gk = grads[key]
-                for i, p in enumerate(plist):
-                    if p.grad is None:
-                        p.grad = gk[i].clone()
-                    else:
-                        p.grad.add_(gk[i])
+            return
+        if self.stacked is not None:
+            for k, p in self.stacked.items():
+                if p.grad is None:
+                    p.grad = grads[k]
+                else:
+                    p.grad.add_(grads[k])
+            return
+        for key, plist in self.plists.items():
+            for p, v in zip(plist, grads[key].unbind(0)):
+                if p.grad is None:
+                    p.grad = v.clone()
+                else:
+                    p.grad.add_(v)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -260,101 +361,86 @@ class _HeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mix, anchor, stack, training):
         buf = stack.ensure()
-        w1, w2 = buf["w1"], buf["w2"]
-        H, N1, N0 = w1.shape
-        N2 = w2.shape[1]
+        H, N1, N0 = buf["w1"].shape
         B = x.shape[0]
         dev = x.device
-        F1, F2 = H * N1, H * N2
-        if x.shape[1] != N0:
-            raise RuntimeError("head: input has %d features, fc1 expects %d" % (x.shape[1], N0))
-        if N0 % 4 or N1 % 4 or N2 % 4:
-            raise RuntimeError("head: layer widths must be multiples of 4 (got %d, %d, %d)" % (N0, N1, N2))
+        if x.dim() != 2 or x.shape[1] != N0:
+            raise RuntimeError("head: input has %s features, fc1 expects %d" % (tuple(x.shape[1:]), N0))
         if training and B < 2:
             raise ValueError("Expected more than 1 value per channel when training, got input size "
                              "[%d, %d]" % (B, N1))
-        x = x.detach().float().contiguous()
-        mix = mix.detach().float().contiguous()
-        # fc1: H1 [B, H*N1] = X [B, N0] (lanes, K-major) x W1 [H*N1, N0] (streamed, K-major)
-        h1 = torch.empty((B, F1), dtype=torch.float32, device=dev)
-        gemm_tf32(x, 0, N0, 0, w1, 0, N0, 0, h1, 0, F1, 0, B, F1, N0)
-        a1, m1, is1 = bn_relu_fwd(h1, buf["g1"].view(-1), buf["be1"].view(-1), buf["rm1"].view(-1),
-                                  buf["rv1"].view(-1), training)
-        # fc2 (grouped): H2_g [B, N2] = A1_g [B, N1] (columns g*N1.. of a1) x W2_g [N2, N1]
-        h2 = torch.empty((B, F2), dtype=torch.float32, device=dev)
-        gemm_tf32(a1, 0, F1, N1, w2, 0, N1, N2 * N1, h2, 0, F2, N2, B, N2, N1, G=H)
-        a2, m2, is2 = bn_relu_fwd(h2, buf["g2"].view(-1), buf["be2"].view(-1), buf["rm2"].view(-1),
-                                  buf["rv2"].view(-1), training)
+        Hg = buf["w3"][0].shape[0]
+        if mix.dim() != 2 or mix.shape[0] != B or mix.shape[1] != Hg:
+            raise RuntimeError("head: mixing weights are %s for a batch of %d and %d heads per group"
+                               % (tuple(mix.shape), B, Hg))
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        mix = mix.detach()
+        if mix.dtype != torch.float32 or not mix.is_contiguous():
+            mix = mix.float().contiguous()
+        desc = stack.desc(training, PRECISION == "fp32")
+        lib = L.lib()
+        dref = C.byref(desc)
+        saved = torch.empty(lib.bdp_head_saved_floats(dref, B), dtype=torch.float32, device=dev)
+        ys = [torch.empty((B, w3.shape[1]), dtype=torch.float32, device=dev) for w3 in buf["w3"]]
+        yptr = (C.c_void_p * len(ys))(*[y.data_ptr() for y in ys])
+        with torch.cuda.device(dev):
+            st = lib.bdp_head_forward(dref, x.data_ptr(), mix.data_ptr(), B, saved.data_ptr(), yptr,
+                                      L.stream_ptr())
+        L.check(st, "bdp_head_forward")
         if training:
             buf["nb1"] += 1
             buf["nb2"] += 1
-        ys, off = [], 0
-        for w3, b3 in zip(buf["w3"], buf["b3"]):
-            Hg = w3.shape[0]
-            if mix.shape[1] != Hg:
-                raise RuntimeError("head: mixing weights have %d columns for %d heads" % (mix.shape[1], Hg))
-            ys.append(fc3_fwd(a2[:, off * N2:(off + Hg) * N2], w3, b3, mix))
-            off += Hg
         ctx.stack = stack
-        ctx.saved = (x, mix, h1, a1, m1, is1, h2, a2, m2, is2)
+        ctx.saved = (x, mix, saved)
         ctx.training = training
-        ctx.dims = (H, N0, N1, N2, B)
+        ctx.precise = PRECISION == "fp32"
         return tuple(ys)
 
     @staticmethod
     def backward(ctx, *dys):
         stack = ctx.stack
         buf = stack.buf
-        x, mix, h1, a1, m1, is1, h2, a2, m2, is2 = ctx.saved
-        H, N0, N1, N2, B = ctx.dims
-        F1, F2 = H * N1, H * N2
-        training = ctx.training
+        x, mix, saved = ctx.saved
+        B = x.shape[0]
         dev = x.device
-        w1, w2 = buf["w1"], buf["w2"]
-        want_dmix = ctx.needs_input_grad[1]
-        if not training:
-            m1, is1 = buf["rm1"].view(-1), torch.rsqrt(buf["rv1"].view(-1) + BN_EPS)
-            m2, is2 = buf["rm2"].view(-1), torch.rsqrt(buf["rv2"].view(-1) + BN_EPS)
-        grads = {}
-        # fc3 backward, group by group, each filling its column slice of da2
-        da2 = torch.empty_like(a2)
-        dmix, off = None, 0
-        for gi, (w3, b3) in enumerate(zip(buf["w3"], buf["b3"])):
-            Hg, O = w3.shape[0], w3.shape[1]
-            dy = dys[gi]
-            dy = torch.zeros((B, O), device=dev) if dy is None else dy.contiguous().float()
-            sl = slice(off * N2, (off + Hg) * N2)
-            _, d_w, d_b, d_m = fc3_bwd(dy, a2[:, sl], w3, b3, mix, want_dmix, da2=da2[:, sl])
-            grads["w3_%d" % gi], grads["b3_%d" % gi] = d_w, d_b
-            if want_dmix:
-                dmix = d_m if dmix is None else dmix + d_m
-            off += Hg
-        # bn2 backward
-        dh2, dg2, dbe2 = bn_relu_bwd(da2, a2, h2, buf["g2"].view(-1), m2, is2, training)
-        # fc2 wgrad: dW2_g [N2, N1] = sum_b dH2_g[b, :]^T A1_g[b, :]   (both MN-major, K = batch)
-        dw2 = torch.empty_like(w2)
-        gemm_tf32(dh2, 1, F2, N2, a1, 1, F1, N1, dw2, 0, N1, N2 * N1, N2, N1, B, G=H)
-        # fc2 dgrad: dA1_g [B, N1] = dH2_g [B, N2] (K-major) x W2_g ([k = N2 rows, n = N1 contiguous]: MN-major)
-        da1 = torch.empty_like(a1)
-        gemm_tf32(dh2, 0, F2, N2, w2, 1, N1, N2 * N1, da1, 0, F1, N1, B, N1, N2, G=H)
-        # bn1 backward
-        dh1, dg1, dbe1 = bn_relu_bwd(da1, a1, h1, buf["g1"].view(-1), m1, is1, training)
-        # fc1 wgrad: dW1 [H*N1, N0] = dH1^T X   (both MN-major, K = batch)
-        dw1 = torch.empty_like(w1)
-        gemm_tf32(dh1, 1, F1, 0, x, 1, N0, 0, dw1, 0, N0, 0, F1, N0, B)
-        grads.update(w1=dw1, g1=dg1.view(H, N1), be1=dbe1.view(H, N1), w2=dw2, g2=dg2.view(H, N2),
-                     be2=dbe2.view(H, N2))
-        stack.deposit(grads)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            # fc1 dgrad: dX [B, N0] = dH1 [B, H*N1] (K-major) x W1 ([k = H*N1 rows, n = N0]: MN-major), split-K
-            n_tiles = (N0 + 255) // 256
-            splits = gemm_splits(F1, max(1, min(64, L.lib().bdp_sm_count() // n_tiles)))
-            parts = torch.empty((splits, B, N0), dtype=torch.float32, device=dev)
-            gemm_tf32(dh1, 0, F1, 0, w1, 1, N0, 0, parts, 0, N0, 0, B, N0, F1, splits=splits,
-                      c_ss=B * N0)
-            dx = torch.empty((B, N0), dtype=torch.float32, device=dev)
-            sum_slabs(parts, B * N0, splits, B * N0, dx)
+        desc = stack.desc(ctx.training, ctx.precise)
+        lib = L.lib()
+        dref = C.byref(desc)
+        dyl = []
+        for dy, w3 in zip(dys, buf["w3"]):
+            if dy is None:
+                dy = torch.zeros((B, w3.shape[1]), dtype=torch.float32, device=dev)
+            elif dy.dtype != torch.float32 or not dy.is_contiguous():
+                dy = dy.float().contiguous()
+            dyl.append(dy)
+        n = len(dyl)
+        ws = stack.workspace(lib.bdp_head_bwd_workspace_floats(dref, B), dev)
+        # first backward since zero_grad: the kernels write the persistent stacked gradient buffers
+        # directly; otherwise they write temporaries that are accumulated
+        fresh = stack.grads_are_fresh()
+        if fresh:
+            grads = stack.grad_buffers()
+        else:
+            grads = {k: torch.empty_like(stack._stacked_tensor(k)) for k in stack._keys()}
+        dmix = torch.empty_like(mix) if ctx.needs_input_grad[1] else None
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        arr = C.c_void_p * n
+        with torch.cuda.device(dev):
+            st = lib.bdp_head_backward(
+                dref, x.data_ptr(), mix.data_ptr(), B, saved.data_ptr(),
+                arr(*[t.data_ptr() for t in dyl]), ws.data_ptr(),
+                grads["w1"].data_ptr(), grads["g1"].data_ptr(), grads["be1"].data_ptr(),
+                grads["w2"].data_ptr(), grads["g2"].data_ptr(), grads["be2"].data_ptr(),
+                arr(*[grads["w3_%d" % g].data_ptr() for g in range(n)]),
+                arr(*[grads["b3_%d" % g].data_ptr() for g in range(n)]),
+                L.ptr(dmix), L.ptr(dx), L.stream_ptr())
+        L.check(st, "bdp_head_backward")
+        if fresh:
+            stack.publish()
+        else:
+            stack.accumulate(grads)
         return dx, dmix, None, None, None
 
 
@@ -463,6 +549,7 @@ def bench(dev, peaks):
     m = _pascal_model(C, K).train()
     keys = torch.randn(K, 3, device=dev)
     n_params = sum(p.numel() for p in m.bin_models.parameters()) + sum(p.numel() for p in m.res_models.parameters())
+    params = list(m.parameters())
     for B in (32, 96):
         x = torch.randn(B, 2048, device=dev, requires_grad=True)
         lab = torch.randint(0, C, (B, 1), device=dev)
@@ -474,7 +561,7 @@ def bench(dev, peaks):
                 m(x, lab)
 
         def step():
-            for p in m.parameters():
+            for p in params:                       # optimizer.zero_grad(set_to_none=True)
                 p.grad = None
             y1, y2 = m(x, lab)
             lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
@@ -523,8 +610,10 @@ def bench(dev, peaks):
     tgt = torch.randn(B, 3, device=dev)
     keys = torch.randn(200, 3, device=dev)
 
+    oparams = list(om.parameters())
+
     def ostep():
-        for p in om.parameters():
+        for p in oparams:
             p.grad = None
         y1, y2 = om.forward_features(x, lab)
         lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)

@@ -267,12 +267,13 @@ def _scratch_grid(centers):
 
 
 def assign_nearest(x, centers, want_residual=True, want_sqdist=False, label_dtype=torch.int64,
-                   grid="auto"):
+                   grid="auto", out_labels=None, out_residual=None):
     """kmeans.predict + residual (binDeltaGenerators.py:27-30).  x [N,d] fp32|fp64, centers [K,d].
 
     grid: "auto" (build a key grid when it pays off), None (brute-force scan) or a KeyGrid built for
-    exactly these centres.  Returns (labels [N] label_dtype, residual [N,d] fp32 | None,
-    sqdist [N] fp64 | None)."""
+    exactly these centres.  out_labels / out_residual: preallocated contiguous CUDA outputs (the
+    pipelined host-to-host path reuses its buffers).  Returns (labels [N] label_dtype,
+    residual [N,d] fp32 | None, sqdist [N] fp64 | None)."""
     _need_cuda(x, centers)
     if x.dtype not in (torch.float32, torch.float64):
         x = x.double()
@@ -283,9 +284,22 @@ def assign_nearest(x, centers, want_residual=True, want_sqdist=False, label_dtyp
     if centers.shape[1] != d:
         raise ValueError("assign_nearest: x has %d columns, centers %d" % (d, centers.shape[1]))
     dev = x.device
-    lab32 = torch.empty(N, dtype=torch.int32, device=dev) if label_dtype == torch.int32 else None
-    lab64 = torch.empty(N, dtype=torch.int64, device=dev) if label_dtype != torch.int32 else None
-    res = torch.empty((N, d), dtype=torch.float32, device=dev) if want_residual else None
+    if out_labels is not None:
+        if out_labels.dtype != label_dtype or out_labels.numel() != N or not out_labels.is_contiguous() \
+                or out_labels.device != dev:
+            raise ValueError("assign_nearest: out_labels must be a contiguous %s [%d] tensor on %s" % (label_dtype, N, dev))
+    if out_residual is not None:
+        if out_residual.dtype != torch.float32 or tuple(out_residual.shape) != (N, d) or \
+                not out_residual.is_contiguous() or out_residual.device != dev:
+            raise ValueError("assign_nearest: out_residual must be a contiguous float32 [%d, %d] tensor on %s" % (N, d, dev))
+    lab32 = lab64 = None
+    if label_dtype == torch.int32:
+        lab32 = out_labels if out_labels is not None else torch.empty(N, dtype=torch.int32, device=dev)
+    else:
+        lab64 = out_labels if out_labels is not None else torch.empty(N, dtype=torch.int64, device=dev)
+    res = None
+    if want_residual:
+        res = out_residual if out_residual is not None else torch.empty((N, d), dtype=torch.float32, device=dev)
     sq = torch.empty(N, dtype=torch.float64, device=dev) if want_sqdist else None
     if isinstance(grid, str):
         if grid != "auto":

@@ -28,6 +28,69 @@ def assign_labels(y, centers):
     return lab, res
 
 
+def assign_labels_host(y, centers, out_bin=None, out_res=None, chunk_rows=1 << 20, device=None):
+    """Host-to-host label generation for arrays that live in (pinned) host memory: y [N,d] CPU
+    tensor -> (bin [N] int64, res [N,d] fp32) pinned CPU tensors.  The rows are cut into chunks that
+    run through three streams — H2D of chunk i+1, the pruned query of chunk i and D2H of chunk i-1
+    overlap (PCIe is full duplex) — and the key grid of the dictionary is built once.  The outputs
+    are complete when the call returns."""
+    if not isinstance(y, torch.Tensor):
+        y = torch.as_tensor(np.ascontiguousarray(y))
+    if y.is_cuda:
+        raise ValueError("assign_labels_host takes host memory; use assign_labels for device tensors")
+    if y.dtype not in (torch.float32, torch.float64):
+        y = y.double()
+    y = y.contiguous()
+    N, d = y.shape
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    c = _cuda(centers, torch.float64).to(dev).contiguous()
+    if out_bin is None:
+        out_bin = torch.empty(N, dtype=torch.int64).pin_memory()
+    if out_res is None:
+        out_res = torch.empty((N, d), dtype=torch.float32).pin_memory()
+    if N == 0:
+        return out_bin, out_res
+    chunk_rows = max(1, min(int(chunk_rows), N))
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_run, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    for s_ in (s_in, s_run, s_out):
+        s_.wait_stream(cur)
+    xb = [torch.empty((chunk_rows, d), dtype=y.dtype, device=dev) for _ in range(2)]
+    lb = [torch.empty(chunk_rows, dtype=torch.int64, device=dev) for _ in range(2)]
+    rb = [torch.empty((chunk_rows, d), dtype=torch.float32, device=dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_run = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    with torch.cuda.stream(s_run):
+        grid = ops.KeyGrid(c) if ops.KeyGrid.supported(c.shape[0], d, chunk_rows) else None
+    for i, r0 in enumerate(range(0, N, chunk_rows)):
+        r1 = min(N, r0 + chunk_rows)
+        n, k = r1 - r0, i % 2
+        with torch.cuda.stream(s_in):
+            if i >= 2:
+                s_in.wait_event(ev_run[k])            # chunk i-2 has consumed this input buffer
+            xb[k][:n].copy_(y[r0:r1], non_blocking=True)
+            ev_in[k].record(s_in)
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(ev_in[k])
+            if i >= 2:
+                s_run.wait_event(ev_out[k])           # chunk i-2's results have left the device
+            ops.assign_nearest(xb[k][:n], c, grid=grid, out_labels=lb[k][:n], out_residual=rb[k][:n])
+            ev_run[k].record(s_run)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_run[k])
+            out_bin[r0:r1].copy_(lb[k][:n], non_blocking=True)
+            out_res[r0:r1].copy_(rb[k][:n], non_blocking=True)
+            ev_out[k].record(s_out)
+    cur.wait_stream(s_out)
+    cur.wait_stream(s_run)
+    cur.wait_stream(s_in)
+    # the device buffers were allocated on `cur`, which now waits for every side stream: their reuse
+    # by later allocations is ordered after the last copy
+    torch.cuda.current_stream(dev).synchronize()
+    return out_bin, out_res
+
+
 def assign_labels_riemannian(y, centers, key_rot=None):
     """RBDGenerator targets (binDeltaGenerators.py:125-139): ydata_rot = get_R(y), bin = predict(y),
     res = get_y(R_key[bin]^T R).  Returns (bin int64, res [N,3] fp32, rot [N,3,3] fp32)."""

@@ -144,6 +144,13 @@ class OneBinDeltaModel(nn.Module):
             object.__setattr__(self, '_stack', st)
         return st
 
+    def stacked_head_parameters(self):
+        """Opt-in fast path for new training loops: the 2*C heads' weights as 10 stacked
+        nn.Parameters (shared memory with the per-module ones).  Build the optimizer over
+        `list(model.feature_model.parameters()) + model.stacked_head_parameters()`; backward() then
+        leaves the head gradients on the stacked Parameters only."""
+        return self._heads().stacked_parameters()
+
     def forward_features(self, feat, label=None, mix=None):
         """Heads only, on precomputed features [B, N0]: label [B,1] int64 or mix [B, C] weights."""
         if mix is None:

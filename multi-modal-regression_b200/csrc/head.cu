@@ -61,6 +61,10 @@ bn_relu_fwd_kernel(const float* __restrict__ h, int64_t F, int B, int64_t ld,
   } else if (ok) {
     mean = (double)running_mean[f];
     invstd = 1.0 / sqrt((double)running_var[f] + (double)eps);
+    if (wy == 0) {                       // the eval-mode backward reads them like batch statistics
+      if (save_mean) save_mean[f] = (float)mean;
+      if (save_invstd) save_invstd[f] = (float)invstd;
+    }
   }
   if (!ok) return;
   const float m = (float)mean, is = (float)invstd, g = gamma[f], bt = beta[f];

@@ -126,3 +126,18 @@ def test_grid_kmeans_fit_identical(cuda):
     assert a["n_iter"] == b["n_iter"]
     assert torch.equal(a["labels"], b["labels"])
     assert torch.equal(a["centers"], b["centers"])
+
+
+@pytest.mark.parametrize("N,chunk", [(250_000, 65_536), (70_001, 1 << 20), (5, 2)])
+def test_host_to_host_pipeline(cuda, N, chunk):
+    """assign_labels_host (chunked three-stream pipeline from pinned host memory) returns exactly
+    what the one-shot device call returns."""
+    import binDeltaGenerators as G
+    rng = np.random.default_rng(N)
+    aa = rand_rot(rng, N + 500)[0]
+    y = torch.from_numpy(aa[:N].astype(np.float32)).pin_memory()
+    c = torch.from_numpy(aa[N:]).to(cuda)
+    b_h, r_h = G.assign_labels_host(y, c, chunk_rows=chunk)
+    b_d, r_d = G.assign_labels(y.to(cuda), c)
+    assert b_h.dtype == torch.int64 and not b_h.is_cuda
+    assert torch.equal(b_h, b_d.cpu()) and torch.equal(r_h, r_d.cpu())
