@@ -629,7 +629,7 @@ def bench(dev, peaks):
 
 
 def profile(dev):
-    """A few head steps for ncu (profiles/prof_targets.py head)."""
+    """One tf32 training step of the Pascal head for ncu (profiles/prof_targets.py head)."""
     from . import ops
     m = _pascal_model().train()
     B, K = 32, 200
@@ -638,9 +638,10 @@ def profile(dev):
     bins = torch.randint(0, K, (B,), device=dev)
     tgt = torch.randn(B, 3, device=dev)
     keys = torch.randn(K, 3, device=dev)
-    for _ in range(3):
-        for p in m.parameters():
-            p.grad = None
+    set_precision("tf32")
+    try:
         y1, y2 = m(x, lab)
         lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
         (lc + lr).backward()
+    finally:
+        set_precision("fp32")

@@ -19,6 +19,9 @@ import torch
 from bdpose import ops
 
 
+_side_streams = {}     # device index -> (H2D, compute, D2H) streams of assign_labels_host
+
+
 # ---- bulk GPU API ------------------------------------------------------------------------------------
 def assign_labels(y, centers):
     """kmeans.predict + residual for a whole array (binDeltaGenerators.py:27-30).
@@ -28,7 +31,7 @@ def assign_labels(y, centers):
     return lab, res
 
 
-def assign_labels_host(y, centers, out_bin=None, out_res=None, chunk_rows=1 << 20, device=None):
+def assign_labels_host(y, centers, out_bin=None, out_res=None, chunk_rows=1 << 19, device=None):
     """Host-to-host label generation for arrays that live in (pinned) host memory: y [N,d] CPU
     tensor -> (bin [N] int64, res [N,d] fp32) pinned CPU tensors.  The rows are cut into chunks that
     run through three streams — H2D of chunk i+1, the pruned query of chunk i and D2H of chunk i-1
@@ -52,7 +55,9 @@ def assign_labels_host(y, centers, out_bin=None, out_res=None, chunk_rows=1 << 2
         return out_bin, out_res
     chunk_rows = max(1, min(int(chunk_rows), N))
     cur = torch.cuda.current_stream(dev)
-    s_in, s_run, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    if dev.index not in _side_streams:
+        _side_streams[dev.index] = tuple(torch.cuda.Stream(dev) for _ in range(3))
+    s_in, s_run, s_out = _side_streams[dev.index]
     for s_ in (s_in, s_run, s_out):
         s_.wait_stream(cur)
     xb = [torch.empty((chunk_rows, d), dtype=y.dtype, device=dev) for _ in range(2)]
@@ -61,8 +66,13 @@ def assign_labels_host(y, centers, out_bin=None, out_res=None, chunk_rows=1 << 2
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_run = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
-    with torch.cuda.stream(s_run):
-        grid = ops.KeyGrid(c) if ops.KeyGrid.supported(c.shape[0], d, chunk_rows) else None
+    # every buffer is allocated on the caller's stream (a block freed under a side stream could not
+    # be reused by the next call without a cudaMalloc); only the work runs on the side streams
+    grid = None
+    if ops.KeyGrid.supported(c.shape[0], d, chunk_rows):
+        gbuf = torch.empty(ops.L.lib().bdp_keygrid_bytes(c.shape[0], d), dtype=torch.uint8, device=dev)
+        with torch.cuda.stream(s_run):
+            grid = ops.KeyGrid(c, gbuf)
     for i, r0 in enumerate(range(0, N, chunk_rows)):
         r1 = min(N, r0 + chunk_rows)
         n, k = r1 - r0, i % 2
