@@ -247,7 +247,10 @@ __device__ __forceinline__ float pose_row(const LossParams& P, int64_t row, int 
 // ---- logits phase, vector path: K % 4 == 0, rows 16-byte aligned, K <= KV*128 -----------------
 template <int KV>
 __device__ __forceinline__ void row_load(const LossParams& P, int64_t row, int lane, int nvec,
-                                         float4 v[KV]) {
+                                         float4 v[KV], int& tgt) {
+  // the target bin is fetched with the row: read right before its use it exposed one full memory
+  // latency per row (15 % of all stall samples)
+  tgt = (int)__ldg(P.bin_true + row);
   const float4* src = reinterpret_cast<const float4*>(P.logits + row * P.ld);
 #pragma unroll
   for (int j = 0; j < KV; ++j) {
@@ -259,34 +262,41 @@ __device__ __forceinline__ void row_load(const LossParams& P, int64_t row, int l
 
 template <int KV>
 __device__ __forceinline__ void row_softmax_ce(const LossParams& P, int64_t row, int lane,
-                                               int nvec, float4 v[KV], float& ce, int& amax) {
-  // max + argmax (lowest index wins)
-  float m = -INFINITY;
+                                               int nvec, float4 v[KV], int tgt, float& ce, int& amax) {
+  // max, then argmax (lowest index wins).  The warp maximum goes through the integer REDUX unit on
+  // an order-preserving key (one instruction instead of a 5-step shuffle tree); only the lanes that
+  // hold the maximum look for its position.
+  float lm = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < KV; ++j) lm = fmaxf(lm, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+  const unsigned lb = __float_as_uint(lm);
+  const unsigned key = (lb & 0x80000000u) ? ~lb : (lb | 0x80000000u);      // monotone float -> uint
+  const unsigned wk = __reduce_max_sync(BDP_FULL_MASK, key);
+  const float m = __uint_as_float((wk & 0x80000000u) ? (wk & 0x7fffffffu) : ~wk);
   int mi = 0x7fffffff;
+  if (lm == m) {                                   // float compare: -0.0 and +0.0 tie, as in torch.max
+#pragma unroll
+    for (int j = KV - 1; j >= 0; --j) {
+      const int base = (lane + j * 32) * 4;
+      if (v[j].w == m) mi = base + 3;
+      if (v[j].z == m) mi = base + 2;
+      if (v[j].y == m) mi = base + 1;
+      if (v[j].x == m) mi = base;
+    }
+  }
+  mi = __reduce_min_sync(BDP_FULL_MASK, mi);
+  // the target logit sits in exactly one lane's registers (predicated selects: indexing v[] with a
+  // runtime index would push it to local memory)
+  float xt = 0.f;
 #pragma unroll
   for (int j = 0; j < KV; ++j) {
     const int base = (lane + j * 32) * 4;
-    const float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (e[q] > m) { m = e[q]; mi = base + q; }   // ascending index order inside a lane
+    xt = (tgt == base) ? v[j].x : xt;
+    xt = (tgt == base + 1) ? v[j].y : xt;
+    xt = (tgt == base + 2) ? v[j].z : xt;
+    xt = (tgt == base + 3) ? v[j].w : xt;
   }
-  warp_argmax(m, mi);
-  const int tgt = (int)__ldg(P.bin_true + row);
-  // the target logit sits in exactly one lane's registers: float4 number tgt/4 = lane + 32*j
-  float xt = 0.f;
-  {
-    const int tv = tgt >> 2;
-    if ((tv & 31) == lane) {
-#pragma unroll
-      for (int j = 0; j < KV; ++j) {
-        if ((tv >> 5) == j) {
-          const int q = tgt & 3;
-          xt = q == 0 ? v[j].x : q == 1 ? v[j].y : q == 2 ? v[j].z : v[j].w;
-        }
-      }
-    }
-  }
+  xt = __shfl_sync(BDP_FULL_MASK, xt, (tgt >> 2) & 31);
   // ex2.approx on (x - m) * log2(e): 3 instructions instead of ~10, relative error ~2^-22, far
   // inside the 1e-5 bar (the sum s and every probability carry it once)
   float s = 0.f;
@@ -301,7 +311,6 @@ __device__ __forceinline__ void row_softmax_ce(const LossParams& P, int64_t row,
     v[j] = make_float4(e[0], e[1], e[2], e[3]);
   }
   s = warp_sum(s);
-  xt = warp_sum(xt);
   ce = (m - xt) + logf(s);
   amax = mi;
   if (P.grad_logits) {
@@ -352,7 +361,7 @@ __device__ __forceinline__ void row_softmax_ce_scalar(const LossParams& P, int64
 }
 
 template <int KV>   // KV == 0: scalar path
-__global__ void __launch_bounds__(256) bd_loss_kernel(const LossParams P) {
+__global__ void __launch_bounds__(128) bd_loss_kernel(const LossParams P) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int R = P.rows_per_warp;
@@ -372,25 +381,40 @@ __global__ void __launch_bounds__(256) bd_loss_kernel(const LossParams P) {
     int my_ind = 0;
     if (has_ce) {
       if (KV > 0) {
-        // two rows in flight per warp: both rows' loads are issued before either is reduced
+        // Software pipeline over row pairs: the loads of the NEXT pair are issued before the current
+        // pair is reduced, so a warp keeps up to four rows (3.2 KB at K=200) in flight — the kernel
+        // is bound by bytes in flight per SM, not by issue slots or DRAM bandwidth.
+        constexpr int KVV = KV > 0 ? KV : 1;
         int r = 0;
+        float4 va[KVV], vb[KVV], na[KVV], nb[KVV];
+        int ta = 0, tb = 0, tna = 0, tnb = 0;
+        if (nrows >= 2) {
+          row_load<KVV>(P, row0, lane, nvec, va, ta);
+          row_load<KVV>(P, row0 + 1, lane, nvec, vb, tb);
+        }
         for (; r + 1 < nrows; r += 2) {
-          float4 va[KV > 0 ? KV : 1], vb[KV > 0 ? KV : 1];
-          row_load<(KV > 0 ? KV : 1)>(P, row0 + r, lane, nvec, va);
-          row_load<(KV > 0 ? KV : 1)>(P, row0 + r + 1, lane, nvec, vb);
+          const bool more = r + 3 < nrows;
+          if (more) {
+            row_load<KVV>(P, row0 + r + 2, lane, nvec, na, tna);
+            row_load<KVV>(P, row0 + r + 3, lane, nvec, nb, tnb);
+          }
           float ce_a, ce_b;
           int ia, ib;
-          row_softmax_ce<(KV > 0 ? KV : 1)>(P, row0 + r, lane, nvec, va, ce_a, ia);
-          row_softmax_ce<(KV > 0 ? KV : 1)>(P, row0 + r + 1, lane, nvec, vb, ce_b, ib);
+          row_softmax_ce<KVV>(P, row0 + r, lane, nvec, va, ta, ce_a, ia);
+          row_softmax_ce<KVV>(P, row0 + r + 1, lane, nvec, vb, tb, ce_b, ib);
           if (lane == r) { my_ce = ce_a; my_ind = ia; }
           if (lane == r + 1) { my_ce = ce_b; my_ind = ib; }
+          if (more) {
+#pragma unroll
+            for (int j = 0; j < KVV; ++j) { va[j] = na[j]; vb[j] = nb[j]; }
+            ta = tna; tb = tnb;
+          }
         }
         if (r < nrows) {
-          float4 va[KV > 0 ? KV : 1];
-          row_load<(KV > 0 ? KV : 1)>(P, row0 + r, lane, nvec, va);
+          row_load<KVV>(P, row0 + r, lane, nvec, va, ta);
           float ce_a;
           int ia;
-          row_softmax_ce<(KV > 0 ? KV : 1)>(P, row0 + r, lane, nvec, va, ce_a, ia);
+          row_softmax_ce<KVV>(P, row0 + r, lane, nvec, va, ta, ce_a, ia);
           if (lane == r) { my_ce = ce_a; my_ind = ia; }
         }
       } else {
@@ -449,8 +473,8 @@ __global__ void __launch_bounds__(256) bd_loss_kernel(const LossParams P) {
   }
 }
 
-constexpr int kLossThreads = 256;
-constexpr int kLossMaxBlocks = 148 * 8;
+constexpr int kLossThreads = 128;
+constexpr int kLossMaxBlocks = 148 * 16;
 
 }  // namespace
 
