@@ -158,17 +158,33 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
             dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=group)
         return t
 
-    # global mean / variance of X (sklearn: X -= X.mean(0); tol = mean(var(X)) * tol)
-    n_tot = allreduce(torch.tensor([float(N)], dtype=torch.float64, device=dev))
-    mean = allreduce(x.sum(0)) / n_tot
-    var = allreduce(((x - mean) ** 2).sum(0)) / n_tot
+    # global mean / variance of X (sklearn: X -= X.mean(0); tol = mean(var(X)) * tol), summed in
+    # fixed point: integer sums do not depend on how the rows are split over ranks, so the centred
+    # data — and with them every label and centre — are bit-identical for any world size
+    MAXOP = dist.ReduceOp.MAX if distributed else None
+    n_tot = allreduce(torch.tensor([N], dtype=torch.int64, device=dev)).double()
+    amax = float(allreduce(x.abs().max().reshape(1) if N else x.new_zeros(1), op=MAXOP))
+    hb0 = _fix_hi_bits(amax)
+    xs = x * float(2.0 ** hb0)
+    fl = torch.floor(xs)
+    limbs = torch.stack([fl.to(torch.int64).sum(0),
+                         torch.trunc((xs - fl) * 4294967296.0).to(torch.int64).sum(0)])
+    del xs, fl
+    allreduce(limbs)
+    mean = (limbs[0].double() * float(2.0 ** -hb0) + limbs[1].double() * float(2.0 ** -(hb0 + 32))) / n_tot
+    d2 = (x - mean) ** 2
+    d2max = float(allreduce(d2.max().reshape(1) if N else x.new_zeros(1), op=MAXOP))
+    sh = 40 if d2max <= 0 else int(max(0, min(40, np.floor(61 - np.log2(d2max * float(n_tot) + 1.0)))))
+    q = allreduce(torch.round(d2 * float(2.0 ** sh)).to(torch.int64).sum(0))
+    del d2
+    var = q.double() * float(2.0 ** -sh) / n_tot
     tol_abs = float(var.mean()) * tol
     if center:
         x = x - mean
         centers = (init.double().to(dev) - mean).contiguous()
     else:
         centers = init.double().to(dev).contiguous().clone()
-    max_abs = allreduce(x.abs().max().reshape(1), op=dist.ReduceOp.MAX if distributed else None)
+    max_abs = allreduce(x.abs().max().reshape(1), op=MAXOP)
     hb = _fix_hi_bits(float(max_abs))
 
     state = LloydState(N, K, d, dev)

@@ -361,7 +361,7 @@ __device__ __forceinline__ void row_softmax_ce_scalar(const LossParams& P, int64
 }
 
 template <int KV>   // KV == 0: scalar path
-__global__ void __launch_bounds__(128) bd_loss_kernel(const LossParams P) {
+__global__ void __launch_bounds__(128, 5) bd_loss_kernel(const LossParams P) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int R = P.rows_per_warp;
