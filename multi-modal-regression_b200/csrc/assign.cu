@@ -688,17 +688,43 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
   int changed = 0, tiles_since_flush = 0;
   double inertia = 0.0;
 
+  // Software pipeline over tiles: the rotations (and, for Lloyd, the previous labels) of the NEXT
+  // tile are requested before the current tile is processed, so their DRAM latency overlaps the
+  // record gather, the candidate screen and the stores of the current one (the kernel was bound by
+  // exposed load latency: x -> cell -> record -> old label were four serial round trips per tile).
+  T nx[kGPts * D];
+  int nlab[kGPts];
+  auto prefetch = [&](int64_t tile) {
+    const int64_t wb = tile * kGTile + (int64_t)warp * (32 * kGPts);
+    const int64_t rem = P.N - wb;
+    const int nv = rem <= 0 ? 0 : (rem < 32 * kGPts ? (int)rem : 32 * kGPts);
+#pragma unroll
+    for (int j = 0; j < kGPts * D; ++j) {
+      const int idx = j * 32 + lane;
+      nx[j] = idx < nv * D ? __ldcs(x + wb * D + idx) : (T)0;   // touched once: keep L1 for the keys
+    }
+    if (LLOYD) {
+#pragma unroll
+      for (int p = 0; p < kGPts; ++p) {
+        const int li = p * 32 + lane;
+        nlab[p] = li < nv ? __ldcs(P.labels32 + wb + li) : 0;
+      }
+    }
+  };
+  if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
+
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t wbase = tile * kGTile + (int64_t)warp * (32 * kGPts);
     const int64_t nrem = P.N - wbase;
     const int nval = nrem <= 0 ? 0 : (nrem < 32 * kGPts ? (int)nrem : 32 * kGPts);
-    // coalesced load of this warp's points
+    // this warp's points: prefetched registers -> shared stage (whole 128-byte lines came in)
+    int olab[kGPts];
 #pragma unroll
-    for (int j = 0; j < kGPts * D; ++j) {
-      const int idx = j * 32 + lane;
-      if (idx < nval * D) stage[idx] = __ldcs(x + wbase * D + idx);   // touched once: keep L1 for the keys
-    }
+    for (int j = 0; j < kGPts * D; ++j) stage[j * 32 + lane] = nx[j];
+#pragma unroll
+    for (int p = 0; p < kGPts; ++p) olab[p] = nlab[p];
     __syncwarp();
+    if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
     double xd[kGPts][D];
     const uint4* recp[kGPts];
     uint4 first[kGPts];
@@ -833,7 +859,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
         }
       }
       if (LLOYD) {
-        changed += (__ldcs(P.labels32 + i) != label[p]);
+        changed += (olab[p] != label[p]);
         __stcs(P.labels32 + i, label[p]);
         inertia += sq;
         if (P.update) {
