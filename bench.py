@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--brute", action="store_true", help="also time the brute-force N*K scan")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -325,15 +326,17 @@ def main():
     torch.cuda.synchronize()
     kernel_s = e0.elapsed_time(e1) / args.steps * 1e-3
     achieved = N_ROT * BYTES_PER_ROT / kernel_s / 1e9
-    # the brute-force scan (the former product path) for reference
-    ops.assign_nearest(x, centers, grid=None)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(3):
+    brute_ms = None
+    if args.brute:
+        # the brute-force N*K scan (same labels; the reference's algorithm) for comparison
         ops.assign_nearest(x, centers, grid=None)
-    e1.record()
-    torch.cuda.synchronize()
-    brute_ms = e0.elapsed_time(e1) / 3
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            ops.assign_nearest(x, centers, grid=None)
+        e1.record()
+        torch.cuda.synchronize()
+        brute_ms = e0.elapsed_time(e1) / 3
 
     # ---- e2e: public API from pinned host buffers, results read back to pinned host buffers -----
     y_host = x.cpu().pin_memory()
@@ -392,9 +395,9 @@ def main():
                          "kernel": "assign_grid_kernel<float,3,false>", "kernel_ms": kernel_s * 1e3,
                          "algorithmic_bytes_per_launch": N_ROT * BYTES_PER_ROT,
                          "note": "32 B/rotation x 10M rotations per launch; traffic = dram read+write of "
-                                 "one launch from profiles/r1_ncu_keygrid.md; the step also runs the 3 "
-                                 "key-grid build launches (~65 us); brute-force scan of the same step: "
-                                 "%.2f ms" % brute_ms},
+                                 "one launch from profiles/r1b_ncu_assign.csv; the step also runs the 3 "
+                                 "key-grid build launches (~65 us)" +
+                                 ("; brute-force scan of the same step: %.2f ms" % brute_ms if brute_ms else "")},
             "cpu_baseline": cpu,
             "extras": ex,
         }
