@@ -377,10 +377,11 @@ int keygrid_G(int K, int d) {
   return 4 * gc;
 }
 
+// Grid geometry from the bounding box of the dictionary; every thread of the (256-thread) block
+// takes part, thread 0 writes *hdr.
 template <int D>
-__global__ void __launch_bounds__(256) keygrid_header_kernel(const double* __restrict__ centers,
-                                                             int K, int G, double margin_frac,
-                                                             GridHdr* __restrict__ hdr) {
+__device__ __forceinline__ void compute_header(const double* __restrict__ centers, int K, int G,
+                                               double margin_frac, GridHdr* hdr) {
   __shared__ double s_lo[8][D], s_hi[8][D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double lo[D], hi[D];
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(256) keygrid_header_kernel(const double* __res
     hdr->G = G;
     hdr->enabled = ok ? 1 : 0;
   }
+  __syncthreads();
 }
 
 // squared distance bounds between key c and the box [lo, hi]
@@ -510,19 +512,106 @@ __device__ __forceinline__ void filter_box(const double* __restrict__ centers, i
   if (lane == 0) rec[0] = (unsigned short)(cnt > cap ? kGridOverflow : (unsigned)cnt);
 }
 
-// Coarse cells (4 fine cells per side): one warp filters the whole dictionary against one cell.
+// A block of 8 warps filters the WHOLE dictionary against one box; the warps take contiguous key
+// ranges so the compacted list stays in ascending key order.  rec has room for K ids.
+template <int D>
+__device__ __forceinline__ void filter_box_block(const double* __restrict__ centers, int K,
+                                                 const double lo[D], const double hi[D],
+                                                 unsigned short* __restrict__ rec) {
+  __shared__ double s_u[8];
+  __shared__ int s_p[8], s_c[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (((K + 7) / 8) + 31) & ~31;
+  const int b0 = min(K, warp * per), b1 = min(K, b0 + per);
+  double u = INFINITY;
+  int piv = 0x7fffffff;
+  for (int k = b0 + lane; k < b1; k += 32) {
+    double mn, mx;
+    box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
+    if (mx < u) { u = mx; piv = k; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ou = __shfl_xor_sync(BDP_FULL_MASK, u, o);
+    const int op = __shfl_xor_sync(BDP_FULL_MASK, piv, o);
+    if (ou < u || (ou == u && op < piv)) { u = ou; piv = op; }
+  }
+  if (lane == 0) { s_u[warp] = u; s_p[warp] = piv; }
+  __syncthreads();
+  u = s_u[0]; piv = s_p[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w)
+    if (s_u[w] < u || (s_u[w] == u && s_p[w] < piv)) { u = s_u[w]; piv = s_p[w]; }
+  if (piv == 0x7fffffff) piv = 0;
+  const double thr = u * (1.0 + 1e-9) + 1e-300;
+  double cp[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) cp[k] = __ldg(centers + (int64_t)piv * D + k);
+  auto keeps = [&](int k) {
+    double mn, mx, sc;
+    box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
+    const double bm = bisector_min<D>(centers + (int64_t)k * D, cp, lo, hi, sc);
+    return mn <= thr && bm <= 1e-9 * sc;
+  };
+  int cnt = 0;
+  for (int k0 = b0; k0 < b1; k0 += 32) {
+    const int k = k0 + lane;
+    cnt += __popc(__ballot_sync(BDP_FULL_MASK, k < b1 && keeps(k)));
+  }
+  if (lane == 0) s_c[warp] = cnt;
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { off += w < warp ? s_c[w] : 0; total += s_c[w]; }
+  for (int k0 = b0; k0 < b1; k0 += 32) {
+    const int k = k0 + lane;
+    const bool keep = k < b1 && keeps(k);
+    const unsigned m = __ballot_sync(BDP_FULL_MASK, keep);
+    if (keep) rec[1 + off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+    off += __popc(m);
+  }
+  if (threadIdx.x == 0) rec[0] = (unsigned short)total;
+  __syncthreads();
+}
+
+// Super cells (4 coarse = 16 fine cells per side): one block per cell over the whole dictionary.
+// Every block derives the grid geometry itself (K*D loads); block 0 publishes it.
+template <int D>
+__global__ void __launch_bounds__(256) keygrid_super_kernel(const double* __restrict__ centers, int K,
+                                                            int G, double margin_frac,
+                                                            GridHdr* __restrict__ hdr,
+                                                            unsigned short* __restrict__ super) {
+  __shared__ GridHdr s_hdr;
+  compute_header<D>(centers, K, G, margin_frac, &s_hdr);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *hdr = s_hdr;
+  const int Gs = (G / 4 + 3) / 4;
+  double lo[D], hi[D];
+  int r = blockIdx.x;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const int ck = r % Gs;
+    r /= Gs;
+    const double eps = kBoxEps * s_hdr.cell[k];
+    lo[k] = s_hdr.origin[k] + (double)(16 * ck) * s_hdr.cell[k] - eps;
+    hi[k] = s_hdr.origin[k] + (double)min(16 * ck + 16, G) * s_hdr.cell[k] + eps;
+  }
+  filter_box_block<D>(centers, K, lo, hi, super + (int64_t)blockIdx.x * (K + 1));
+}
+
+// Coarse cells (4 fine cells per side): one warp filters its super cell's list against one cell.
 template <int D>
 __global__ void __launch_bounds__(256) keygrid_coarse_kernel(const double* __restrict__ centers,
                                                              int K, const GridHdr* __restrict__ hdr,
+                                                             const unsigned short* __restrict__ super,
                                                              unsigned short* __restrict__ coarse) {
   const int lane = threadIdx.x & 31;
-  const int Gc = hdr->G / 4;
+  const int Gc = hdr->G / 4, Gs = (Gc + 3) / 4;
   const int64_t n_cells = ipow64(Gc, D);
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t cell = warp0; cell < n_cells; cell += n_warps) {
     double lo[D], hi[D];
-    int64_t r = cell;
+    int64_t r = cell, parent = 0, pm = 1;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       const int ck = (int)(r % Gc);
@@ -530,8 +619,12 @@ __global__ void __launch_bounds__(256) keygrid_coarse_kernel(const double* __res
       const double eps = kBoxEps * hdr->cell[k];
       lo[k] = hdr->origin[k] + (double)(4 * ck) * hdr->cell[k] - eps;
       hi[k] = hdr->origin[k] + (double)(4 * ck + 4) * hdr->cell[k] + eps;
+      parent += (int64_t)(ck / 4) * pm;
+      pm *= Gs;
     }
-    filter_box<D>(centers, K, nullptr, K, lo, hi, coarse + cell * (kCoarseCap + 1), kCoarseCap, lane);
+    const unsigned short* prec = super + parent * (K + 1);
+    filter_box<D>(centers, K, prec + 1, (int)prec[0], lo, hi, coarse + cell * (kCoarseCap + 1),
+                  kCoarseCap, lane);
   }
 }
 
@@ -971,14 +1064,19 @@ int keygrid_check(const void* grid, int64_t grid_bytes, int K, int d, const char
   return BDP_OK;
 }
 
+// layout: [GridHdr][fine records][coarse records][super records]
+int64_t keygrid_super_cells(int G, int d) { return ipow64((G / 4 + 3) / 4, d); }
+
 void keygrid_pointers(const void* grid, int K, int d, const GridHdr** hdr,
-                      const unsigned short** coarse, const unsigned short** fine) {
+                      const unsigned short** coarse, const unsigned short** fine,
+                      const unsigned short** super = nullptr) {
   const unsigned char* b = reinterpret_cast<const unsigned char*>(grid);
   const int G = keygrid_G(K, d);
-  const int64_t n_coarse = ipow64(G / 4, d);
+  const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
   *hdr = reinterpret_cast<const GridHdr*>(b);
-  *coarse = reinterpret_cast<const unsigned short*>(b + sizeof(GridHdr));
-  *fine = *coarse + n_coarse * (kCoarseCap + 1);
+  *fine = reinterpret_cast<const unsigned short*>(b + sizeof(GridHdr));
+  *coarse = *fine + n_fine * (kGridCap + 1);
+  if (super) *super = *coarse + n_coarse * (kCoarseCap + 1);
 }
 
 // ---- argmax |<key, q>| -----------------------------------------------------------------------
@@ -1336,7 +1434,8 @@ extern "C" int64_t bdp_keygrid_bytes(int K, int d) {
   if ((d != 3 && d != 4) || K < 1 || K > kGridMaxK) return -1;
   const int G = keygrid_G(K, d);
   const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
-  return (int64_t)sizeof(GridHdr) + n_coarse * (kCoarseCap + 1) * 2 + n_fine * (kGridCap + 1) * 2;
+  return (int64_t)sizeof(GridHdr) + n_coarse * (kCoarseCap + 1) * 2 + n_fine * (kGridCap + 1) * 2 +
+         keygrid_super_cells(G, d) * (K + 1) * 2;
 }
 
 extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
@@ -1346,15 +1445,17 @@ extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid
   int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_build");
   if (rc != BDP_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const GridHdr* hdr; const unsigned short *coarse, *fine;
-  keygrid_pointers(grid, K, d, &hdr, &coarse, &fine);
+  const GridHdr* hdr; const unsigned short *coarse, *fine, *super;
+  keygrid_pointers(grid, K, d, &hdr, &coarse, &fine, &super);
   GridHdr* h = const_cast<GridHdr*>(hdr);
   unsigned short* co = const_cast<unsigned short*>(coarse);
   unsigned short* fi = const_cast<unsigned short*>(fine);
+  unsigned short* su = const_cast<unsigned short*>(super);
   const int G = keygrid_G(K, d);
   const double r = pow((double)K, 1.0 / d);
   const double margin_frac = r > 2.0 ? 1.0 / r : 0.5;
   const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
+  const unsigned n_super = (unsigned)keygrid_super_cells(G, d);
   const int sms = bdp_num_sms();
   auto blocks_for = [&](int64_t cells) {
     int64_t b = ceil_div64(cells, 8);                  // 8 warps per block, one cell per warp
@@ -1363,12 +1464,12 @@ extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid
   };
   const unsigned fine_blocks = (unsigned)ceil_div64(n_fine, 256);
   if (d == 3) {
-    keygrid_header_kernel<3><<<1, 256, 0, st>>>(centers, K, G, margin_frac, h);
-    keygrid_coarse_kernel<3><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, co);
+    keygrid_super_kernel<3><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, h, su);
+    keygrid_coarse_kernel<3><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, su, co);
     keygrid_fine_kernel<3><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi);
   } else {
-    keygrid_header_kernel<4><<<1, 256, 0, st>>>(centers, K, G, margin_frac, h);
-    keygrid_coarse_kernel<4><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, co);
+    keygrid_super_kernel<4><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, h, su);
+    keygrid_coarse_kernel<4><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, su, co);
     keygrid_fine_kernel<4><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi);
   }
   BDP_CUDA_CHECK_LAUNCH("keygrid kernels");

@@ -37,6 +37,6 @@ for K in (1000, 200, 16):
     buf = g.buf.cpu().numpy()
     G = int(np.frombuffer(buf[96:100].tobytes(), dtype=np.int32)[0])
     ncoarse = (G // 4) ** 3
-    fine = np.frombuffer(buf[160 + ncoarse * 512:160 + ncoarse * 512 + G ** 3 * 64].tobytes(), dtype=np.uint16).reshape(-1, 32)
+    fine = np.frombuffer(buf[160:160 + G ** 3 * 64].tobytes(), dtype=np.uint16).reshape(-1, 32)
     cnt = fine[:, 0].astype(np.int64)
     print("  G=%d cells=%d mean cand %.2f max %d overflow cells %d  hist %s" % (G, G ** 3, cnt[cnt < 65535].mean(), cnt[cnt < 65535].max(), int((cnt == 65535).sum()), np.bincount(cnt[cnt < 65535])[:12].tolist()))
