@@ -203,6 +203,18 @@ int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, const double* 
                                void* stream);
 
 /*
+ * One whole Lloyd iteration in one call: acc_stats [K*(2d+1) + 2] (accumulators followed by the
+ * {changed, unused} counters — the layout that is all-reduced across ranks) is zeroed, the key grid
+ * is rebuilt for `centers` (grid == NULL: brute-force scan), the E+M step runs, and when centers_new
+ * is given the M-step is finalised (single rank; with several ranks pass NULL, all-reduce acc_stats,
+ * then call bdp_kmeans_finalize).
+ */
+int bdp_kmeans_iteration(const double* x, int64_t N, int d, const double* centers, int K, void* grid,
+                         int64_t grid_bytes, int32_t* labels, int64_t* acc_stats, int fix_hi_bits,
+                         double* inertia, int update, double* centers_new, double* shift2,
+                         int64_t* n_empty, void* stream);
+
+/*
  * M-step finalisation on the device (no host round trip): centers_new = sum / count from the
  * fixed-point accumulators (exactly rounded sum, then one division), empty clusters take the
  * centre of the heaviest cluster (sklearn _average_centers), shift2[0] = sum ||new - old||^2,

@@ -44,6 +44,8 @@ SIGNATURES = {
     "bdp_assign_nearest_grid": (_int, [_p, _int, _i64, _int, _p, _int, _p, _i64, _p, _p, _p, _p, _p]),
     "bdp_kmeans_lloyd_step_grid": (_int, [_p, _i64, _int, _p, _int, _p, _i64, _p, _p, _int, _p, _p,
                                           _int, _p]),
+    "bdp_kmeans_iteration": (_int, [_p, _i64, _int, _p, _int, _p, _i64, _p, _p, _int, _p, _int, _p, _p,
+                                    _p, _p]),
     "bdp_kmeans_finalize": (_int, [_p, _int, _int, _int, _p, _p, _p, _p, _p]),
     "bdp_gemm_tf32": (_int, [_p, _int, _i64, _i64, _p, _int, _i64, _i64, _p, _int, _i64, _i64, _i64,
                              _i64, _i64, _int, _int, _i64, _int, _p]),

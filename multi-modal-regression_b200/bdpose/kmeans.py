@@ -63,6 +63,21 @@ def lloyd_step(x, centers, state, fix_hi_bits, update=True, grid=None, want_iner
     L.check(st, "bdp_kmeans_lloyd_step")
 
 
+def lloyd_iteration(x, centers, centers_new, state, fix_hi_bits, grid=None, do_finalize=True):
+    """zero accumulators + key-grid rebuild + E/M step (+ finalisation) in ONE library call."""
+    N, d = x.shape
+    K = centers.shape[0]
+    lib = L.lib()
+    with torch.cuda.device(x.device):
+        st = lib.bdp_kmeans_iteration(
+            x.data_ptr(), N, d, centers.data_ptr(), K,
+            None if grid is None else grid.buf.data_ptr(), 0 if grid is None else grid.nbytes,
+            state.labels.data_ptr(), state.acc_stats.data_ptr(), fix_hi_bits, None, 1,
+            centers_new.data_ptr() if do_finalize else None, state.shift2.data_ptr(),
+            state.n_empty.data_ptr(), L.stream_ptr())
+    L.check(st, "bdp_kmeans_iteration")
+
+
 def finalize(state, centers_old, centers_new, fix_hi_bits):
     K, d = centers_old.shape
     with torch.cuda.device(centers_old.device):
@@ -196,10 +211,16 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     n_iter = 0
     iters = fixed_iters if fixed_iters is not None else max_iter
     for it in range(iters):
-        state.acc_stats.zero_()
-        step_fn(x, centers, state, hb, update=True, grid=grid)
-        allreduce(state.acc_stats)
-        finalize_fn(state, centers, centers_new, hb)
+        if _backend is None:
+            lloyd_iteration(x, centers, centers_new, state, hb, grid=grid, do_finalize=not distributed)
+            if distributed:
+                allreduce(state.acc_stats)
+                finalize_fn(state, centers, centers_new, hb)
+        else:
+            state.acc_stats.zero_()
+            step_fn(x, centers, state, hb, update=True, grid=grid)
+            allreduce(state.acc_stats)
+            finalize_fn(state, centers, centers_new, hb)
         if fixed_iters is None:
             # one small D2H read per iteration: {changed, n_empty} and the centre shift
             host = torch.cat([state.stats[:1].double(), state.n_empty.double(), state.shift2]).tolist()

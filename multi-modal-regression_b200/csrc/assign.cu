@@ -1519,3 +1519,34 @@ extern "C" int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, con
   keygrid_pointers(grid, K, d, &P.ghdr, &coarse, &P.gfine);
   return dispatch_assign_grid<true>(P, BDP_F64, d, reinterpret_cast<cudaStream_t>(stream));
 }
+
+// One Lloyd iteration as a single launch sequence: zero the accumulators, rebuild the key grid for
+// the current centres, E+M step, and (single rank) the M-step finalisation.  With several ranks the
+// caller all-reduces acc_stats between this call (centers_new == NULL) and bdp_kmeans_finalize.
+extern "C" int bdp_kmeans_iteration(const double* x, int64_t N, int d, const double* centers, int K,
+                                    void* grid, int64_t grid_bytes, int32_t* labels,
+                                    int64_t* acc_stats, int fix_hi_bits, double* inertia, int update,
+                                    double* centers_new, double* shift2, int64_t* n_empty,
+                                    void* stream) {
+  BDP_REQUIRE(acc_stats != nullptr, "kmeans_iteration: acc_stats is NULL");
+  BDP_REQUIRE(d == 3 || d == 4, "kmeans_iteration: d must be 3 or 4 (got %d)", d);
+  BDP_REQUIRE(K >= 1, "kmeans_iteration: K must be >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n_acc = (size_t)K * (2 * d + 1);
+  BDP_CUDA_CALL(cudaMemsetAsync(acc_stats, 0, (n_acc + 2) * sizeof(int64_t), st));
+  int rc;
+  if (grid) {
+    rc = bdp_keygrid_build(centers, K, d, grid, grid_bytes, stream);
+    if (rc != BDP_OK) return rc;
+    rc = bdp_kmeans_lloyd_step_grid(x, N, d, centers, K, grid, grid_bytes, labels, acc_stats,
+                                    fix_hi_bits, acc_stats + n_acc, inertia, update, stream);
+  } else {
+    rc = bdp_kmeans_lloyd_step(x, N, d, centers, K, labels, acc_stats, fix_hi_bits,
+                               acc_stats + n_acc, inertia, update, stream);
+  }
+  if (rc != BDP_OK) return rc;
+  if (centers_new)
+    return bdp_kmeans_finalize(acc_stats, K, d, fix_hi_bits, centers, centers_new, shift2, n_empty,
+                               stream);
+  return BDP_OK;
+}
