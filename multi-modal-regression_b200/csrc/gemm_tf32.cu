@@ -473,9 +473,37 @@ EncodeTiledFn encode_fn() {
 
 // rank-3 fp32 map over [dim2][dim1][dim0] (dim0 contiguous), 128-byte swizzle (16 B atoms for
 // K-major tiles, 32 B atoms for MN-major tiles), zero OOB fill
+// Encoded maps are cached: a training step issues the same 8 GEMMs every iteration (same pointers
+// when the caching allocator hands the same blocks back, always the same weights), and one
+// cuTensorMapEncodeTiled costs ~2 us of host time on a step that is host-bound.
+struct MapKey {
+  const float* ptr;
+  uint64_t dim0, dim1, dim2, s1, s2;
+  uint32_t box0, box1, mn;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && dim0 == o.dim0 && dim1 == o.dim1 && dim2 == o.dim2 && s1 == o.s1 &&
+           s2 == o.s2 && box0 == o.box0 && box1 == o.box1 && mn == o.mn;
+  }
+};
+constexpr int kMapCache = 64;
+thread_local MapKey t_keys[kMapCache];
+thread_local CUtensorMap t_maps[kMapCache];
+thread_local bool t_valid[kMapCache];
+
 int make_map(CUtensorMap* map, const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,
              uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1,
              bool mn_major) {
+  const MapKey key = {ptr, dim0, dim1, dim2, stride1_elems, stride2_elems, box0, box1,
+                      mn_major ? 1u : 0u};
+  uint64_t h = reinterpret_cast<uint64_t>(ptr) >> 4;
+  h = (h ^ (dim0 * 0x9E3779B97F4A7C15ull) ^ (dim1 * 0xC2B2AE3D27D4EB4Full) ^ (dim2 << 7) ^
+       (stride1_elems << 17) ^ (stride2_elems << 29) ^ ((uint64_t)box1 << 41) ^ key.mn) *
+      0xD6E8FEB86659FD93ull;
+  const int slot = (int)((h >> 32) % kMapCache);
+  if (t_valid[slot] && t_keys[slot] == key) {
+    *map = t_maps[slot];
+    return BDP_OK;
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) { bdp_set_error("gemm_tf32: cuTensorMapEncodeTiled entry point unavailable"); return BDP_ERR_CUDA; }
   cuuint64_t dims[3] = {dim0, dim1, dim2};
@@ -493,6 +521,9 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t dim0, uint64_t dim1, u
                   (unsigned long long)strides[1], box0, box1);
     return BDP_ERR_CUDA;
   }
+  t_keys[slot] = key;
+  t_maps[slot] = *map;
+  t_valid[slot] = true;
   return BDP_OK;
 }
 
@@ -553,7 +584,10 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   P.b_g = (b_gstride != 0 || G == 1) ? 1 : 0;
   P.C = C; P.ldc = ldc; P.c_gstride = c_gstride; P.c_sstride = c_sstride; P.c_nm = c_layout;
   P.precise = precise ? 1 : 0;
-  { const char* e = getenv("BDP_GEMM_NO_ROTATE"); P.k_rotate = (e && e[0] == '1') ? 0 : 1; }
+  {
+    static const int no_rotate = [] { const char* e = getenv("BDP_GEMM_NO_ROTATE"); return (e && e[0] == '1') ? 1 : 0; }();
+    P.k_rotate = no_rotate ? 0 : 1;
+  }
   // small-M problems (M = batch) fetch only the rows that exist
   if (P.m_tiles == 1) P.a_rows = a_major ? (int)((M + 31) / 32 * 32) : (int)((M + 7) / 8 * 8);
   else P.a_rows = kBM;
