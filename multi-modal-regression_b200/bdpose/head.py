@@ -569,8 +569,8 @@ def bench(dev, peaks):
         for mode in ("fp32", "tf32"):
             set_precision(mode)
             try:
-                ms_f = _time(fwd, 20, 5)
-                ms = _time(step, 20, 5)
+                ms_f = _time(fwd, 30, 15)
+                ms = _time(step, 40, 20)
             finally:
                 set_precision("fp32")
             wbytes = n_params * 4
@@ -580,6 +580,28 @@ def bench(dev, peaks):
                 "fwd_hbm_frac": wbytes / (ms_f * 1e-3) / 1e9 / hbm,
                 "fwd_bwd_hbm_frac": 3 * wbytes / (ms * 1e-3) / 1e9 / hbm,
                 "weight_bytes": wbytes}
+    # opt-in fast path: 10 stacked Parameters instead of 336 per-module ones
+    sp = m.stacked_head_parameters()
+    for B in (32, 96):
+        x = torch.randn(B, 2048, device=dev, requires_grad=True)
+        lab = torch.randint(0, C, (B, 1), device=dev)
+        bins = torch.randint(0, K, (B,), device=dev)
+        tgt = torch.randn(B, 3, device=dev)
+
+        def sstep():
+            for p in sp:
+                p.grad = None
+            y1, y2 = m(x, lab)
+            lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
+            (lc + lr).backward()
+        set_precision("tf32")
+        try:
+            ms = _time(sstep, 40, 20)
+        finally:
+            set_precision("fp32")
+        out["pascal_head_B%d_tf32_stacked_params" % B] = {
+            "samples_per_s_fwd_bwd": B / (ms * 1e-3), "ms_fwd_bwd": ms,
+            "fwd_bwd_hbm_frac": 3 * n_params * 4 / (ms * 1e-3) / 1e9 / hbm}
     # raw fc1 GEMM: the dominant kernel of the head (197 MB of weights streamed once)
     H, N1, N0, B = 24, 1000, 2048, 32
     w1 = m._heads().ensure()["w1"]
@@ -621,7 +643,7 @@ def bench(dev, peaks):
     for mode in ("fp32", "tf32"):
         set_precision(mode)
         try:
-            ms = _time(ostep, 20, 5)
+            ms = _time(ostep, 40, 20)
         finally:
             set_precision("fp32")
         out["objectnet_head_B256_%s" % mode] = {"samples_per_s_fwd_bwd": B / (ms * 1e-3), "ms_fwd_bwd": ms}
