@@ -219,6 +219,10 @@ def extras(dev, x, centers, peaks, rank, world):
                                  "ms_per_iteration": per_iter, "fit_ms_22_iterations": long_,
                                  "n_rotations_total": N_ROT, "scaling": "strong",
                                  "hbm_frac": (n_local * 28.0 / (per_iter * 1e-3)) / 1e9 / hbm}
+    # ---- config 4: data-parallel head step (all ranks), gradients all-reduced over NCCL ----------
+    if world > 1:
+        from bdpose import head as _head
+        out.update(_head.bench_dp(dev, world))
     if rank != 0:
         return out
     # ---- config 1b: fused loss fwd+bwd, 1 M rows, K=200 ------------------------------------------
