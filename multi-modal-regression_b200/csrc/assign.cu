@@ -861,31 +861,40 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
       const float tau = P.err_coef * sN * sN;
       float best = INFINITY, second = INFINITY;
       int bidx = 0;
-      // the record is a stream of 16-bit ids after the count; 128 bits (8 entries) are resident
-      unsigned long long w0 = ((unsigned long long)first[p].y << 32) | first[p].x;
-      unsigned long long w1 = ((unsigned long long)first[p].w << 32) | first[p].z;
-      int left = 7;                                     // ids left in the resident 128 bits
-      w0 = (w0 >> 16) | (w1 << 48);
-      w1 >>= 16;
-      for (unsigned e = 1; e <= cnt; ++e) {
-        if (left == 0) {
-          const uint4 ch = __ldg(recp[p] + (e >> 3));
-          w0 = ((unsigned long long)ch.y << 32) | ch.x;
-          w1 = ((unsigned long long)ch.w << 32) | ch.z;
-          left = 8;
-        }
-        const int id = (int)(w0 & 0xFFFFull);
-        w0 = (w0 >> 16) | (w1 << 48);
-        w1 >>= 16;
-        --left;
-        const float4 cr = s_rec[id];
-        const float cn = (D == 4) ? s_cn[id] : 0.f;
+      // Entries 1..7 sit in the 16 bytes already loaded: statically unrolled, two instructions turn
+      // a 16-bit id into the byte offset of its screening record (a generic shift of the 128-bit
+      // register group cost five per candidate).  Longer lists (3 % of the cells) continue from
+      // global memory.
+      unsigned boff = 0;                                 // byte offset (id * 16) of the best record
+      const unsigned fw[4] = {first[p].x, first[p].y, first[p].z, first[p].w};
+      const char* recs = reinterpret_cast<const char*>(s_rec);
+#pragma unroll
+      for (int e = 1; e <= 7; ++e) {
+        if ((unsigned)e > cnt) break;
+        const unsigned w = fw[e >> 1];
+        const unsigned off = (e & 1) ? ((w >> 12) & 0xFFFF0u) : ((w << 4) & 0xFFFF0u);
+        const float4 cr = *reinterpret_cast<const float4*>(recs + off);
+        const float cn = (D == 4) ? s_cn[off >> 4] : 0.f;
         const float d = screen_dist<D>(xf, cr, cn);
         const bool lt = d < best;
         second = fminf(second, lt ? best : d);
-        bidx = lt ? id : bidx;
+        boff = lt ? off : boff;
         best = fminf(best, d);
       }
+      if (cnt > 7u) {
+        const unsigned short* ids = reinterpret_cast<const unsigned short*>(recp[p]);
+        for (unsigned e = 8; e <= cnt; ++e) {
+          const unsigned off = (unsigned)__ldg(ids + e) << 4;
+          const float4 cr = *reinterpret_cast<const float4*>(recs + off);
+          const float cn = (D == 4) ? s_cn[off >> 4] : 0.f;
+          const float d = screen_dist<D>(xf, cr, cn);
+          const bool lt = d < best;
+          second = fminf(second, lt ? best : d);
+          boff = lt ? off : boff;
+          best = fminf(best, d);
+        }
+      }
+      bidx = (int)(boff >> 4);
       if (!(second - best > tau) && cnt > 1u) {
         // near tie: exact fp64 pass over the same candidates (ascending ids: lowest index wins)
         double bd = INFINITY;
