@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
     for (int p = 0; p < kGPts; ++p) olab[p] = nlab[p];
     __syncwarp();
     if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
-    double xd[kGPts][D];
+    T xv[kGPts][D];          // the rotations in their input type; widened where exactness needs it
     const uint4* recp[kGPts];
     uint4 first[kGPts];
     bool in_grid[kGPts], valid[kGPts];
@@ -831,9 +831,8 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
       int64_t cidx = 0, mul = 1;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
-        const T xv = valid[p] ? stage[li * D + k] : (T)0;
-        xd[p][k] = (double)xv;
-        const T t = (xv - g_org[k]) * g_inv[k];
+        xv[p][k] = valid[p] ? stage[li * D + k] : (T)0;
+        const T t = (xv[p][k] - g_org[k]) * g_inv[k];
         ok = ok && (t >= (T)0) && (t < Gt);             // false for NaN as well
         const int ck = ok ? (int)t : 0;                 // t >= 0: truncation == floor
         cidx += (int64_t)ck * mul;
@@ -856,7 +855,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
       float xf[D];
       float n2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < D; ++k) { xf[k] = (float)xd[p][k]; n2 += xf[k] * xf[k]; }
+      for (int k = 0; k < D; ++k) { xf[k] = (float)xv[p][k]; n2 += xf[k] * xf[k]; }
       const float sN = sqrtf(n2) * 1.0000002f + cmax;
       const float tau = P.err_coef * sN * sN;
       float best = INFINITY, second = INFINITY;
@@ -905,7 +904,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
           double sq = 0.0;
 #pragma unroll
           for (int k = 0; k < D; ++k) {
-            const double df = xd[p][k] - __ldg(c + k);
+            const double df = (double)xv[p][k] - __ldg(c + k);
             sq += df * df;
           }
           if (sq < bd) { bd = sq; bidx = id; }
@@ -922,7 +921,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
         m &= m - 1;
         double xe[D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) xe[k] = __shfl_sync(BDP_FULL_MASK, xd[p][k], src);
+        for (int k = 0; k < D; ++k) xe[k] = (double)__shfl_sync(BDP_FULL_MASK, xv[p][k], src);
         double bd = INFINITY;
         int bi = 0x7fffffff;
         for (int j = lane; j < P.K; j += 32) {
@@ -956,7 +955,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
         const double* c = P.centers + (int64_t)label[p] * D;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          diff[k] = xd[p][k] - __ldg(c + k);
+          diff[k] = (double)xv[p][k] - __ldg(c + k);
           sq += diff[k] * diff[k];
         }
       }
@@ -970,7 +969,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
 #pragma unroll
             for (int k = 0; k < D; ++k) {
               long long hi, lo;
-              to_limbs(xd[p][k], P.scale_hi, hi, lo);
+              to_limbs((double)xv[p][k], P.scale_hi, hi, lo);
               const unsigned ub = (unsigned)(hi + 2147483648LL);      // hi in [-2^31, 2^31)
               const unsigned ul = (unsigned)lo;
               atomicAdd(a + 4 * k, ub & 0xFFFFu);
@@ -984,7 +983,7 @@ __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignP
 #pragma unroll
             for (int k = 0; k < D; ++k) {
               long long hi, lo;
-              to_limbs(xd[p][k], P.scale_hi, hi, lo);
+              to_limbs((double)xv[p][k], P.scale_hi, hi, lo);
               atomicAdd(a + 2 * k, (unsigned long long)hi);
               atomicAdd(a + 2 * k + 1, (unsigned long long)lo);
             }
