@@ -43,6 +43,8 @@ constexpr int kGemmThreads = 512;
 constexpr int kSplitThreads = 256;   // warps 8-15
 constexpr int kABytes = kBM * kBK * 4;     // 16 KB per stage
 constexpr int kMaxStages = 10;
+constexpr int kEpiPitch = 36;        // floats per staged row (32 + 4: conflict-free float4 rows)
+constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;   // 4 epilogue warps x 32 rows
 
 struct GemmParams {
   int M, N, K, G;
@@ -60,6 +62,7 @@ struct GemmParams {
   int a_rows;                       // A rows actually fetched per stage (small-M problems)
   int a_bytes;                      // smem reserved for the A tile of one stage (1 KB multiple)
   int acc_stages;                   // TMEM accumulator stages (2 only when a CTA runs >1 tile)
+  int stage_out;                    // 1: epilogue transposes through smem so stores are whole 128-byte row segments
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -189,6 +192,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto split_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxStages + 2 + s); };
+  const uint32_t epi_base = bar_base + 8u * (3 * kMaxStages + 4);      // 16-byte aligned
   __shared__ uint32_t s_tmem_base;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -411,7 +415,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int nb = n0 + c * 32;
         const int wcols = full ? 32 : 16;
-        if (!P.c_nm) {
+        if (P.stage_out) {
+          // Big outputs (wgrad: 197 MB): lane r holds 32 columns of ROW r, so a direct store writes
+          // 32 scattered 16-byte pieces per instruction and every 32-byte sector twice.  Transposed
+          // through shared memory each instruction writes four whole 128-byte row segments.
+          const uint32_t tile = epi_base + static_cast<uint32_t>(q) * (32 * kEpiPitch * 4);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (lane * kEpiPitch + 4 * j) * 4),
+                         "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+          __syncwarp();
+          const int sub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub;
+            const int mr = mt * kBM + q * 32 + rr;
+            uint32_t o0, o1, o2, o3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(tile + (rr * kEpiPitch + c4) * 4));
+            if (mr < P.M && c4 < wcols && nb + c4 < P.N)          // N % 4 == 0 on this path
+              *reinterpret_cast<float4*>(Cg + static_cast<long long>(mr) * P.ldc + nb + c4) =
+                  make_float4(__uint_as_float(o0), __uint_as_float(o1), __uint_as_float(o2), __uint_as_float(o3));
+          }
+          __syncwarp();
+        } else if (!P.c_nm) {
           if (m < P.M) {
             float* dst = Cg + static_cast<long long>(m) * P.ldc + nb;
             const bool vec = (nb + wcols <= P.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
@@ -583,6 +610,8 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   P.a_g = (a_gstride != 0 || G == 1) ? 1 : 0;
   P.b_g = (b_gstride != 0 || G == 1) ? 1 : 0;
   P.C = C; P.ldc = ldc; P.c_gstride = c_gstride; P.c_sstride = c_sstride; P.c_nm = c_layout;
+  P.stage_out = (c_layout == 0 && M >= 64 && N % 4 == 0 && ldc % 4 == 0 && c_gstride % 4 == 0 &&
+                 c_sstride % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
   P.precise = precise ? 1 : 0;
   {
     static const int no_rotate = [] { const char* e = getenv("BDP_GEMM_NO_ROTATE"); return (e && e[0] == '1') ? 1 : 0; }();
@@ -608,7 +637,7 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   // The MMA always reads 128 A rows from shared memory (rows >= a_rows produce discarded D rows), so
   // a shrunk A reservation is followed by `slack` bytes that keep those reads inside the allocation.
   const size_t slack = (size_t)(kABytes - P.a_bytes);
-  const size_t fixed = 1024 + 8 * (3 * kMaxStages + 4) + slack;
+  const size_t fixed = 1024 + 8 * (3 * kMaxStages + 4) + slack + (P.stage_out ? kEpiBytes : 0);
   int stages = (int)((224 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
