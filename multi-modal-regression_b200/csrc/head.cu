@@ -111,81 +111,158 @@ bn_relu_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a,
 }
 
 // ---- fc3 + mixing ---------------------------------------------------------------------------------
-// a2 is [B, ld] batch-major; the activations of head hd are columns [col0 + hd*N2, col0 + (hd+1)*N2)
-constexpr int kFc3OutPerBlock = 32;
+// a2 is [B, ld] batch-major; the activations of head hd are columns [hd*N2, (hd+1)*N2).  These
+// kernels move little data (w3 is 4.8 MB for the Pascal bin heads) and are latency-bound: each one
+// is shaped so that a thread's loads are independent and issued together (one memory round trip per
+// output instead of a serial chain of them).  N2 % 4 == 0 and 16-byte aligned rows (checked by the
+// callers), so rows are read as float4.
+constexpr int kFc3Warps = 8;
 
-__global__ void __launch_bounds__(256)
+// one warp per (sample, output): y[b,o] = sum_h mix[b,h] * (b3[h,o] + w3[h,o,:] . a2[b,h,:])
+__global__ void __launch_bounds__(kFc3Warps * 32)
 fc3_fwd_kernel(const float* __restrict__ a2, int64_t ld, const float* __restrict__ w3,
                const float* __restrict__ b3, const float* __restrict__ mix, int H, int O, int N2,
                float* __restrict__ y) {
-  extern __shared__ float s_col[];                    // [N2] activations of (sample, head)
   const int b = blockIdx.y;
-  const int o0 = blockIdx.x * kFc3OutPerBlock;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc[kFc3OutPerBlock / 8] = {0.f, 0.f, 0.f, 0.f};
+  const int o = blockIdx.x * kFc3Warps + warp;
+  if (o >= O) return;
+  const int nv = N2 >> 2;
+  float acc = 0.f;
   for (int hd = 0; hd < H; ++hd) {
-    const float p = mix[(int64_t)b * H + hd];
-    if (p == 0.f) continue;                           // block-uniform
-    __syncthreads();
-    for (int j = threadIdx.x; j < N2; j += blockDim.x)
-      s_col[j] = a2[(int64_t)b * ld + (int64_t)hd * N2 + j];
-    __syncthreads();
+    const float p = __ldg(mix + (int64_t)b * H + hd);
+    if (p == 0.f) continue;                           // warp-uniform
+    const float4* w = reinterpret_cast<const float4*>(w3 + ((int64_t)hd * O + o) * N2);
+    const float4* a = reinterpret_cast<const float4*>(a2 + (int64_t)b * ld + (int64_t)hd * N2);
+    float d = 0.f;
+    for (int j0 = 0; j0 < nv; j0 += 128) {            // 4 independent float4 pairs per lane in flight
+      float4 wv[4], av[4];
 #pragma unroll
-    for (int i = 0; i < kFc3OutPerBlock / 8; ++i) {
-      const int o = o0 + warp * (kFc3OutPerBlock / 8) + i;
-      if (o >= O) continue;
-      const float* w = w3 + ((int64_t)hd * O + o) * N2;
-      float d = 0.f;
-      for (int j = lane; j < N2; j += 32) d = fmaf(w[j], s_col[j], d);
-      d = warp_sum(d);
-      acc[i] += p * (d + b3[(int64_t)hd * O + o]);
-    }
-  }
-  if (lane == 0) {
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 32 + lane;
+        const bool ok = j < nv;
+        wv[u] = ok ? __ldg(w + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        av[u] = ok ? __ldg(a + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-    for (int i = 0; i < kFc3OutPerBlock / 8; ++i) {
-      const int o = o0 + warp * (kFc3OutPerBlock / 8) + i;
-      if (o < O) y[(int64_t)b * O + o] = acc[i];
+      for (int u = 0; u < 4; ++u)
+        d = fmaf(wv[u].x, av[u].x, fmaf(wv[u].y, av[u].y, fmaf(wv[u].z, av[u].z, fmaf(wv[u].w, av[u].w, d))));
     }
+    d = warp_sum(d);
+    acc += p * (d + __ldg(b3 + (int64_t)hd * O + o));
   }
+  if (lane == 0) y[(int64_t)b * O + o] = acc;
 }
 
-// da2[b, hd*N2 + j] = mix[b,hd] * sum_o dy[b,o] w3[hd,o,j]   (zeros where the mixing weight is 0)
-__global__ void __launch_bounds__(256)
+// da2[b, hd*N2 + j] = mix[b,hd] * sum_o dy[b,o] w3[hd,o,j]   (zeros where the mixing weight is 0).
+// One block per (head, sample); the O outputs are split over G thread groups, each thread keeps a
+// float4 of columns, partial sums meet in shared memory.
+constexpr int kFc3ActThreads = 512;
+
+__global__ void __launch_bounds__(kFc3ActThreads)
 fc3_bwd_act_kernel(const float* __restrict__ dy, const float* __restrict__ w3,
                    const float* __restrict__ mix, int64_t ld, int H, int O, int N2,
                    float* __restrict__ da2) {
-  extern __shared__ float s_dy[];                     // [O]
+  extern __shared__ __align__(16) float s_fc3[];      // [O] scaled dy, then [G][N2] partial sums
   const int hd = blockIdx.x, b = blockIdx.y;
   const float p = mix[(int64_t)b * H + hd];
-  float* out = da2 + (int64_t)b * ld + (int64_t)hd * N2;
+  const int nv = N2 >> 2;
+  float4* out = reinterpret_cast<float4*>(da2 + (int64_t)b * ld + (int64_t)hd * N2);
   if (p == 0.f) {
-    for (int j = threadIdx.x; j < N2; j += blockDim.x) out[j] = 0.f;
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) out[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
+  float* s_dy = s_fc3;
+  float4* s_part = reinterpret_cast<float4*>(s_fc3 + ((O + 3) & ~3));
   for (int o = threadIdx.x; o < O; o += blockDim.x) s_dy[o] = p * dy[(int64_t)b * O + o];
   __syncthreads();
-  for (int j = threadIdx.x; j < N2; j += blockDim.x) {
-    const float* w = w3 + (int64_t)hd * O * N2 + j;
-    float d = 0.f;
-    for (int o = 0; o < O; ++o) d = fmaf(s_dy[o], w[(int64_t)o * N2], d);
-    out[j] = d;
+  const int W = nv < (int)blockDim.x ? nv : (int)blockDim.x;     // threads per output group
+  const int G = (int)blockDim.x / W;                              // output groups
+  const int og = threadIdx.x / W, jt = threadIdx.x % W;
+  if (og < G) {
+    const int o0 = (int)(((int64_t)O * og) / G), o1 = (int)(((int64_t)O * (og + 1)) / G);
+    for (int j = jt; j < nv; j += W) {
+      const float4* w = reinterpret_cast<const float4*>(w3 + (int64_t)hd * O * N2) + j;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int o = o0;
+      for (; o + 8 <= o1; o += 8) {                   // 8 independent row loads in flight
+        float4 wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (int64_t)(o + u) * nv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float s = s_dy[o + u];
+          acc.x = fmaf(s, wv[u].x, acc.x); acc.y = fmaf(s, wv[u].y, acc.y);
+          acc.z = fmaf(s, wv[u].z, acc.z); acc.w = fmaf(s, wv[u].w, acc.w);
+        }
+      }
+      for (; o < o1; ++o) {
+        const float4 wv = __ldg(w + (int64_t)o * nv);
+        const float s = s_dy[o];
+        acc.x = fmaf(s, wv.x, acc.x); acc.y = fmaf(s, wv.y, acc.y);
+        acc.z = fmaf(s, wv.z, acc.z); acc.w = fmaf(s, wv.w, acc.w);
+      }
+      s_part[(int64_t)og * nv + j] = acc;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    float4 acc = s_part[j];
+    for (int g = 1; g < G; ++g) {
+      const float4 q = s_part[(int64_t)g * nv + j];
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
+    out[j] = acc;
   }
 }
 
 constexpr int kFc3WOut = 8;   // outputs per block in the weight-gradient kernel
 
+// dw3[hd,o,j] = sum_b mix[b,hd] dy[b,o] a2[b,hd*N2+j], db3[hd,o] = sum_b mix[b,hd] dy[b,o]; only the
+// samples with a non-zero mixing weight for this head are visited (one-hot: B/H of them on average)
 __global__ void __launch_bounds__(256)
 fc3_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int64_t ld,
                  const float* __restrict__ mix, int B, int H, int O, int N2,
                  float* __restrict__ dw3, float* __restrict__ db3) {
-  extern __shared__ float s_pd[];                     // [B][kFc3WOut] mix * dy
+  extern __shared__ __align__(16) float s_fc3[];      // [B][kFc3WOut] mix * dy, then [B] active list
+  __shared__ int s_nact;
   const int hd = blockIdx.x;
   const int o0 = blockIdx.y * kFc3WOut;
-  for (int i = threadIdx.x; i < B * kFc3WOut; i += blockDim.x) {
-    const int b = i / kFc3WOut, oo = i % kFc3WOut;
-    const int o = o0 + oo;
-    s_pd[i] = (o < O) ? mix[(int64_t)b * H + hd] * dy[(int64_t)b * O + o] : 0.f;
+  float* s_pd = s_fc3;
+  int* s_act = reinterpret_cast<int*>(s_fc3 + (size_t)B * kFc3WOut);
+  if (threadIdx.x == 0) s_nact = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float p = mix[(int64_t)b * H + hd];
+    if (p != 0.f) {
+      const int slot = atomicAdd(&s_nact, 1);
+      s_act[slot] = b;
+#pragma unroll
+      for (int oo = 0; oo < kFc3WOut; ++oo)
+        s_pd[slot * kFc3WOut + oo] = (o0 + oo < O) ? p * dy[(int64_t)b * O + o0 + oo] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int nact = s_nact;
+  // (the order of the active samples varies between launches: sums of <= B terms, fp32 — the parity
+  // tolerance covers the reordering; sort the short list to make it launch-invariant)
+  if (threadIdx.x == 0 && nact > 1) {
+    for (int i = 1; i < nact; ++i) {                  // insertion sort, keeps s_pd rows with their sample
+      const int key = s_act[i];
+      float row[kFc3WOut];
+#pragma unroll
+      for (int oo = 0; oo < kFc3WOut; ++oo) row[oo] = s_pd[i * kFc3WOut + oo];
+      int k = i - 1;
+      while (k >= 0 && s_act[k] > key) {
+        s_act[k + 1] = s_act[k];
+#pragma unroll
+        for (int oo = 0; oo < kFc3WOut; ++oo) s_pd[(k + 1) * kFc3WOut + oo] = s_pd[k * kFc3WOut + oo];
+        --k;
+      }
+      s_act[k + 1] = key;
+#pragma unroll
+      for (int oo = 0; oo < kFc3WOut; ++oo) s_pd[(k + 1) * kFc3WOut + oo] = row[oo];
+    }
   }
   __syncthreads();
   for (int j = threadIdx.x; j < N2; j += blockDim.x) {
@@ -193,19 +270,19 @@ fc3_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int
     float acc[kFc3WOut];
 #pragma unroll
     for (int oo = 0; oo < kFc3WOut; ++oo) acc[oo] = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float av = ac[(int64_t)b * ld];           // coalesced over j
+    for (int i = 0; i < nact; ++i) {
+      const float av = ac[(int64_t)s_act[i] * ld];    // coalesced over j
 #pragma unroll
-      for (int oo = 0; oo < kFc3WOut; ++oo) acc[oo] = fmaf(s_pd[b * kFc3WOut + oo], av, acc[oo]);
+      for (int oo = 0; oo < kFc3WOut; ++oo) acc[oo] = fmaf(s_pd[i * kFc3WOut + oo], av, acc[oo]);
     }
 #pragma unroll
     for (int oo = 0; oo < kFc3WOut; ++oo)
       if (o0 + oo < O) dw3[((int64_t)hd * O + o0 + oo) * N2 + j] = acc[oo];
   }
   if (threadIdx.x < kFc3WOut && o0 + threadIdx.x < O) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += s_pd[b * kFc3WOut + threadIdx.x];
-    db3[(int64_t)hd * O + o0 + threadIdx.x] = s;
+    float sacc = 0.f;
+    for (int i = 0; i < nact; ++i) sacc += s_pd[i * kFc3WOut + threadIdx.x];
+    db3[(int64_t)hd * O + o0 + threadIdx.x] = sacc;
   }
 }
 
@@ -286,8 +363,11 @@ extern "C" int bdp_head_fc3_fwd(const float* a2, int64_t ld, const float* w3, co
   BDP_REQUIRE(a2 && w3 && b3 && mix && y, "head_fc3_fwd: NULL buffer");
   BDP_REQUIRE(B > 0 && B <= 65535 && H > 0 && O > 0 && N2 > 0 && N2 <= 12000,
               "head_fc3_fwd: bad sizes B=%lld H=%d O=%d N2=%d", (long long)B, H, O, N2);
-  dim3 grid((unsigned)((O + kFc3OutPerBlock - 1) / kFc3OutPerBlock), (unsigned)B);
-  fc3_fwd_kernel<<<grid, 256, N2 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+  BDP_REQUIRE(N2 % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a2) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(w3) & 15) == 0,
+              "head_fc3_fwd: N2 and ld must be multiples of 4 and a2 / w3 16-byte aligned");
+  dim3 grid((unsigned)((O + kFc3Warps - 1) / kFc3Warps), (unsigned)B);
+  fc3_fwd_kernel<<<grid, kFc3Warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       a2, ld, w3, b3, mix, H, O, N2, y);
   BDP_CUDA_CHECK_LAUNCH("fc3_fwd_kernel");
   return BDP_OK;
@@ -299,18 +379,26 @@ extern "C" int bdp_head_fc3_bwd(const float* dy, const float* a2, int64_t ld, co
   BDP_REQUIRE(dy && a2 && w3 && b3 && mix, "head_fc3_bwd: NULL buffer");
   BDP_REQUIRE(B > 0 && B <= 65535 && H > 0 && H <= 65535 && O > 0 && O <= 12000 && N2 > 0 &&
                   N2 <= 12000, "head_fc3_bwd: bad sizes");
-  BDP_REQUIRE((size_t)B * kFc3WOut * 4 <= 48 * 1024, "head_fc3_bwd: batch too large (%lld)", (long long)B);
+  BDP_REQUIRE((size_t)B * (kFc3WOut + 1) * 4 <= 48 * 1024, "head_fc3_bwd: batch too large (%lld)", (long long)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  BDP_REQUIRE(N2 % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(w3) & 15) == 0 &&
+                  (!da2 || (reinterpret_cast<uintptr_t>(da2) & 15) == 0),
+              "head_fc3_bwd: N2 and ld must be multiples of 4 and w3 / da2 16-byte aligned");
   if (da2) {
-    fc3_bwd_act_kernel<<<dim3(H, (unsigned)B), 256, O * sizeof(float), st>>>(dy, w3, mix, ld, H, O,
-                                                                            N2, da2);
+    const int nv = N2 / 4;
+    const int W = nv < kFc3ActThreads ? nv : kFc3ActThreads;
+    const int G = kFc3ActThreads / W;
+    const size_t smem = ((size_t)((O + 3) & ~3) + (size_t)G * N2) * sizeof(float);
+    if (smem > 48 * 1024)
+      BDP_CUDA_CALL(cudaFuncSetAttribute(fc3_bwd_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fc3_bwd_act_kernel<<<dim3(H, (unsigned)B), kFc3ActThreads, smem, st>>>(dy, w3, mix, ld, H, O, N2, da2);
     BDP_CUDA_CHECK_LAUNCH("fc3_bwd_act_kernel");
   }
   if (dw3) {
     BDP_REQUIRE(db3 != nullptr, "head_fc3_bwd: db3 is NULL");
     fc3_bwd_w_kernel<<<dim3(H, (unsigned)((O + kFc3WOut - 1) / kFc3WOut)), 256,
-                       (size_t)B * kFc3WOut * sizeof(float), st>>>(dy, a2, ld, mix, (int)B, H, O,
-                                                                   N2, dw3, db3);
+                       (size_t)B * (kFc3WOut + 1) * sizeof(float), st>>>(dy, a2, ld, mix, (int)B, H, O,
+                                                                         N2, dw3, db3);
     BDP_CUDA_CHECK_LAUNCH("fc3_bwd_w_kernel");
   }
   if (dmix) {
