@@ -598,6 +598,24 @@ def bench(dev, peaks):
         out["pascal_head_B%d_tf32_stacked_params" % B] = {
             "samples_per_s_fwd_bwd": B / (ms * 1e-3), "ms_fwd_bwd": ms,
             "fwd_bwd_hbm_frac": 3 * n_params * 4 / (ms * 1e-3) / 1e9 / hbm}
+    # opt-in CUDA-graph step: heads forward + fused loss + heads backward in one graph launch
+    from .graph_step import GraphedBinDeltaStep
+    for B in (32, 96):
+        x = torch.randn(B, 2048, device=dev)
+        lab = torch.randint(0, C, (B, 1), device=dev)
+        bins = torch.randint(0, K, (B,), device=dev)
+        tgt = torch.randn(B, 3, device=dev)
+        for mode in ("tf32", "fp32"):
+            set_precision(mode)
+            try:
+                gs = GraphedBinDeltaStep(m, B, keys, L.POSE_GEODESIC_AA, True)
+                ms = _time(lambda: gs(x, lab, bins, tgt), 50, 20)
+            finally:
+                set_precision("fp32")
+            out["pascal_head_B%d_%s_cuda_graph" % (B, mode)] = {
+                "samples_per_s_fwd_bwd": B / (ms * 1e-3), "ms_fwd_bwd": ms,
+                "fwd_bwd_hbm_frac": 3 * n_params * 4 / (ms * 1e-3) / 1e9 / hbm}
+            del gs
     # raw fc1 GEMM: the dominant kernel of the head (197 MB of weights streamed once)
     H, N1, N0, B = 24, 1000, 2048, 32
     w1 = m._heads().ensure()["w1"]

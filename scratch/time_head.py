@@ -54,3 +54,17 @@ for B in (32, 96):
         head.set_precision(mode)
         g, h = t(step2)
         print("B=%d %s fwd+bwd STACKED gpu %.0f us  host-issue %.0f us" % (B, mode, g, h))
+
+# CUDA-graph step
+from bdpose.graph_step import GraphedBinDeltaStep
+for B in (32, 96):
+    x = torch.randn(B, 2048, device=dev)
+    lab = torch.randint(0, 12, (B, 1), device=dev)
+    bins = torch.randint(0, 200, (B,), device=dev)
+    tgt = torch.randn(B, 3, device=dev)
+    for mode in ("tf32", "fp32"):
+        head.set_precision(mode)
+        gs = GraphedBinDeltaStep(m, B, keys, L.POSE_GEODESIC_AA, True)
+        g, h = t(lambda: gs(x, lab, bins, tgt))
+        print("B=%d %s fwd+bwd GRAPH   gpu %.0f us  host-issue %.0f us" % (B, mode, g, h))
+head.set_precision("fp32")

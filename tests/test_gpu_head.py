@@ -435,3 +435,52 @@ def test_persistent_grad_buffers_and_stacked_parameters(cuda):
     before = m.res_models[1].fc2.weight.detach().clone()
     opt.step()
     assert not torch.equal(before, m.res_models[1].fc2.weight)     # the modules see the update
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_graphed_step_matches_eager(cuda, mode):
+    """The CUDA-graph step (heads forward + fused loss + heads backward in one graph launch) gives
+    the losses, parameter gradients, input gradient and BatchNorm statistics of the eager
+    autograd path on the same weights and batch."""
+    import copy
+    import binDeltaModels as M
+    from bdpose import head, ops, _lib as L
+    from bdpose.graph_step import GraphedBinDeltaStep
+    torch.manual_seed(5)
+    C, K, N0, N1, N2, nd, B = 4, 24, 96, 64, 32, 3, 12
+    head.set_precision(mode)
+    try:
+        m1 = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+        m1.feature_model = torch.nn.Identity()
+        m1.cuda().train()
+        m2 = copy.deepcopy(m1)
+        keys = torch.randn(K, 3, device=cuda)
+        step = GraphedBinDeltaStep(m2, B, keys, L.POSE_GEODESIC_AA, True)
+        for it in range(3):                       # several steps: running statistics keep moving
+            x = torch.randn(B, N0, device=cuda)
+            lab = torch.randint(0, C, (B, 1), device=cuda)
+            bins = torch.randint(0, K, (B,), device=cuda)
+            tgt = torch.randn(B, 3, device=cuda)
+            w = 0.5 + it
+            for p in m1.parameters():
+                p.grad = None
+            xe = x.clone().requires_grad_(True)
+            y1, y2 = m1(xe, lab)
+            lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
+            (lc + w * lr).backward()
+            if it == 1:
+                for p in m2.parameters():
+                    p.grad = None                 # zero_grad(set_to_none): views are handed out again
+            glc, glr = step(x, lab, bins, tgt, pose_weight=w)
+            assert torch.allclose(glc, lc.detach(), rtol=1e-6, atol=0) and torch.allclose(glr, lr.detach(), rtol=1e-6, atol=0)
+            scale_close(step.dx, xe.grad, 1e-6, "graph dx")
+            for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+                assert p2.grad is not None, n
+                if float(p1.grad.abs().max()) > 0:
+                    scale_close(p2.grad, p1.grad, 1e-6, "graph grad " + n)
+                else:
+                    assert float(p2.grad.abs().max()) == 0
+            for (n, b1), (_, b2) in zip(m1.named_buffers(), m2.named_buffers()):
+                assert torch.equal(b1, b2), n
+    finally:
+        head.set_precision("fp32")
