@@ -640,6 +640,7 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   const size_t fixed = 1024 + 8 * (3 * kMaxStages + 4) + slack + (P.stage_out ? kEpiBytes : 0);
   int stages = (int)((224 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  { const char* e = getenv("BDP_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
   if (stages < 2) stages = 2;
   P.stages = stages;
   const size_t smem = stages * stage_bytes + fixed;
