@@ -665,17 +665,40 @@ def bench(dev, peaks):
 
 
 def bench_dp(dev, world):
-    """BASELINE config 4 / north star (e): batch data-parallel head step on every rank — forward,
-    fused loss, backward, then ONE all-reduce(mean) per stacked gradient tensor over NCCL.  Each rank
-    has its own batch (per-GPU BatchNorm statistics).  Returns aggregate samples/s (max over ranks)."""
+    """BASELINE config 4 / north star (e): batch data-parallel head step on every rank.  Each rank
+    runs the CUDA-graph step (heads forward, fused loss, heads backward: one graph launch) on its own
+    batch (per-GPU BatchNorm statistics), then ONE NCCL all-reduce(AVG) over the flat gradient
+    buffer.  The eager autograd step is measured next to it: with 8 processes on one host it is
+    host-bound (the Python issue path of every rank competes for the same cores).
+    Returns aggregate samples/s (time = max over ranks)."""
     import torch.distributed as dist
     import objectnetHelperFunctions as OH
     from . import ops
+    from .graph_step import GraphedBinDeltaStep
     out = {}
+
+    def timed(step):
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(30):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 30], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
     set_precision("tf32")
     try:
         for name in ("objectnet", "pascal"):
             torch.manual_seed(0)
+            keys = torch.randn(200, 3, device=dev)
             if name == "objectnet":
                 m = OH.OneBinDeltaModel.__new__(OH.OneBinDeltaModel)
                 torch.nn.Module.__init__(m)
@@ -685,45 +708,43 @@ def bench_dp(dev, world):
                 m.res_model = OH.res_3layer(2148, 1000, 500, 3).cuda()
                 object.__setattr__(m, "_stack", None)
                 B, C = 256, 100
-                fwd = m.forward_features
+                stack = HeadStack([[m.bin_model], [m.res_model]])
+                object.__setattr__(m, "_stack", stack)
             else:
                 m = _pascal_model()
                 B, C = 96, 12
-                fwd = m.forward_features
+                stack = m._heads()
             m.train()
             params = list(m.parameters())
             x = torch.randn(B, 2048, device=dev, requires_grad=True)
             lab = torch.randint(0, C, (B, 1), device=dev)
             bins = torch.randint(0, 200, (B,), device=dev)
             tgt = torch.randn(B, 3, device=dev)
-            keys = torch.randn(200, 3, device=dev)
 
-            def step():
+            def eager():
                 for p in params:
                     p.grad = None
-                y1, y2 = fwd(x, lab)
+                y1, y2 = m.forward_features(x, lab)
                 lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
                 (lc + lr).backward()
                 sync_head_gradients(m)
-            for _ in range(10):
-                step()
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(30):
-                step()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = torch.tensor([e0.elapsed_time(e1) / 30], device=dev)
-            if world > 1:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            ms_eager = timed(eager)
+            gs = GraphedBinDeltaStep(stack, B, keys, L.POSE_GEODESIC_AA, True)
+            zero_lab = torch.zeros_like(lab)
+
+            def graphed():
+                if name == "objectnet":       # one MLP pair for all classes on cat(features, one-hot)
+                    gs(torch.cat((x.detach(), onehot(lab, C)), dim=1), zero_lab, bins, tgt)
+                else:
+                    gs(x, lab, bins, tgt)
+                allreduce_stack_grads(stack)
+            ms = timed(graphed)
             n_par = sum(p.numel() for p in params)
             out["%s_head_dp%d_B%d_tf32" % (name, world, B)] = {
-                "samples_per_s_fwd_bwd": B * world / (float(ms) * 1e-3), "ms_fwd_bwd_allreduce": float(ms),
+                "samples_per_s_fwd_bwd": B * world / (ms * 1e-3), "ms_fwd_bwd_allreduce": ms,
+                "ms_eager_autograd_step": ms_eager, "step": "cuda graph + one NCCL all-reduce(AVG)",
                 "allreduce_bytes": n_par * 4, "per_gpu_batch": B}
-            del m
+            del m, gs
     finally:
         set_precision("fp32")
     return out

@@ -230,41 +230,33 @@ fc3_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ a2, int
   const int o0 = blockIdx.y * kFc3WOut;
   float* s_pd = s_fc3;
   int* s_act = reinterpret_cast<int*>(s_fc3 + (size_t)B * kFc3WOut);
-  if (threadIdx.x == 0) s_nact = 0;
-  __syncthreads();
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const float p = mix[(int64_t)b * H + hd];
-    if (p != 0.f) {
-      const int slot = atomicAdd(&s_nact, 1);
+  // ordered compaction of the active samples (ascending b: the accumulation order is fixed, so the
+  // result is launch-invariant): ballot inside a warp, warp counts through shared memory
+  __shared__ int s_wcnt[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int base = 0;
+  for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+    const int b = b0 + threadIdx.x;
+    const float p = b < B ? mix[(int64_t)b * H + hd] : 0.f;
+    const bool act = p != 0.f;
+    const unsigned m = __ballot_sync(BDP_FULL_MASK, act);
+    if (lane == 0) s_wcnt[warp] = __popc(m);
+    __syncthreads();
+    int off = base, tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { off += w < warp ? s_wcnt[w] : 0; tot += s_wcnt[w]; }
+    if (act) {
+      const int slot = off + __popc(m & ((1u << lane) - 1u));
       s_act[slot] = b;
 #pragma unroll
       for (int oo = 0; oo < kFc3WOut; ++oo)
         s_pd[slot * kFc3WOut + oo] = (o0 + oo < O) ? p * dy[(int64_t)b * O + o0 + oo] : 0.f;
     }
+    base += tot;
+    __syncthreads();
   }
+  if (threadIdx.x == 0) s_nact = base;
   __syncthreads();
   const int nact = s_nact;
-  // (the order of the active samples varies between launches: sums of <= B terms, fp32 — the parity
-  // tolerance covers the reordering; sort the short list to make it launch-invariant)
-  if (threadIdx.x == 0 && nact > 1) {
-    for (int i = 1; i < nact; ++i) {                  // insertion sort, keeps s_pd rows with their sample
-      const int key = s_act[i];
-      float row[kFc3WOut];
-#pragma unroll
-      for (int oo = 0; oo < kFc3WOut; ++oo) row[oo] = s_pd[i * kFc3WOut + oo];
-      int k = i - 1;
-      while (k >= 0 && s_act[k] > key) {
-        s_act[k + 1] = s_act[k];
-#pragma unroll
-        for (int oo = 0; oo < kFc3WOut; ++oo) s_pd[(k + 1) * kFc3WOut + oo] = s_pd[k * kFc3WOut + oo];
-        --k;
-      }
-      s_act[k + 1] = key;
-#pragma unroll
-      for (int oo = 0; oo < kFc3WOut; ++oo) s_pd[(k + 1) * kFc3WOut + oo] = row[oo];
-    }
-  }
-  __syncthreads();
   for (int j = threadIdx.x; j < N2; j += blockDim.x) {
     const float* ac = a2 + (int64_t)hd * N2 + j;
     float acc[kFc3WOut];
