@@ -164,11 +164,19 @@ def _pose_targets(ds):
 class _LabelTable:
     """name -> row index into per-class label arrays held on the host (tiny: N x (1 + d) numbers)."""
 
-    def __init__(self, ds, centers, riemannian=False, soft_gamma=None):
+    def __init__(self, ds, centers, riemannian=False, soft_gamma=None, gmm=None):
         per_class = _pose_targets(ds)
         sizes = [len(r) for r in per_class]
         y = torch.from_numpy(np.concatenate(per_class)).cuda()
-        if soft_gamma is not None:
+        if gmm is not None:
+            # GMM dictionaries are outside the kernel scope (SURVEY §2): the pickled estimator's own
+            # predict_proba runs once over the whole dataset (binDeltaGenerators.py:52-55)
+            yh = y.cpu().numpy()
+            p = np.asarray(gmm.predict_proba(yh))
+            b = torch.from_numpy(p).float()
+            r = torch.from_numpy(yh - np.dot(p, gmm.means_)).float()
+            rot = None
+        elif soft_gamma is not None:
             b, r = assign_soft_labels(y, centers, soft_gamma)
             rot = None
         elif riemannian:
@@ -198,11 +206,19 @@ def _make(name, ydata_type, mode):
         ImagesAll = _images_all()
 
         class _Gen(ImagesAll):
-            def __init__(self, db_path, db_type, kmeans_file):
+            def _setup(self, db_path, db_type, dict_file):
+                if mode == 'gmm':
+                    ImagesAll.__init__(self, db_path, db_type)
+                    with open(dict_file, 'rb') as f:
+                        self.gmm = pickle.load(f)
+                    self.num_clusters = self.gmm.n_components
+                    self._table = _LabelTable(ds=self, centers=None, gmm=self.gmm)
+                    return
+                kmeans_file = dict_file
                 if ydata_type == 'axis_angle':
-                    super().__init__(db_path, db_type)
+                    ImagesAll.__init__(self, db_path, db_type)
                 else:
-                    super().__init__(db_path, db_type, 'quaternion')
+                    ImagesAll.__init__(self, db_path, db_type, 'quaternion')
                 with open(kmeans_file, 'rb') as f:
                     self.kmeans = pickle.load(f)
                 self.num_clusters = self.kmeans.n_clusters
@@ -216,6 +232,13 @@ def _make(name, ydata_type, mode):
                     self.rotations_dict = rot.cpu().numpy()
                 self._table = _LabelTable(ds=self, centers=centers, riemannian=(mode == 'riemannian'),
                                           soft_gamma=(10.0 if mode == 'soft' else None))
+
+            if mode == 'gmm':
+                def __init__(self, db_path, db_type, gmm_file):
+                    self._setup(db_path, db_type, gmm_file)
+            else:
+                def __init__(self, db_path, db_type, kmeans_file):
+                    self._setup(db_path, db_type, kmeans_file)
 
             def __len__(self):
                 return np.amax(self.num_images)
@@ -239,6 +262,7 @@ def _make(name, ydata_type, mode):
 
 _factories = {
     'GBDGenerator': _make('GBDGenerator', 'axis_angle', 'hard'),        # binDeltaGenerators.py:10-32
+    'XPBDGenerator': _make('XPBDGenerator', 'axis_angle', 'gmm'),       # :35-57 (GMM soft bins)
     'GBDGeneratorQ': _make('GBDGeneratorQ', 'quaternion', 'hard'),      # :60-83
     'XPBDGeneratorQ': _make('XPBDGeneratorQ', 'quaternion', 'soft'),    # :86-110
     'RBDGenerator': _make('RBDGenerator', 'axis_angle', 'riemannian'),  # :113-139

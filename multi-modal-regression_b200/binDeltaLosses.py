@@ -231,8 +231,11 @@ class RelaXedProbabilisticLossQ(_ProbBase):
 
 
 class RelaXedProbabilisticMultiresLoss(RelaXedProbabilisticLoss):
-    """binDeltaLosses.py:174-186"""
+    """binDeltaLosses.py:169-180 (the reference names the dictionary argument kmeans_file here)"""
     per_bin_delta = True
+
+    def __init__(self, alpha, kmeans_file, my_loss):
+        super().__init__(alpha, kmeans_file, my_loss)
 
 
 class ProbabilisticMultiresLoss(ProbabilisticLoss):

@@ -10,7 +10,30 @@ from torch import nn
 import torch.nn.functional as F
 
 from bdpose import head as _head
-from binDeltaModels import bin_3layer, res_3layer, res_2layer, _feature_model   # noqa: F401
+import binDeltaModels as _bdm
+from binDeltaModels import _feature_model
+
+
+# the reference's ObjectNet copies of the building blocks use lower-case argument names
+class bin_3layer(_bdm.bin_3layer):
+    """objectnetHelperFunctions.py:110-123"""
+
+    def __init__(self, n0, n1, n2, num_clusters):
+        super().__init__(n0, n1, n2, num_clusters)
+
+
+class res_3layer(_bdm.res_3layer):
+    """objectnetHelperFunctions.py:126-139"""
+
+    def __init__(self, n0, n1, n2, dim):
+        super().__init__(n0, n1, n2, dim)
+
+
+class res_2layer(_bdm.res_2layer):
+    """objectnetHelperFunctions.py:142-152"""
+
+    def __init__(self, n0, n1, dim):
+        super().__init__(n0, n1, dim)
 
 
 def _cat_onehot(feat, label, num_classes):
