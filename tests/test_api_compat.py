@@ -21,7 +21,7 @@ LEFT_TO_REFERENCE = {
     "objectnetHelperFunctions": {"TrainImages", "TestImages", "preprocess_real", "preprocess_render"},
     "binDeltaGenerators": set(),
     "binDeltaModels": set(), "binDeltaLosses": set(), "poseModels": set(),
-    "axisAngle": set(), "quaternion": set(),
+    "axisAngle": set(), "quaternion": set(), "featureModels": set(),
 }
 
 
