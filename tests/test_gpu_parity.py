@@ -483,3 +483,26 @@ def test_eval_full_size_properties(cuda):
     assert int(b30) == int((eh < 30).sum())
     sub = slice(0, 2000)
     close(e[sub], O.errors_aa(a[sub].cpu().numpy(), b[sub].cpu().numpy()), rtol=1e-9, atol=1e-6)
+
+
+def test_kmeans_plusplus_fit_runs_and_improves(cuda):
+    """The default path of learnKmeansDictionary.py:41-42 (k-means++ seeding, several restarts): the
+    seeding stream is torch's, so there is no bit parity with sklearn here — check the fit contract
+    (shapes, dtype, labels consistent with the centres, inertia no worse than a plain first-K init)."""
+    from bdpose.kmeans import KMeans
+    from bdpose import ops
+    rng = np.random.default_rng(2)
+    X = rand_rot(rng, 60_000)[0]
+    K = 64
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        km = KMeans(n_clusters=K, n_init=2, max_iter=30, random_state=3, n_jobs=10).fit(X)
+        base = KMeans(n_clusters=K, init=X[:K].copy(), max_iter=30).fit(X)
+    assert km.cluster_centers_.shape == (K, 3) and km.cluster_centers_.dtype == np.float64
+    assert km.labels_.shape == (X.shape[0],) and km.labels_.dtype == np.int32
+    lab, _, sq = ops.assign_nearest(torch.from_numpy(X).to(cuda), torch.from_numpy(km.cluster_centers_).to(cuda),
+                                    want_residual=False, want_sqdist=True, label_dtype=torch.int32)
+    assert np.array_equal(lab.cpu().numpy(), km.labels_)
+    close(float(sq.sum()), km.inertia_, rtol=1e-9)
+    assert km.inertia_ <= base.inertia_ * 1.05
+    assert np.array_equal(km.predict(X[:1000].astype(np.float32)), km.labels_[:1000])
