@@ -455,6 +455,164 @@ class _HeadFn(torch.autograd.Function):
         return dx, dmix, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------
+# stacks of two-layer heads (one delta per bin: SURVEY §8(f)-1)
+# ------------------------------------------------------------------------------------------------
+class Mlp2Stack:
+    """H identical two-layer heads fc2(relu(bn1(fc1 x))) (binDeltaModels.res_2layer, 49-59) over
+    stacked storage: fc1 [H,N1,N0] streams through the tcgen05 GEMM (for OneDeltaPerBinModel C*K = 192
+    heads: 157 MB of weights), BatchNorm through bn_relu, the tiny per-head output layer through
+    a batched matmul.  Same caching rules as HeadStack (Parameters are views of the stacked buffers)."""
+    _slots = (("w1", "fc1", "weight"), ("g1", "bn1", "weight"), ("be1", "bn1", "bias"),
+              ("w2", "fc2", "weight"), ("b2", "fc2", "bias"))
+    _bufs = (("rm1", "bn1", "running_mean"), ("rv1", "bn1", "running_var"),
+             ("nb1", "bn1", "num_batches_tracked"))
+
+    def __init__(self, heads):
+        self.heads = list(heads)
+        self.buf = None
+        self.grad = None
+        self.gviews = None
+        self._expected = None
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_no_stack, ())
+
+    def _probe(self):
+        out = []
+        for m in self.heads:
+            mods = m._modules
+            out.append(mods["fc1"]._parameters["weight"].data_ptr())
+            out.append(mods["bn1"]._buffers["running_mean"].data_ptr())
+            out.append(mods["fc2"]._parameters["weight"].data_ptr())
+        return out
+
+    def ensure(self):
+        if self.buf is not None and self._probe() == self._expected:
+            return self.buf
+        dev = self.heads[0].fc1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("bdpose heads run on CUDA only (parameters are on %s); call .cuda()" % dev)
+        buf = {}
+        with torch.no_grad():
+            for key, sub, name in self._slots:
+                src = [getattr(getattr(m, sub), name) for m in self.heads]
+                st = torch.stack([p.detach().to(dev, torch.float32) for p in src]).contiguous()
+                for i, p in enumerate(src):
+                    p.data = st[i]
+                buf[key] = st
+            for key, sub, name in self._bufs:
+                src = [getattr(getattr(m, sub), name) for m in self.heads]
+                st = torch.stack([b.detach().to(dev) for b in src]).contiguous()
+                for i, m in enumerate(self.heads):
+                    getattr(m, sub)._buffers[name] = st[i]
+                buf[key] = st
+        self.buf = buf
+        self.grad = None
+        self.gviews = None
+        self.plists = {key: [getattr(getattr(m, sub), name) for m in self.heads]
+                       for key, sub, name in self._slots}
+        self._expected = self._probe()
+        return buf
+
+    def publish_or_accumulate(self, grads):
+        """First backward since zero_grad: the Parameters' .grad become views of the persistent
+        stacked buffers (filled with `grads`); otherwise accumulate."""
+        first = self.plists["w1"][0].grad
+        if self.grad is None:
+            self.grad = {k: torch.empty_like(self.buf[k]) for k, _, _ in self._slots}
+            self.gviews = {k: g.unbind(0) for k, g in self.grad.items()}
+        mine = first is not None and first.data_ptr() == self.grad["w1"].data_ptr()
+        if first is None:
+            for k in self.grad:
+                self.grad[k].copy_(grads[k])
+            for k, plist in self.plists.items():
+                for p, v in zip(plist, self.gviews[k]):
+                    p.grad = v
+        elif mine:
+            for k in self.grad:
+                self.grad[k].add_(grads[k])
+        else:
+            for k, plist in self.plists.items():
+                for p, v in zip(plist, grads[k].unbind(0)):
+                    p.grad = v.clone() if p.grad is None else p.grad.add_(v)
+
+
+class _Mlp2Fn(torch.autograd.Function):
+    """Y [B, H, O] = every head of an Mlp2Stack on x [B, N0]."""
+
+    @staticmethod
+    def forward(ctx, x, stack, training):
+        buf = stack.ensure()
+        H, N1, N0 = buf["w1"].shape
+        O = buf["w2"].shape[1]
+        B = x.shape[0]
+        F1 = H * N1
+        if x.dim() != 2 or x.shape[1] != N0:
+            raise RuntimeError("head: input has %s features, fc1 expects %d" % (tuple(x.shape[1:]), N0))
+        if N0 % 4 or N1 % 4:
+            raise RuntimeError("head: layer widths must be multiples of 4 (got %d, %d)" % (N0, N1))
+        if training and B < 2:
+            raise ValueError("Expected more than 1 value per channel when training, got input size "
+                             "[%d, %d]" % (B, N1))
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        h1 = torch.empty((B, F1), dtype=torch.float32, device=x.device)
+        gemm_tf32(x, 0, N0, 0, buf["w1"], 0, N0, 0, h1, 0, F1, 0, B, F1, N0)
+        a1, m1, is1 = bn_relu_fwd(h1, buf["g1"].view(-1), buf["be1"].view(-1), buf["rm1"].view(-1),
+                                  buf["rv1"].view(-1), training)
+        if not training:
+            m1, is1 = buf["rm1"].view(-1).clone(), torch.rsqrt(buf["rv1"].view(-1) + BN_EPS)
+        else:
+            buf["nb1"] += 1
+        # per-head output layer: [H, B, N1] x [H, N1, O] + bias
+        y = torch.baddbmm(buf["b2"].unsqueeze(1), a1.view(B, H, N1).transpose(0, 1),
+                          buf["w2"].transpose(1, 2))
+        ctx.stack, ctx.training = stack, training
+        ctx.saved = (x, h1, a1, m1, is1)
+        return y.transpose(0, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, dy):
+        stack = ctx.stack
+        buf = stack.buf
+        x, h1, a1, m1, is1 = ctx.saved
+        H, N1, N0 = buf["w1"].shape
+        B = x.shape[0]
+        F1 = H * N1
+        dyh = dy.float().transpose(0, 1).contiguous()                      # [H, B, O]
+        a1h = a1.view(B, H, N1).transpose(0, 1)                            # [H, B, N1]
+        grads = {"w2": torch.bmm(dyh.transpose(1, 2), a1h), "b2": dyh.sum(1)}
+        da1 = torch.bmm(dyh, buf["w2"]).transpose(0, 1).reshape(B, F1).contiguous()
+        dh1, dg1, dbe1 = bn_relu_bwd(da1, a1, h1, buf["g1"].view(-1), m1, is1, ctx.training)
+        dw1 = torch.empty_like(buf["w1"])
+        gemm_tf32(dh1, 1, F1, 0, x, 1, N0, 0, dw1, 0, N0, 0, F1, N0, B)
+        grads.update(w1=dw1, g1=dg1.view(H, N1), be1=dbe1.view(H, N1))
+        stack.publish_or_accumulate(grads)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            n_tiles = (N0 + 255) // 256
+            splits = gemm_splits(F1, max(1, min(64, L.lib().bdp_sm_count() // n_tiles)))
+            parts = torch.empty((splits, B, N0), dtype=torch.float32, device=x.device)
+            gemm_tf32(dh1, 0, F1, 0, buf["w1"], 1, N0, 0, parts, 0, N0, 0, B, N0, F1, splits=splits,
+                      c_ss=B * N0)
+            dx = torch.empty((B, N0), dtype=torch.float32, device=x.device)
+            sum_slabs(parts, B * N0, splits, B * N0, dx)
+        return dx, None, None
+
+
+def run_mlp2_all(stack, x, training):
+    """Every head of an Mlp2Stack on features x [B, N0] -> [B, H, O]."""
+    stack.ensure()
+    if not x.requires_grad:
+        x = x.detach().requires_grad_(True)      # keeps the node alive so parameter grads are produced
+    return _Mlp2Fn.apply(x, stack, training)
+
+
 def allreduce_stack_grads(stack, group=None, average=True):
     """Data-parallel step of the head: all-reduce the STACKED gradient buffers of a
     HeadStack in place — a handful of large contiguous tensors (fc1 alone is 197 MB for the Pascal

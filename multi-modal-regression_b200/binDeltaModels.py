@@ -10,8 +10,10 @@ kernels.
   built on the device (the reference round-trips it through the CPU every forward,
   binDeltaModels.py:116-117).  `forward_mixed(x, mix)` is the soft-mixing form the joint
   category+pose scripts build by hand (learnJointCatPoseModel_weighted.py:107-115).
-* The 1- and 2-layer blocks and the one-delta-per-bin models keep the reference's
-  structure on stock torch layers.
+* `OneDeltaPerBinModel` / `ProbabilisticOneDeltaPerBinModel` run their C*K two-layer
+  delta heads as one stack too (`bdpose.head.Mlp2Stack`: one fc1 GEMM over 2048 -> C*K*N3, BatchNorm,
+  a batched output layer) instead of the reference's python loop over C*K modules; a single
+  1- / 2-layer block called on its own stays on stock torch layers.
 """
 import torch
 from torch import nn
@@ -172,8 +174,8 @@ def _onehot_cpu_like(idx, n):
 
 
 class OneDeltaPerBinModel(nn.Module):
-    """binDeltaModels.py:124-151: C bin heads (fused stack) + C*K res_2layer heads (stock torch layers,
-    SURVEY §8(f)-1), delta selected by class then by argmax bin."""
+    """binDeltaModels.py:124-151: C bin heads (fused 3-layer stack) + C*K res_2layer heads (fused
+    2-layer stack), delta selected by class then by argmax bin."""
 
     def __init__(self, feature_network, num_classes, num_clusters, N0, N1, N2, N3, ndim):
         super().__init__()
@@ -186,6 +188,7 @@ class OneDeltaPerBinModel(nn.Module):
         self.bin_models = nn.ModuleList([bin_3layer(N0, N1, N2, num_clusters) for i in range(self.num_classes)]).cuda()
         self.res_models = nn.ModuleList([res_2layer(N0, N3, ndim) for i in range(self.num_classes * self.num_clusters)]).cuda()
         object.__setattr__(self, '_stack', None)
+        object.__setattr__(self, '_stack2', None)
 
     def _bin_scores(self, x, mix):
         st = self.__dict__.get('_stack')
@@ -195,19 +198,27 @@ class OneDeltaPerBinModel(nn.Module):
             object.__setattr__(self, '_stack', st)
         return _head.run_heads(st, x, mix, self.training)[0]
 
-    def _all_deltas(self, x, class_mix):
-        y2 = torch.stack([m(x) for m in self.res_models])
-        y2 = y2.view(self.num_classes, self.num_clusters, -1, self.ndim).permute(1, 2, 3, 0)
-        return torch.squeeze(torch.matmul(y2, class_mix.unsqueeze(2)), 3)          # [K, B, ndim]
+    def _class_deltas(self, x, class_label):
+        """All K per-bin deltas of every sample's own class: [B, K, ndim].  The C*K two-layer heads
+        run fused (one fc1 GEMM over the stacked 2048 -> C*K*N3 weights, BatchNorm, batched output
+        layer); the reference's one-hot matmul select (binDeltaModels.py:141-145) is a gather."""
+        st = self.__dict__.get('_stack2')
+        heads = list(self.res_models)
+        if st is None or len(st.heads) != len(heads) or any(a is not b for a, b in zip(st.heads, heads)):
+            st = _head.Mlp2Stack(heads)
+            object.__setattr__(self, '_stack2', st)
+        y = _head.run_mlp2_all(st, x, self.training)                     # [B, C*K, ndim]
+        y = y.view(y.shape[0], self.num_classes, self.num_clusters, self.ndim)
+        idx = class_label.reshape(-1, 1, 1, 1).expand(-1, 1, self.num_clusters, self.ndim)
+        return torch.gather(y, 1, idx).squeeze(1)
 
     def forward(self, x, class_label):
         x = self.feature_model(x)
         class_mix = _onehot_cpu_like(class_label, self.num_classes)
         y1 = self._bin_scores(x, class_mix)
-        y2 = self._all_deltas(x, class_mix)
-        pose_label = torch.argmax(y1, dim=1, keepdim=True)
-        pose_mix = _onehot_cpu_like(pose_label, self.num_clusters).unsqueeze(2)
-        y2 = torch.squeeze(torch.bmm(y2.permute(1, 2, 0), pose_mix), 2)
+        y2 = self._class_deltas(x, class_label)                          # [B, K, ndim]
+        pose_label = torch.argmax(y1, dim=1, keepdim=True)               # first maximum, as torch.max
+        y2 = torch.gather(y2, 1, pose_label.unsqueeze(2).expand(-1, 1, self.ndim)).squeeze(1)
         return [y1, y2]
 
 
@@ -218,5 +229,4 @@ class ProbabilisticOneDeltaPerBinModel(OneDeltaPerBinModel):
         x = self.feature_model(x)
         class_mix = _onehot_cpu_like(class_label, self.num_classes)
         y1 = self._bin_scores(x, class_mix)
-        y2 = self._all_deltas(x, class_mix).permute(1, 0, 2)
-        return [y1, y2]
+        return [y1, self._class_deltas(x, class_label)]

@@ -355,3 +355,42 @@ class ObjectnetHeads(nn.Module):
         onehot = torch.zeros(label.size(0), self.num_classes).scatter_(1, label, 1.0)
         x = torch.cat((x, onehot), dim=1)
         return [self.bin_model(x), self.res_model(x)]
+
+
+class Mlp2(nn.Module):
+    """bin_2layer / res_2layer — binDeltaModels.py:36-59"""
+
+    def __init__(self, N0, N1, Nout):
+        super().__init__()
+        self.fc1 = nn.Linear(N0, N1, bias=False)
+        self.bn1 = nn.BatchNorm1d(N1)
+        self.fc2 = nn.Linear(N1, Nout)
+
+    def forward(self, x):
+        return self.fc2(F.relu(self.bn1(self.fc1(x))))
+
+
+class OneDeltaPerBinHeads(nn.Module):
+    """The head part of OneDeltaPerBinModel / ProbabilisticOneDeltaPerBinModel
+    (binDeltaModels.py:124-178): C bin heads + C*K two-layer delta heads; the delta is picked by the
+    class label and then by the argmax bin (146-149), or all K deltas of the class are returned
+    (probabilistic: 174-176)."""
+
+    def __init__(self, num_classes, num_clusters, N0, N1, N2, N3, ndim):
+        super().__init__()
+        self.num_classes, self.num_clusters, self.ndim = num_classes, num_clusters, ndim
+        self.bin_models = nn.ModuleList([Mlp3(N0, N1, N2, num_clusters) for _ in range(num_classes)])
+        self.res_models = nn.ModuleList([Mlp2(N0, N3, ndim) for _ in range(num_classes * num_clusters)])
+
+    def forward(self, x, class_label, probabilistic=False):
+        y1 = torch.stack([m(x) for m in self.bin_models]).permute(1, 2, 0)
+        y2 = torch.stack([m(x) for m in self.res_models])
+        y2 = y2.view(self.num_classes, self.num_clusters, -1, self.ndim).permute(1, 2, 3, 0)
+        cl = torch.zeros(class_label.size(0), self.num_classes).scatter_(1, class_label, 1.0).unsqueeze(2)
+        y1 = torch.squeeze(torch.bmm(y1, cl), 2)
+        y2 = torch.squeeze(torch.matmul(y2, cl), 3)                     # [K, B, ndim]
+        if probabilistic:
+            return [y1, y2.permute(1, 0, 2)]
+        _, pose_label = torch.max(y1, dim=1, keepdim=True)
+        pl = torch.zeros(pose_label.size(0), self.num_clusters).scatter_(1, pose_label, 1.0).unsqueeze(2)
+        return [y1, torch.squeeze(torch.bmm(y2.permute(1, 2, 0), pl), 2)]

@@ -258,6 +258,53 @@ def main():
     print("golden vectors written to", OUT)
 
 
+def main_perbin():
+    """heads_perbin.npz: OneDeltaPerBinModel / ProbabilisticOneDeltaPerBinModel of the reference
+    (binDeltaModels.py:124-178) on small layer sizes; own seeds, so the other files are untouched.
+    Run with `python tests/golden/make_golden.py perbin`."""
+    install_shims()
+    import binDeltaModels as ref_models
+    ref_models.resnet_model = lambda *a, **k: nn.Identity()
+    torch.manual_seed(11)
+    Cc, Kc, N0, N1, N2, N3, nd, Bh = 3, 4, 64, 40, 24, 12, 3, 10
+    model = ref_models.OneDeltaPerBinModel("resnet", Cc, Kc, N0, N1, N2, N3, nd)
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm1d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.5, 2.0)
+    out = dict(dims=np.array([Cc, Kc, N0, N1, N2, N3, nd, Bh]))
+    for k, v in model.state_dict().items():
+        out["sd0/" + k] = v.clone().numpy()
+    x = torch.randn(Bh, N0)
+    label = torch.randint(0, Cc, (Bh, 1))
+    out.update(x=x.numpy(), label=label.numpy())
+    model.train()
+    xr = x.clone().requires_grad_(True)
+    y1, y2 = model(xr, label)
+    w1, w2 = torch.randn_like(y1), torch.randn_like(y2)
+    (y1 * w1).sum().add((y2 * w2).sum()).backward()
+    out.update(train_y1=y1.detach().numpy(), train_y2=y2.detach().numpy(), w1=w1.numpy(), w2=w2.numpy(),
+               train_gx=xr.grad.numpy())
+    for k, p in model.named_parameters():
+        out["train_grad/" + k] = p.grad.numpy()
+    for k, v in model.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            out["train_sd/" + k] = v.clone().numpy()
+    # the probabilistic model shares the layer structure: same weights, all K deltas of the class
+    prob = ref_models.ProbabilisticOneDeltaPerBinModel("resnet", Cc, Kc, N0, N1, N2, N3, nd)
+    prob.load_state_dict(model.state_dict())
+    prob.eval()
+    model.eval()
+    with torch.no_grad():
+        e1, e2_ = model(x, label)
+        p1, p2 = prob(x, label)
+    out.update(eval_y1=e1.numpy(), eval_y2=e2_.numpy(), prob_y1=p1.numpy(), prob_y2=p2.numpy())
+    np.savez(os.path.join(OUT, "heads_perbin.npz"), **out)
+    print("heads_perbin.npz written")
+
+
 class _PickleDict:
     """Minimal stand-in for the pickled estimator the reference losses load: they only read
     `.cluster_centers_` and `.n_clusters` (binDeltaLosses.py:35-36, 138-139)."""
@@ -268,4 +315,7 @@ class _PickleDict:
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "perbin":
+        main_perbin()
+    else:
+        main()

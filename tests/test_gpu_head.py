@@ -484,3 +484,47 @@ def test_graphed_step_matches_eager(cuda, mode):
                 assert torch.equal(b1, b2), n
     finally:
         head.set_precision("fp32")
+
+
+def test_one_delta_per_bin_models_golden(cuda, golden):
+    """OneDeltaPerBinModel / ProbabilisticOneDeltaPerBinModel (fused 2-layer delta stack) against
+    the reference's outputs, input gradient, parameter gradients and BatchNorm statistics."""
+    import binDeltaModels as M
+    g = golden("heads_perbin")
+    Cc, Kc, N0, N1, N2, N3, nd, Bh = [int(v) for v in g["dims"]]
+    m = M.OneDeltaPerBinModel("none", Cc, Kc, N0, N1, N2, N3, nd)
+    m.feature_model = torch.nn.Identity()
+    _load_sd(m, g)
+    m.cuda().train()
+    x = torch.from_numpy(g["x"]).to(cuda).requires_grad_(True)
+    lab = torch.from_numpy(g["label"]).to(cuda)
+    y1, y2 = m(x, lab)
+    (y1 * torch.from_numpy(g["w1"]).to(cuda)).sum().add((y2 * torch.from_numpy(g["w2"]).to(cuda)).sum()).backward()
+    scale_close(y1, torch.from_numpy(g["train_y1"]), FP32_TOL, "perbin y1")
+    scale_close(y2, torch.from_numpy(g["train_y2"]), FP32_TOL, "perbin y2")
+    scale_close(x.grad, torch.from_numpy(g["train_gx"]), GRAD_TOL, "perbin dx")
+    for n, p in m.named_parameters():
+        ref = torch.from_numpy(g["train_grad/" + n])
+        assert p.grad is not None, n
+        scale_close(p.grad, ref, GRAD_TOL, "perbin grad " + n)
+    sd = m.state_dict()
+    for k in g.files:
+        if k.startswith("train_sd/"):
+            name = k[len("train_sd/"):]
+            if "num_batches" in name:
+                assert int(sd[name]) == int(g[k]), name
+            else:
+                scale_close(sd[name], torch.from_numpy(g[k]), FP32_TOL, name)
+    # eval mode + the probabilistic variant (all K deltas of the class) on the same weights
+    p = M.ProbabilisticOneDeltaPerBinModel("none", Cc, Kc, N0, N1, N2, N3, nd)
+    p.feature_model = torch.nn.Identity()
+    _load_sd(p, g)
+    # the reference's probabilistic model was given the weights AFTER the train-mode forward above
+    p.load_state_dict({k[len("train_sd/"):]: torch.from_numpy(g[k]) for k in g.files
+                       if k.startswith("train_sd/")}, strict=False)
+    p.cuda().eval()
+    with torch.no_grad():
+        p1, p2 = p(x.detach(), lab)
+    scale_close(p1, torch.from_numpy(g["prob_y1"]), FP32_TOL, "prob y1")
+    scale_close(p2, torch.from_numpy(g["prob_y2"]), FP32_TOL, "prob y2")
+    assert p2.shape == (Bh, Kc, nd)

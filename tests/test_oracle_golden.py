@@ -146,3 +146,29 @@ def test_heads(golden):
         e1, e2 = m(x, label)
     np.testing.assert_allclose(e1.numpy(), g["eval_y1"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(e2.numpy(), g["eval_y2"], rtol=1e-5, atol=1e-6)
+
+
+def test_per_bin_delta_heads_oracle_vs_reference(golden):
+    """oracle.OneDeltaPerBinHeads reproduces the reference's OneDeltaPerBinModel /
+    ProbabilisticOneDeltaPerBinModel (binDeltaModels.py:124-178) from heads_perbin.npz."""
+    import torch
+    import bdpose_oracle as O
+    g = golden("heads_perbin")
+    Cc, Kc, N0, N1, N2, N3, nd, Bh = [int(v) for v in g["dims"]]
+    m = O.OneDeltaPerBinHeads(Cc, Kc, N0, N1, N2, N3, nd)
+    m.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd0/")})
+    x, lab = torch.from_numpy(g["x"]), torch.from_numpy(g["label"])
+    m.train()
+    xr = x.clone().requires_grad_(True)
+    y1, y2 = m(xr, lab)
+    (y1 * torch.from_numpy(g["w1"])).sum().add((y2 * torch.from_numpy(g["w2"])).sum()).backward()
+    assert torch.allclose(y1, torch.from_numpy(g["train_y1"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(y2, torch.from_numpy(g["train_y2"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(xr.grad, torch.from_numpy(g["train_gx"]), rtol=1e-4, atol=1e-6)
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(x, lab)
+        p1, p2 = m(x, lab, probabilistic=True)
+    assert torch.allclose(e2, torch.from_numpy(g["eval_y2"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(p2, torch.from_numpy(g["prob_y2"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(p1, torch.from_numpy(g["prob_y1"]), rtol=1e-5, atol=1e-6)
