@@ -138,26 +138,60 @@ def bd_loss(logits, bin_true, pred, target, keys=None, pose_mode=L.POSE_NONE, us
 
 
 class _PoseLossRows(torch.autograd.Function):
-    """reduce=False pose loss: per-sample values, per-sample upstream gradients."""
+    """reduce=False pose loss: per-sample values, per-sample upstream gradients.  The gradient w.r.t.
+    the SECOND argument is produced too when it is asked for: the soft-bin losses call
+    `my_loss(ydata, centers[k] + residual)` with the prediction in the `ytrue` slot
+    (binDeltaLosses.py:120, 143, 164)."""
 
     @staticmethod
     def forward(ctx, pred, target, pose_mode):
         r = bd_loss_raw(None, None, pred, target, None, pose_mode, False,
                         want_grad=pred.requires_grad, per_sample=True)
-        ctx.save_for_backward(r["grad_pred"])
-        ctx.shape = pred.shape
+        g_target = None
+        if target.requires_grad:
+            if pose_mode == L.POSE_GEODESIC_AA:
+                # the axis-angle geodesic distance is symmetric in its arguments (both are normalised,
+                # axisAngle.py:110-120): d/d target = d/d pred of the swapped call
+                g_target = bd_loss_raw(None, None, target, pred, None, pose_mode, False,
+                                       want_grad=True, per_sample=True)["grad_pred"]
+            else:
+                raise RuntimeError("pose loss: gradient w.r.t. the second argument is only fused for "
+                                   "the axis-angle geodesic loss")
+        ctx.save_for_backward(r["grad_pred"], g_target)
+        ctx.shapes = (pred.shape, target.shape)
         return r["row_pose"]
 
     @staticmethod
     def backward(ctx, g_rows):
-        (g_pred,) = ctx.saved_tensors
-        if g_pred is None:
-            return None, None, None
-        return (g_pred * g_rows.reshape(-1, 1)).reshape(ctx.shape), None, None
+        g_pred, g_target = ctx.saved_tensors
+        gp = gt = None
+        if g_pred is not None and ctx.needs_input_grad[0]:
+            gp = (g_pred * g_rows.reshape(-1, 1)).reshape(ctx.shapes[0])
+        if g_target is not None and ctx.needs_input_grad[1]:
+            gt = (g_target * g_rows.reshape(-1, 1)).reshape(ctx.shapes[1])
+        return gp, gt, None
+
+
+def _quat_geodesic_torch(pred, target, reduce):
+    """quaternion.geodesic_loss (quaternion.py:156-163) in torch ops: used when the gradient has to
+    reach the un-normalised second argument (the loss is not symmetric in its arguments)."""
+    qh = torch.nn.functional.normalize(pred.float(), dim=1)
+    w = torch.sum(target.float() * qh, dim=1)
+    theta = 2.0 * torch.acos(torch.clamp(torch.abs(w), -1.0 + 1e-6, 1.0 - 1e-6))
+    return theta.mean() if reduce else theta
 
 
 def pose_loss(pred, target, pose_mode, reduce=True):
     """Stand-alone pose loss (axisAngle.geodesic_loss, quaternion.geodesic_loss, rotmat my_loss)."""
+    two_sided = torch.is_grad_enabled() and isinstance(target, torch.Tensor) and target.requires_grad
+    if two_sided:
+        if pose_mode == L.POSE_GEODESIC_Q:
+            return _quat_geodesic_torch(pred, target, reduce)
+        if pose_mode == L.POSE_GEODESIC_AA:
+            rows = _PoseLossRows.apply(pred, target, pose_mode)
+            return rows.mean() if reduce else rows
+        raise RuntimeError("pose loss: the second argument requires a gradient, which mode %d does "
+                           "not provide" % pose_mode)
     if reduce:
         return _BDLoss.apply(None, pred, None, target, None, pose_mode, False)[1]
     return _PoseLossRows.apply(pred, target, pose_mode)

@@ -305,6 +305,52 @@ def main_perbin():
     print("heads_perbin.npz written")
 
 
+def main_problosses():
+    """losses_prob.npz: the soft-bin loss family of the reference (binDeltaLosses.py:109-208) with
+    my_loss = geodesic_loss(reduce=False): values and gradients w.r.t. score and residual.
+    Run with `python tests/golden/make_golden.py problosses`."""
+    install_shims()
+    import axisAngle as ref_aa
+    import quaternion as ref_q
+    import binDeltaLosses as ref_losses
+    rng = np.random.default_rng(21)
+    torch.manual_seed(21)
+    B, K = 14, 6
+    centers = rand_rotations(rng, K)[0]
+    tmp = tempfile.mkdtemp()
+    kfile = os.path.join(tmp, "k.pkl")
+    with open(kfile, "wb") as f:
+        pickle.dump(_PickleDict(centers), f)
+    ydata, ydata_q = rand_rotations(rng, B)
+    out = dict(centers=centers, ydata=ydata.astype(np.float32), ydata_q=ydata_q.astype(np.float32))
+    score = torch.randn(B, K)
+    res = 0.2 * torch.randn(B, 3)
+    res_k = 0.2 * torch.randn(B, K, 3)
+    res_q = 0.2 * torch.randn(B, 4)
+    bins = torch.randint(0, K, (B,))
+    prob = torch.softmax(torch.randn(B, K), 1)
+    out.update(score=score.numpy(), res=res.numpy(), res_k=res_k.numpy(), res_q=res_q.numpy(),
+               bins=bins.numpy(), prob=prob.numpy())
+    yt = torch.from_numpy(out["ydata"])
+    ytq = torch.from_numpy(out["ydata_q"])
+    cases = {
+        "prob": (ref_losses.ProbabilisticLoss(0.7, kfile, ref_aa.geodesic_loss(reduce=False)), res, bins, yt),
+        "prob_multires": (ref_losses.ProbabilisticMultiresLoss(0.7, kfile, ref_aa.geodesic_loss(reduce=False)), res_k, bins, yt),
+        "relaxed_q": (ref_losses.RelaXedProbabilisticLossQ(0.7, kfile, ref_q.geodesic_loss(reduce=False)), res_q, prob, ytq),
+        "m3_geo": (ref_losses.loss_m3(0.7, kfile, ref_aa.geodesic_loss(reduce=False)), res, prob, yt),
+    }
+    for name, (crit, r, t0, t1) in cases.items():
+        s_ = score.clone().requires_grad_(True)
+        r_ = r.clone().requires_grad_(True)
+        loss = crit([s_, r_], [t0, t1])
+        loss.backward()
+        out[name + "/loss"] = loss.detach().numpy()
+        out[name + "/g_score"] = s_.grad.numpy()
+        out[name + "/g_res"] = r_.grad.numpy()
+    np.savez(os.path.join(OUT, "losses_prob.npz"), **out)
+    print("losses_prob.npz written")
+
+
 class _PickleDict:
     """Minimal stand-in for the pickled estimator the reference losses load: they only read
     `.cluster_centers_` and `.n_clusters` (binDeltaLosses.py:35-36, 138-139)."""
@@ -317,5 +363,7 @@ class _PickleDict:
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "perbin":
         main_perbin()
+    elif len(sys.argv) > 1 and sys.argv[1] == "problosses":
+        main_problosses()
     else:
         main()

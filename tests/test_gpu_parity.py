@@ -506,3 +506,38 @@ def test_kmeans_plusplus_fit_runs_and_improves(cuda):
     close(float(sq.sum()), km.inertia_, rtol=1e-9)
     assert km.inertia_ <= base.inertia_ * 1.05
     assert np.array_equal(km.predict(X[:1000].astype(np.float32)), km.labels_[:1000])
+
+
+def test_soft_bin_losses_golden(cuda, golden, tmp_path):
+    """The soft-bin loss family (binDeltaLosses.py:109-208, 300-320) against the
+    reference's own outputs: value and gradients w.r.t. score and residual.  These losses call
+    `my_loss(ydata, centers[k] + residual)` with the prediction in the SECOND slot, so the pose
+    loss has to propagate the gradient to its second argument."""
+    import axisAngle
+    import quaternion
+    import binDeltaLosses as BL
+    g = golden("losses_prob")
+    kfile = tmp_path / "k.pkl"
+
+    from bdpose.kmeans import KMeans
+    km = KMeans(n_clusters=int(g["centers"].shape[0]))
+    km.cluster_centers_ = np.asarray(g["centers"])
+    with open(kfile, "wb") as f:
+        pickle.dump(km, f)
+    t = lambda a: torch.from_numpy(np.asarray(a)).to(cuda)
+    cases = {
+        "prob": (lambda: BL.ProbabilisticLoss(0.7, str(kfile), axisAngle.geodesic_loss(reduce=False)), "res", "bins", "ydata"),
+        "prob_multires": (lambda: BL.ProbabilisticMultiresLoss(0.7, str(kfile), axisAngle.geodesic_loss(reduce=False)), "res_k", "bins", "ydata"),
+        "relaxed_q": (lambda: BL.RelaXedProbabilisticLossQ(0.7, str(kfile), quaternion.geodesic_loss(reduce=False)), "res_q", "prob", "ydata_q"),
+        "m3_geo": (lambda: BL.loss_m3(0.7, str(kfile), axisAngle.geodesic_loss(reduce=False)), "res", "prob", "ydata"),
+    }
+    for name, (make, rk, tk, yk) in cases.items():
+        crit = make()
+        s_ = t(g["score"]).requires_grad_(True)
+        r_ = t(g[rk]).requires_grad_(True)
+        loss = crit([s_, r_], [t(g[tk]), t(g[yk])])
+        loss.backward()
+        close(loss, g[name + "/loss"], rtol=1e-5, msg=name + " loss")
+        ref_s, ref_r = g[name + "/g_score"], g[name + "/g_res"]
+        close(s_.grad, ref_s, rtol=0, atol=1e-5 * float(np.abs(ref_s).max()), msg=name + " g_score")
+        close(r_.grad, ref_r, rtol=0, atol=1e-5 * float(np.abs(ref_r).max()), msg=name + " g_res")
