@@ -115,6 +115,20 @@ int bdp_error_stats(const double* err_deg, const int64_t* labels, int64_t N, int
                     double* median, int64_t* count, int64_t* below30, double* max_err,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Expected pose loss of the soft-bin losses (binDeltaLosses.py:119-123, 141-146, 162-167, 176-180,
+ * 311-316, 327-333; the reference loops over the K bins in python):
+ *   rows[b] = sum_k softmax(logits[b])_k * L(target[b], keys[k] + delta[b(,k)])
+ * L = axis-angle geodesic (pose_mode BDP_POSE_GEODESIC_AA, ndim 3) or the quaternion geodesic with
+ * the prediction in the un-normalised `ytrue` slot (BDP_POSE_GEODESIC_Q, ndim 4), as the reference
+ * calls my_loss(ydata, pose).  delta [B, ndim] (per_bin = 0) or [B, K, ndim] (per_bin = 1).
+ * grad_logits [B, K] = d rows[b] / d logits, grad_delta (shape of delta) = d rows[b] / d delta.
+ */
+int bdp_expected_pose_loss(const float* logits, int64_t B, int64_t K, int64_t ld_logits,
+                           const float* delta, int per_bin, int ndim, const float* keys,
+                           const float* target, int pose_mode, float* rows, float* grad_logits,
+                           float* grad_delta, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (c) nearest-dictionary-key assignment + residual, and the k-means Lloyd step.
  *   kmeans.predict + residual        binDeltaGenerators.py:27-30, 78-82 (quaternion keys: 67)

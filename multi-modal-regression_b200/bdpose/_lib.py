@@ -31,6 +31,8 @@ SIGNATURES = {
     "bdp_bd_loss_workspace_bytes": (_i64, [_i64]),
     "bdp_bd_loss_fwd_bwd": (_int, [_p, _i64, _i64, _i64, _p, _p, _int, _p, _int, _p, _int, _p, _p,
                                    _p, _p, _p, _f32, _p, _p, _i64, _p]),
+    "bdp_expected_pose_loss": (_int, [_p, _i64, _i64, _i64, _p, _int, _int, _p, _p, _int, _p, _p, _p,
+                                      _p]),
     "bdp_geodesic_error_deg": (_int, [_p, _p, _int, _int, _i64, _p, _p]),
     "bdp_error_stats_workspace_bytes": (_i64, [_i64, _int]),
     "bdp_error_stats": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p, _p, _i64, _p]),

@@ -197,6 +197,49 @@ def pose_loss(pred, target, pose_mode, reduce=True):
     return _PoseLossRows.apply(pred, target, pose_mode)
 
 
+class _ExpectedPose(torch.autograd.Function):
+    """rows[b] = sum_k softmax(score_b)_k * L(target_b, keys_k + delta_b[k]) in one launch."""
+
+    @staticmethod
+    def forward(ctx, score, delta, target, keys, pose_mode, per_bin):
+        B, K = score.shape
+        nd = keys.shape[1]
+        score_c = score.detach().float().contiguous()
+        delta_c = delta.detach().float().contiguous()
+        rows = torch.empty(B, dtype=torch.float32, device=score.device)
+        g_s = torch.empty((B, K), dtype=torch.float32, device=score.device)
+        g_d = torch.empty_like(delta_c)
+        with torch.cuda.device(score.device):
+            st = L.lib().bdp_expected_pose_loss(
+                L.ptr(score_c), B, K, K, L.ptr(delta_c), 1 if per_bin else 0, nd, L.ptr(keys),
+                L.ptr(target), pose_mode, L.ptr(rows), L.ptr(g_s), L.ptr(g_d), L.stream_ptr())
+        L.check(st, "bdp_expected_pose_loss")
+        ctx.save_for_backward(g_s, g_d)
+        ctx.dshape = delta.shape
+        return rows
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        g_s, g_d = ctx.saved_tensors
+        gs = g_s * g_rows.reshape(-1, 1) if ctx.needs_input_grad[0] else None
+        gd = None
+        if ctx.needs_input_grad[1]:
+            shape = [-1] + [1] * (g_d.dim() - 1)
+            gd = (g_d * g_rows.reshape(shape)).reshape(ctx.dshape)
+        return gs, gd, None, None, None, None
+
+
+def expected_pose_loss(score, delta, target, keys, pose_mode):
+    """Per-row expectation of the pose loss over the bins (soft-bin losses).  score [B,K],
+    delta [B,nd] or [B,K,nd], target [B,nd], keys [K,nd]; returns [B] with autograd to score, delta."""
+    _need_cuda(score, delta, target, keys)
+    K = score.shape[1]
+    keys = keys.detach().float().reshape(K, -1).contiguous()
+    target = target.detach().float().reshape(score.shape[0], -1).contiguous()
+    per_bin = delta.dim() == 3
+    return _ExpectedPose.apply(score, delta, target, keys, pose_mode, per_bin)
+
+
 # ------------------------------------------------------------------------------------------------
 # (d) evaluation
 # ------------------------------------------------------------------------------------------------

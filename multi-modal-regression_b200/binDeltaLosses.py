@@ -128,6 +128,10 @@ class RiemannianLoss(nn.Module):
 
 
 # ---- soft-bin families ------------------------------------------------------------
+# True: the expectation over the bins runs as one fused launch (bdp_expected_pose_loss); False: the
+# reference's loop over the K bins on the per-row pose-loss kernel (kept for foreign my_loss callables)
+FUSE_EXPECTED_POSE = True
+
 
 def _kl(logits, soft_bins):
     # nn.KLDivLoss() default reduction ('mean' over all elements), as the reference constructs it
@@ -195,6 +199,12 @@ class _ProbBase(nn.Module):
     def forward(self, ypred, ytrue):
         score, res = ypred[0], ypred[1]
         l1 = _kl(score, ytrue[0]) if self.use_kl else F.cross_entropy(score, ytrue[0])
+        mode = _pose_mode_of(self.my_loss, res.shape[-1])
+        if FUSE_EXPECTED_POSE and mode in (L.POSE_GEODESIC_AA, L.POSE_GEODESIC_Q) and \
+                not getattr(self.my_loss, 'reduce', True) and score.is_cuda and not ytrue[1].requires_grad:
+            # one fused launch instead of the reference's python loop over the K bins
+            rows = ops.expected_pose_loss(score, res, ytrue[1], self.cluster_centers, mode)
+            return l1 + self.alpha * rows.mean()
         if self.per_bin_delta:       # residual is [B, K, ndim]: one delta per bin (Multires)
             y = self.cluster_centers + res
             l2 = _expected_pose_loss(score, self.my_loss, ytrue[1], lambda k: y[:, k])

@@ -473,6 +473,80 @@ __global__ void __launch_bounds__(128, 5) bd_loss_kernel(const LossParams P) {
   }
 }
 
+// ---- expected pose loss of the soft-bin family -------------------------------
+// E_b = sum_k softmax(score_b)_k * L(ydata_b, key_k + delta_b[k])      binDeltaLosses.py:119-123,
+// 141-146, 162-167, 176-180, 311-316, 327-333: the reference loops over the K bins in python (K pose-loss
+// launches forward, K backward); here one warp owns a row and its lanes the bins.  L is the
+// axis-angle geodesic distance (symmetric in its arguments) or the quaternion one with the prediction
+// in the un-normalised `ytrue` slot, as the reference calls it.
+//   dE/dscore_j = p_j (L_j - E),   dE/ddelta = sum_k p_k dL_k/dpose  (shared delta)  |  p_k dL_k/dpose (per bin)
+__device__ __forceinline__ double quat_second_arg(const double pose[4], const double t[4], double g[4]) {
+  // quaternion.py:156-163 with ypred = t (normalised), ytrue = pose (as is)
+  const double n = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3]);
+  const double in = 1.0 / fmax(n, BDP_NORM_EPS_D);
+  const double th[4] = {t[0] * in, t[1] * in, t[2] * in, t[3] * in};
+  const double w = pose[0] * th[0] + pose[1] * th[1] + pose[2] * th[2] + pose[3] * th[3];
+  const double c = fabs(w);
+  const double theta = 2.0 * acos(fmin(c, 1.0 - BDP_EPS_D));
+  double dth_dw = 0.0;
+  if (c <= 1.0 - BDP_EPS_D && w != 0.0) dth_dw = (w > 0.0 ? -2.0 : 2.0) / sqrt(1.0 - c * c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = dth_dw * th[i];
+  return theta;
+}
+
+struct ExpParams {
+  const float* logits; int64_t B, K, ld;
+  const float* delta; int per_bin; int nd;
+  const float* keys; const float* target; int mode;
+  float* rows; float* g_logits; float* g_delta;
+};
+
+__global__ void __launch_bounds__(128) expected_pose_kernel(const ExpParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= P.B) return;
+  const float* s = P.logits + row * P.ld;
+  const int K = (int)P.K, nd = P.nd;
+  float m = -INFINITY;
+  for (int k = lane; k < K; k += 32) m = fmaxf(m, s[k]);
+  m = warp_max(m);
+  float z = 0.f;
+  for (int k = lane; k < K; k += 32) z += expf(s[k] - m);
+  z = warp_sum(z);
+  const float iz = 1.f / z;
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < nd; ++i) t[i] = (double)__ldg(P.target + row * nd + i);
+  double e_acc = 0.0, gs[4] = {0.0, 0.0, 0.0, 0.0};
+  float* gl = P.g_logits + row * K;                   // holds L_k between the two passes
+  for (int k = lane; k < K; k += 32) {
+    const float* d = P.per_bin ? P.delta + (row * K + k) * nd : P.delta + row * nd;
+    double pose[4] = {0.0, 0.0, 0.0, 0.0}, g[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < nd; ++i) pose[i] = (double)__fadd_rn(__ldg(d + i), __ldg(P.keys + (int64_t)k * nd + i));
+    const double Lk = P.mode == BDP_POSE_GEODESIC_AA ? pose_geodesic_aa(pose, t, g) : quat_second_arg(pose, t, g);
+    const double p = (double)(expf(s[k] - m) * iz);
+    e_acc += p * Lk;
+    gl[k] = (float)Lk;
+    if (P.per_bin) {
+      float* gd = P.g_delta + (row * K + k) * nd;
+      for (int i = 0; i < nd; ++i) gd[i] = (float)(p * g[i]);
+    } else {
+      for (int i = 0; i < nd; ++i) gs[i] += p * g[i];
+    }
+  }
+  e_acc = warp_sum(e_acc);
+  if (!P.per_bin) {
+    for (int i = 0; i < nd; ++i) gs[i] = warp_sum(gs[i]);
+    if (lane == 0) for (int i = 0; i < nd; ++i) P.g_delta[row * nd + i] = (float)gs[i];
+  }
+  if (lane == 0) P.rows[row] = (float)e_acc;
+  __syncwarp();
+  for (int k = lane; k < K; k += 32) {
+    const float p = expf(s[k] - m) * iz;
+    gl[k] = p * (gl[k] - (float)e_acc);
+  }
+}
+
 constexpr int kLossThreads = 128;
 constexpr int kLossMaxBlocks = 148 * 16;
 
@@ -560,5 +634,25 @@ extern "C" int bdp_bd_loss_fwd_bwd(const float* logits, int64_t B, int64_t K, in
     bd_loss_kernel<8><<<(unsigned)blocks, kLossThreads, 0, st>>>(P);
   }
   BDP_CUDA_CHECK_LAUNCH("bd_loss_kernel");
+  return BDP_OK;
+}
+
+extern "C" int bdp_expected_pose_loss(const float* logits, int64_t B, int64_t K, int64_t ld_logits,
+                                      const float* delta, int per_bin, int ndim, const float* keys,
+                                      const float* target, int pose_mode, float* rows,
+                                      float* grad_logits, float* grad_delta, void* stream) {
+  BDP_REQUIRE(B > 0 && K > 0 && ld_logits >= K, "expected_pose_loss: bad sizes");
+  BDP_REQUIRE(logits && delta && keys && target && rows && grad_logits && grad_delta,
+              "expected_pose_loss: NULL buffer");
+  BDP_REQUIRE((pose_mode == BDP_POSE_GEODESIC_AA && ndim == 3) ||
+                  (pose_mode == BDP_POSE_GEODESIC_Q && ndim == 4),
+              "expected_pose_loss: axis-angle (ndim 3) or quaternion (ndim 4) geodesic loss only");
+  ExpParams P;
+  P.logits = logits; P.B = B; P.K = K; P.ld = ld_logits; P.delta = delta; P.per_bin = per_bin ? 1 : 0;
+  P.nd = ndim; P.keys = keys; P.target = target; P.mode = pose_mode; P.rows = rows;
+  P.g_logits = grad_logits; P.g_delta = grad_delta;
+  const unsigned blocks = (unsigned)((B + 3) / 4);
+  expected_pose_kernel<<<blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+  BDP_CUDA_CHECK_LAUNCH("expected_pose_kernel");
   return BDP_OK;
 }

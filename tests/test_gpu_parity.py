@@ -531,13 +531,17 @@ def test_soft_bin_losses_golden(cuda, golden, tmp_path):
         "relaxed_q": (lambda: BL.RelaXedProbabilisticLossQ(0.7, str(kfile), quaternion.geodesic_loss(reduce=False)), "res_q", "prob", "ydata_q"),
         "m3_geo": (lambda: BL.loss_m3(0.7, str(kfile), axisAngle.geodesic_loss(reduce=False)), "res", "prob", "ydata"),
     }
-    for name, (make, rk, tk, yk) in cases.items():
-        crit = make()
-        s_ = t(g["score"]).requires_grad_(True)
-        r_ = t(g[rk]).requires_grad_(True)
-        loss = crit([s_, r_], [t(g[tk]), t(g[yk])])
-        loss.backward()
-        close(loss, g[name + "/loss"], rtol=1e-5, msg=name + " loss")
-        ref_s, ref_r = g[name + "/g_score"], g[name + "/g_res"]
-        close(s_.grad, ref_s, rtol=0, atol=1e-5 * float(np.abs(ref_s).max()), msg=name + " g_score")
-        close(r_.grad, ref_r, rtol=0, atol=1e-5 * float(np.abs(ref_r).max()), msg=name + " g_res")
+    for fused in (True, False):
+        BL.FUSE_EXPECTED_POSE = fused          # one fused launch / the reference's loop over bins
+        for name, (make, rk, tk, yk) in cases.items():
+            crit = make()
+            s_ = t(g["score"]).requires_grad_(True)
+            r_ = t(g[rk]).requires_grad_(True)
+            loss = crit([s_, r_], [t(g[tk]), t(g[yk])])
+            loss.backward()
+            tag = name + (" fused" if fused else " loop")
+            close(loss, g[name + "/loss"], rtol=1e-5, msg=tag + " loss")
+            ref_s, ref_r = g[name + "/g_score"], g[name + "/g_res"]
+            close(s_.grad, ref_s, rtol=0, atol=1e-5 * float(np.abs(ref_s).max()), msg=tag + " g_score")
+            close(r_.grad, ref_r, rtol=0, atol=1e-5 * float(np.abs(ref_r).max()), msg=tag + " g_res")
+    BL.FUSE_EXPECTED_POSE = True
