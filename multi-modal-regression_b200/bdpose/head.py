@@ -456,6 +456,182 @@ class _HeadFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# dense outputs of every head (scripts that loop `bin_models[i](x)` themselves)
+# ------------------------------------------------------------------------------------------------
+class _HeadAllFn(torch.autograd.Function):
+    """(Y_0 [B, Hg, O_0], Y_1 [B, Hg, O_1], ...) = the UNMIXED outputs of every head of a HeadStack
+    on x.  fc1 / fc2 run as the stacked tcgen05 GEMMs, BatchNorm through bn_relu, the output layers as
+    one batched matmul per fc3 group."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, stack, training):
+        buf = stack.ensure()
+        w1, w2 = buf["w1"], buf["w2"]
+        H, N1, N0 = w1.shape
+        N2 = w2.shape[1]
+        B = x.shape[0]
+        F1, F2 = H * N1, H * N2
+        if x.dim() != 2 or x.shape[1] != N0:
+            raise RuntimeError("head: input has %s features, fc1 expects %d" % (tuple(x.shape[1:]), N0))
+        if training and B < 2:
+            raise ValueError("Expected more than 1 value per channel when training, got input size "
+                             "[%d, %d]" % (B, N1))
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        dev = x.device
+        h1 = torch.empty((B, F1), dtype=torch.float32, device=dev)
+        gemm_tf32(x, 0, N0, 0, w1, 0, N0, 0, h1, 0, F1, 0, B, F1, N0)
+        a1, m1, is1 = bn_relu_fwd(h1, buf["g1"].view(-1), buf["be1"].view(-1), buf["rm1"].view(-1),
+                                  buf["rv1"].view(-1), training)
+        h2 = torch.empty((B, F2), dtype=torch.float32, device=dev)
+        gemm_tf32(a1, 0, F1, N1, w2, 0, N1, N2 * N1, h2, 0, F2, N2, B, N2, N1, G=H)
+        a2, m2, is2 = bn_relu_fwd(h2, buf["g2"].view(-1), buf["be2"].view(-1), buf["rm2"].view(-1),
+                                  buf["rv2"].view(-1), training)
+        if training:
+            buf["nb1"] += 1
+            buf["nb2"] += 1
+        else:
+            m1, is1 = buf["rm1"].view(-1).clone(), torch.rsqrt(buf["rv1"].view(-1) + BN_EPS)
+            m2, is2 = buf["rm2"].view(-1).clone(), torch.rsqrt(buf["rv2"].view(-1) + BN_EPS)
+        a2h = a2.view(B, H, N2).transpose(0, 1)                          # [H, B, N2]
+        ys, off = [], 0
+        for w3, b3 in zip(buf["w3"], buf["b3"]):
+            Hg = w3.shape[0]
+            y = torch.baddbmm(b3.unsqueeze(1), a2h[off:off + Hg], w3.transpose(1, 2))   # [Hg, B, O]
+            ys.append(y.transpose(0, 1).contiguous())
+            off += Hg
+        ctx.stack, ctx.training = stack, training
+        ctx.saved = (x, h1, a1, m1, is1, h2, a2, m2, is2)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        stack = ctx.stack
+        buf = stack.buf
+        x, h1, a1, m1, is1, h2, a2, m2, is2 = ctx.saved
+        w1, w2 = buf["w1"], buf["w2"]
+        H, N1, N0 = w1.shape
+        N2 = w2.shape[1]
+        B = x.shape[0]
+        F1, F2 = H * N1, H * N2
+        dev = x.device
+        training = ctx.training
+        a2h = a2.view(B, H, N2).transpose(0, 1)
+        grads = {}
+        da2h = torch.empty((H, B, N2), dtype=torch.float32, device=dev)
+        off = 0
+        for gi, (w3, b3) in enumerate(zip(buf["w3"], buf["b3"])):
+            Hg, O = w3.shape[0], w3.shape[1]
+            dy = dys[gi]
+            dy = torch.zeros((B, Hg, O), device=dev) if dy is None else dy.float()
+            dyh = dy.transpose(0, 1).contiguous()                                  # [Hg, B, O]
+            grads["w3_%d" % gi] = torch.bmm(dyh.transpose(1, 2), a2h[off:off + Hg])
+            grads["b3_%d" % gi] = dyh.sum(1)
+            torch.bmm(dyh, w3, out=da2h[off:off + Hg])
+            off += Hg
+        da2 = da2h.transpose(0, 1).reshape(B, F2).contiguous()
+        dh2, dg2, dbe2 = bn_relu_bwd(da2, a2, h2, buf["g2"].view(-1), m2, is2, training)
+        dw2 = torch.empty_like(w2)
+        gemm_tf32(dh2, 1, F2, N2, a1, 1, F1, N1, dw2, 0, N1, N2 * N1, N2, N1, B, G=H)
+        da1 = torch.empty_like(a1)
+        gemm_tf32(dh2, 0, F2, N2, w2, 1, N1, N2 * N1, da1, 0, F1, N1, B, N1, N2, G=H)
+        dh1, dg1, dbe1 = bn_relu_bwd(da1, a1, h1, buf["g1"].view(-1), m1, is1, training)
+        dw1 = torch.empty_like(w1)
+        gemm_tf32(dh1, 1, F1, 0, x, 1, N0, 0, dw1, 0, N0, 0, F1, N0, B)
+        grads.update(w1=dw1, g1=dg1.view(H, N1), be1=dbe1.view(H, N1), w2=dw2, g2=dg2.view(H, N2),
+                     be2=dbe2.view(H, N2))
+        if stack.grads_are_fresh():
+            gb = stack.grad_buffers()
+            for k in gb:
+                gb[k].copy_(grads[k])
+            stack.publish()
+        else:
+            stack.accumulate(grads)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            n_tiles = (N0 + 255) // 256
+            splits = gemm_splits(F1, max(1, min(64, L.lib().bdp_sm_count() // n_tiles)))
+            parts = torch.empty((splits, B, N0), dtype=torch.float32, device=dev)
+            gemm_tf32(dh1, 0, F1, 0, w1, 1, N0, 0, parts, 0, N0, 0, B, N0, F1, splits=splits, c_ss=B * N0)
+            dx = torch.empty((B, N0), dtype=torch.float32, device=dev)
+            sum_slabs(parts, B * N0, splits, B * N0, dx)
+        return dx, None, None, None
+
+
+def run_heads_all(stack, x, training):
+    """Unmixed outputs of every head: one [B, Hg, O_g] tensor per fc3 group."""
+    stack.ensure()
+    return _HeadAllFn.apply(x, stack.anchor, stack, training)
+
+
+MEMO = os.environ.get("BDPOSE_HEAD_MEMO", "1") != "0"
+
+
+class HeadFamily:
+    """The sibling heads of one model (OneBinDeltaModel: bin_models + res_models).  Scripts that define
+    their own forward call `self.bin_models[i](x)` head by head with the same x
+    (learnJointCatPoseModel_weighted.py:112-113, evaluateJointModel.py:86-96): the first such call
+    runs ALL heads fused (`run_heads_all`) and the siblings' calls return their slices, which is the
+    same work the reference does in its loop — every head sees every sample — in 1/24 of the launches.
+    A result is reused only for the same input tensor (object, version, storage) and mode; parameter
+    versions are re-checked at the start of every round (head 0, or a head asked twice).  BDPOSE_HEAD_MEMO=0 turns this off (every call then runs as a one-head
+    stack)."""
+
+    def __init__(self, lists):
+        self.lists = lists                 # the nn.ModuleLists, in fc3-group order
+        self._stack = None
+        self._key = None
+        self._x_ref = None
+        self._outs = None
+        self._pver = None
+        self._served = set()
+
+    def __deepcopy__(self, memo):
+        import copy
+        return HeadFamily([copy.deepcopy(l, memo) for l in self.lists])
+
+    def __reduce__(self):
+        return (HeadFamily, (self.lists,))
+
+    def stack(self):
+        groups = [list(l) for l in self.lists]
+        st = self._stack
+        flat = [m for g in groups for m in g]
+        if st is None or len(st.heads) != len(flat) or any(a is not b for a, b in zip(st.heads, flat)):
+            st = HeadStack(groups)
+            self._stack = st
+            self._key = None
+        return st
+
+    def _param_versions(self, st):
+        return tuple(p._version for plist in st.plists.values() for p in plist)
+
+    def output_of(self, module, x, training):
+        st = self.stack()
+        st.ensure()
+        key = (id(x), x._version, x.data_ptr(), tuple(x.shape), bool(training), torch.is_grad_enabled(),
+               x.requires_grad)
+        fresh = key != self._key or self._x_ref is not x
+        if not fresh and (id(module) in self._served or module is st.heads[0]):
+            # a head asked twice for the same input, or a new round of the script's loop starting at
+            # head 0: make sure no parameter was updated in place since the cached run (the
+            # Parameters' version counters: 8 per head, read once per round)
+            fresh = self._param_versions(st) != self._pver
+        if fresh:
+            self._outs = run_heads_all(st, x, training)
+            self._key, self._x_ref = key, x
+            self._pver = self._param_versions(st)
+            self._served = set()
+        self._served.add(id(module))
+        for gi, g in enumerate(st.groups):
+            for j, m in enumerate(g):
+                if m is module:
+                    return self._outs[gi][:, j, :]
+        raise RuntimeError("head is not a member of its family")
+
+
+# ------------------------------------------------------------------------------------------------
 # stacks of two-layer heads (one delta per bin: SURVEY §8(f)-1)
 # ------------------------------------------------------------------------------------------------
 class Mlp2Stack:
@@ -645,12 +821,15 @@ def allreduce_stack_grads(stack, group=None, average=True):
 
 def sync_head_gradients(model, group=None):
     """All-reduce(mean) the head gradients of every fused stack found under `model` (the
-    OneBinDeltaModel-style containers keep theirs in `_stack`)."""
+    containers keep theirs in `_stack` / `_stack2`, sibling heads in their `_family`)."""
     seen = set()
     for m in model.modules():
-        for name in ("_stack", "_solo"):
-            st = m.__dict__.get(name)
-            if st is not None and id(st) not in seen and st.grad is not None:
+        cands = [m.__dict__.get(name) for name in ("_stack", "_solo", "_stack2")]
+        fam = m.__dict__.get("_family")
+        if fam is not None:
+            cands.append(fam._stack)
+        for st in cands:
+            if st is not None and id(st) not in seen and getattr(st, "grad", None) is not None:
                 seen.add(id(st))
                 allreduce_stack_grads(st, group)
 
@@ -774,6 +953,37 @@ def bench(dev, peaks):
                 "samples_per_s_fwd_bwd": B / (ms * 1e-3), "ms_fwd_bwd": ms,
                 "fwd_bwd_hbm_frac": 3 * n_params * 4 / (ms * 1e-3) / 1e9 / hbm}
             del gs
+    # config 5: joint category+pose model written the way the reference scripts write it — per-head
+    # calls `bin_models[i](x)` mixed with softmax(fc(x)) (learnJointCatPoseModel_weighted.py:107-126,
+    # loss 175-180); the head family runs the 2C per-head calls as one fused stack
+    mj = _pascal_model(C, K).train()
+    fcj = torch.nn.Linear(2048, C).cuda()
+    jparams = list(mj.parameters()) + list(fcj.parameters())
+    for B in (32, 96):
+        x = torch.randn(B, 2048, device=dev, requires_grad=True)
+        lab = torch.randint(0, C, (B,), device=dev)
+        bins = torch.randint(0, K, (B,), device=dev)
+        tgt = torch.randn(B, 3, device=dev)
+
+        def jstep():
+            for p in jparams:
+                p.grad = None
+            y0 = fcj(x)
+            mixw = torch.unsqueeze(torch.softmax(y0, dim=1), dim=2)
+            y1 = torch.stack([mj.bin_models[i](x) for i in range(C)]).permute(1, 2, 0)
+            y2 = torch.stack([mj.res_models[i](x) for i in range(C)]).permute(1, 2, 0)
+            y1 = torch.squeeze(torch.bmm(y1, mixw), 2)
+            y2 = torch.squeeze(torch.bmm(y2, mixw), 2)
+            lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
+            (0.1 * torch.nn.functional.cross_entropy(y0, lab) + lc + lr).backward()
+        set_precision("tf32")
+        try:
+            ms = _time(jstep, 30, 15)
+        finally:
+            set_precision("fp32")
+        out["joint_weighted_script_style_B%d_tf32" % B] = {
+            "samples_per_s_fwd_bwd": B / (ms * 1e-3), "ms_fwd_bwd": ms}
+    del mj
     # raw fc1 GEMM: the dominant kernel of the head (197 MB of weights streamed once)
     H, N1, N0, B = 24, 1000, 2048, 32
     w1 = m._heads().ensure()["w1"]

@@ -90,8 +90,12 @@ class _mlp3(nn.Module):
         object.__setattr__(self, '_solo', None)
 
     def forward(self, x):
-        # a single head = a stack of one, mixing weight 1 (used by scripts that call
-        # `self.bin_models[i](x)` themselves: learnJointCatPoseModel_weighted.py:112-113)
+        # scripts call `self.bin_models[i](x)` head by head (learnJointCatPoseModel_weighted.py:112-113):
+        # the family runs all sibling heads fused on the first call and hands out slices
+        fam = self.__dict__.get('_family')
+        if fam is not None and _head.MEMO and x.is_cuda:
+            return fam.output_of(self, x, self.training)
+        # a head on its own = a stack of one, mixing weight 1
         solo = self._solo
         if solo is None or solo.heads[0] is not self:
             solo = _head.HeadStack([[self]])
@@ -105,6 +109,9 @@ class _mlp3(nn.Module):
         memo[id(self)] = new
         for k, v in self.__dict__.items():
             if k == '_solo':
+                continue
+            if k == '_family':           # re-created by the copied model (or copied with its lists)
+                new.__dict__[k] = copy.deepcopy(v, memo)
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         object.__setattr__(new, '_solo', None)
@@ -135,16 +142,21 @@ class OneBinDeltaModel(nn.Module):
             self.feature_model = fm
         self.bin_models = nn.ModuleList([bin_3layer(N0, N1, N2, num_clusters) for i in range(self.num_classes)]).cuda()
         self.res_models = nn.ModuleList([res_3layer(N0, N1, N2, ndim) for i in range(self.num_classes)]).cuda()
-        object.__setattr__(self, '_stack', None)
+        # the heads know their siblings: a script-defined forward that calls them one by one
+        # (learnJointCatPoseModel_weighted.py:107-126) still runs them as one fused stack
+        fam = _head.HeadFamily([self.bin_models, self.res_models])
+        for m in list(self.bin_models) + list(self.res_models):
+            object.__setattr__(m, '_family', fam)
 
     def _heads(self):
-        st = self.__dict__.get('_stack')
         bins, ress = list(self.bin_models), list(self.res_models)
-        if st is None or len(st.heads) != len(bins) + len(ress) or \
-                any(a is not b for a, b in zip(st.heads, bins + ress)):
-            st = _head.HeadStack([bins, ress])
-            object.__setattr__(self, '_stack', st)
-        return st
+        fam = bins[0].__dict__.get('_family') if bins else None
+        if fam is None or len(fam.lists) != 2 or fam.lists[0] is not self.bin_models or \
+                fam.lists[1] is not self.res_models:
+            fam = _head.HeadFamily([self.bin_models, self.res_models])
+            for m in bins + ress:
+                object.__setattr__(m, '_family', fam)
+        return fam.stack()
 
     def stacked_head_parameters(self):
         """Opt-in fast path for new training loops: the 2*C heads' weights as 10 stacked

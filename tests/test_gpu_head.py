@@ -528,3 +528,77 @@ def test_one_delta_per_bin_models_golden(cuda, golden):
     scale_close(p1, torch.from_numpy(g["prob_y1"]), FP32_TOL, "prob y1")
     scale_close(p2, torch.from_numpy(g["prob_y2"]), FP32_TOL, "prob y2")
     assert p2.shape == (Bh, Kc, nd)
+
+
+def test_script_style_per_head_calls_run_fused(cuda):
+    """A script-defined forward that calls `self.bin_models[i](x)` head by head and mixes with softmax
+    weights (learnJointCatPoseModel_weighted.py:107-115) gets the outputs / gradients of the oracle,
+    and all 2C sibling heads run as ONE fused stack per input (the family memo)."""
+    import binDeltaModels as M
+    from bdpose import head
+    torch.manual_seed(9)
+    C, K, N0, N1, N2, nd, B = 3, 16, 64, 40, 24, 3, 10
+    ref = O.OneBinDeltaHeads(C, K, N0, N1, N2, nd)
+    m = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+    m.feature_model = torch.nn.Identity()
+    m.load_state_dict(ref.state_dict())
+    m.cuda().train(); ref.train()
+    fc_ref = torch.nn.Linear(N0, C)
+    fc = torch.nn.Linear(N0, C)
+    fc.load_state_dict(fc_ref.state_dict())
+    fc.cuda()
+
+    def script_forward(model, fcl, x):                 # the body of JointCatPoseModel.forward
+        y0 = fcl(x)
+        label = torch.unsqueeze(torch.softmax(y0, dim=1), dim=2)
+        y1 = torch.stack([model.bin_models[i](x) for i in range(C)]).permute(1, 2, 0)
+        y2 = torch.stack([model.res_models[i](x) for i in range(C)]).permute(1, 2, 0)
+        return [y0, torch.squeeze(torch.bmm(y1, label), 2), torch.squeeze(torch.bmm(y2, label), 2)]
+
+    calls = {"n": 0}
+    orig = head.run_heads_all
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+    head.run_heads_all = counting
+    try:
+        x = torch.randn(B, N0)
+        xr = x.clone().requires_grad_(True)
+        r0, r1, r2 = script_forward(ref, fc_ref, xr)
+        (r0.sum() + (r1 * r1).sum() + r2.sum()).backward()
+        xg = x.clone().to(cuda).requires_grad_(True)
+        y0, y1, y2 = script_forward(m, fc, xg)
+        assert calls["n"] == 1, "the 2C per-head calls must share one fused launch sequence"
+        (y0.sum() + (y1 * y1).sum() + y2.sum()).backward()
+        scale_close(y1, r1, FP32_TOL, "script y1")
+        scale_close(y2, r2, FP32_TOL, "script y2")
+        scale_close(xg.grad, xr.grad, GRAD_TOL, "script dx")
+        scale_close(fc.weight.grad, fc_ref.weight.grad, GRAD_TOL, "script dfc")
+        for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+            if float(q.grad.abs().max()) > 0:
+                scale_close(p.grad, q.grad, GRAD_TOL, "script grad " + n)
+        for (n, b1), (_, b2) in zip(m.named_buffers(), ref.named_buffers()):
+            if "num_batches" in n:
+                assert int(b1) == int(b2), n
+            else:
+                scale_close(b1, b2, FP32_TOL, "script " + n)
+        # a new input, or the same input after the weights moved, is recomputed
+        script_forward(m, fc, torch.randn(B, N0, device=cuda))
+        assert calls["n"] == 2
+        xs = torch.randn(B, N0, device=cuda)
+        a = m.bin_models[1](xs)
+        with torch.no_grad():
+            m.bin_models[1].fc3.bias.add_(1.0)
+        b = m.bin_models[1](xs)
+        assert calls["n"] == 4 and torch.allclose(b, a.detach() + 1.0, atol=1e-5)
+        # eval mode: pure function of (x, weights); mixed model call and per-head calls agree
+        m.eval()
+        with torch.no_grad():
+            lab = torch.randint(0, C, (B, 1), device=cuda)
+            z1, _ = m(xs, lab)
+            per = torch.stack([m.bin_models[i](xs) for i in range(C)])          # [C, B, K]
+            pick = per[lab.view(-1), torch.arange(B, device=cuda)]
+        scale_close(pick, z1, FP32_TOL, "per-head vs mixed")
+    finally:
+        head.run_heads_all = orig
