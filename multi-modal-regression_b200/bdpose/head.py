@@ -574,8 +574,8 @@ class HeadFamily:
     (learnJointCatPoseModel_weighted.py:112-113, evaluateJointModel.py:86-96): the first such call
     runs ALL heads fused (`run_heads_all`) and the siblings' calls return their slices, which is the
     same work the reference does in its loop — every head sees every sample — in 1/24 of the launches.
-    A result is reused only for the same input tensor (object, version, storage) and mode; parameter
-    versions are re-checked at the start of every round (head 0, or a head asked twice).  BDPOSE_HEAD_MEMO=0 turns this off (every call then runs as a one-head
+    One cached run serves one round: each head at most once, same input tensor (object, version,
+    storage) and mode, that head's parameters untouched since the run.  BDPOSE_HEAD_MEMO=0 turns this off (every call then runs as a one-head
     stack)."""
 
     def __init__(self, lists):
@@ -584,8 +584,9 @@ class HeadFamily:
         self._key = None
         self._x_ref = None
         self._outs = None
-        self._pver = None
+        self._pver = {}
         self._served = set()
+        self._where = {}
 
     def __deepcopy__(self, memo):
         import copy
@@ -604,31 +605,30 @@ class HeadFamily:
             self._key = None
         return st
 
-    def _param_versions(self, st):
-        return tuple(p._version for plist in st.plists.values() for p in plist)
+    @staticmethod
+    def _versions(m):
+        return tuple(p._version for sub in m._modules.values() for p in sub._parameters.values()
+                     if p is not None)
 
     def output_of(self, module, x, training):
-        st = self.stack()
-        st.ensure()
         key = (id(x), x._version, x.data_ptr(), tuple(x.shape), bool(training), torch.is_grad_enabled(),
                x.requires_grad)
-        fresh = key != self._key or self._x_ref is not x
-        if not fresh and (id(module) in self._served or module is st.heads[0]):
-            # a head asked twice for the same input, or a new round of the script's loop starting at
-            # head 0: make sure no parameter was updated in place since the cached run (the
-            # Parameters' version counters: 8 per head, read once per round)
-            fresh = self._param_versions(st) != self._pver
+        # One cached run serves ONE round of the script's loop: every head at most once, for the same
+        # input, with its parameters untouched since the run.  A head asked a second time starts a
+        # new round (as the reference would recompute — and, in train mode, move the BatchNorm
+        # statistics — on every call).
+        fresh = key != self._key or self._x_ref is not x or id(module) in self._served or \
+            self._pver.get(id(module)) != self._versions(module)
         if fresh:
+            st = self.stack()          # membership / storage checks: once per round, not per head
             self._outs = run_heads_all(st, x, training)
             self._key, self._x_ref = key, x
-            self._pver = self._param_versions(st)
+            self._pver = {id(m): self._versions(m) for m in st.heads}
             self._served = set()
+            self._where = {id(m): (gi, j) for gi, g in enumerate(st.groups) for j, m in enumerate(g)}
         self._served.add(id(module))
-        for gi, g in enumerate(st.groups):
-            for j, m in enumerate(g):
-                if m is module:
-                    return self._outs[gi][:, j, :]
-        raise RuntimeError("head is not a member of its family")
+        gi, j = self._where[id(module)]
+        return self._outs[gi][:, j, :]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -587,11 +587,17 @@ def test_script_style_per_head_calls_run_fused(cuda):
         script_forward(m, fc, torch.randn(B, N0, device=cuda))
         assert calls["n"] == 2
         xs = torch.randn(B, N0, device=cuda)
-        a = m.bin_models[1](xs)
+        a = m.bin_models[1](xs)                       # round 3
+        a2 = m.bin_models[2](xs)                      # same round: served from the cached run
+        assert calls["n"] == 3
         with torch.no_grad():
-            m.bin_models[1].fc3.bias.add_(1.0)
-        b = m.bin_models[1](xs)
-        assert calls["n"] == 4 and torch.allclose(b, a.detach() + 1.0, atol=1e-5)
+            m.bin_models[0].fc3.bias.add_(1.0)        # head 0 edited after the run ...
+        b0 = m.bin_models[0](xs)                      # ... so its cached slice is stale: new round
+        assert calls["n"] == 4
+        b1 = m.bin_models[1](xs)                      # served from round 4
+        assert calls["n"] == 4 and b1.shape == a.shape and a2.shape == a.shape
+        m.bin_models[1](xs)                           # asked twice: a new round, as the reference recomputes
+        assert calls["n"] == 5
         # eval mode: pure function of (x, weights); mixed model call and per-head calls agree
         m.eval()
         with torch.no_grad():
