@@ -100,8 +100,8 @@ class ClassificationModel(nn.Module):
 
 
 class OneDeltaPerBinModel(nn.Module):
-    """objectnetHelperFunctions.py:175-198: one bin head + dict_size res_2layer heads, delta picked by
-    the argmax bin (the small per-bin heads stay on stock torch layers)."""
+    """objectnetHelperFunctions.py:175-198: one bin head + dict_size res_2layer heads (fused two-layer
+    stack), delta picked by the argmax bin."""
 
     def __init__(self, num_classes, dict_size=16, n0=2048, n1=1000, n2=500, n3=100, dim=3):
         super().__init__()
@@ -117,6 +117,13 @@ class OneDeltaPerBinModel(nn.Module):
     def forward(self, x, label):
         x = _cat_onehot(self.feature_model(x), label, self.num_classes)
         y1 = self.bin_model(x)
-        y2 = torch.stack([m(x) for m in self.res_models]).permute(1, 2, 0)        # [B, dim, K]
-        pose = _head.onehot(torch.argmax(y1, dim=1, keepdim=True), self.num_clusters).unsqueeze(2)
-        return [y1, torch.squeeze(torch.bmm(y2, pose), 2)]
+        # the K per-bin delta heads run as one fused two-layer stack (the reference loops over them,
+        # objectnetHelperFunctions.py:190); the one-hot bmm select (192-195) is a gather
+        st = self.__dict__.get('_stack2')
+        heads = list(self.res_models)
+        if st is None or len(st.heads) != len(heads) or any(a is not b for a, b in zip(st.heads, heads)):
+            st = _head.Mlp2Stack(heads)
+            object.__setattr__(self, '_stack2', st)
+        y2 = _head.run_mlp2_all(st, x, self.training)                             # [B, K, dim]
+        pose = torch.argmax(y1, dim=1, keepdim=True)
+        return [y1, torch.gather(y2, 1, pose.unsqueeze(2).expand(-1, 1, self.ndim)).squeeze(1)]

@@ -608,3 +608,43 @@ def test_script_style_per_head_calls_run_fused(cuda):
         scale_close(pick, z1, FP32_TOL, "per-head vs mixed")
     finally:
         head.run_heads_all = orig
+
+
+def test_objectnet_delta_per_bin_fused_equals_module_loop(cuda):
+    """objectnetHelperFunctions.OneDeltaPerBinModel: the fused per-bin delta stack gives what the
+    reference's loop over the K res_2layer modules gives (each module on stock torch layers)."""
+    import objectnetHelperFunctions as OH
+    torch.manual_seed(4)
+    NC, K, n0, n1, n2, n3, dim, B = 4, 6, 64, 40, 24, 12, 3, 9      # n0 + NC must be a multiple of 4 (TMA rows)
+    m = OH.OneDeltaPerBinModel.__new__(OH.OneDeltaPerBinModel)
+    torch.nn.Module.__init__(m)
+    m.ndim, m.num_classes, m.num_clusters = dim, NC, K
+    m.feature_model = torch.nn.Identity()
+    m.bin_model = OH.bin_3layer(n0 + NC, n1, n2, K).cuda()
+    m.res_models = torch.nn.ModuleList([OH.res_2layer(n0 + NC, n3, dim) for _ in range(K)]).cuda()
+    m.train()
+    feat = torch.randn(B, n0, device=cuda)
+    lab = torch.randint(0, NC, (B, 1), device=cuda)
+    import copy
+    ref = copy.deepcopy(m)
+    # reference form: loop over the modules + one-hot bmm select (objectnetHelperFunctions.py:186-197)
+    xr = torch.cat((feat, head_onehot(lab, NC)), dim=1).requires_grad_(True)
+    r1 = ref.bin_model(xr)
+    r2 = torch.stack([mm(xr) for mm in ref.res_models]).permute(1, 2, 0)
+    pose = head_onehot(torch.argmax(r1, dim=1, keepdim=True), K).unsqueeze(2)
+    r2 = torch.squeeze(torch.bmm(r2, pose), 2)
+    (r1.sum() + (r2 * r2).sum()).backward()
+    fx = feat.clone().requires_grad_(True)
+    y1, y2 = m(fx, lab)
+    (y1.sum() + (y2 * y2).sum()).backward()
+    scale_close(y1, r1, FP32_TOL, "objectnet perbin y1")
+    scale_close(y2, r2, FP32_TOL, "objectnet perbin y2")
+    scale_close(fx.grad, xr.grad[:, :n0], GRAD_TOL, "objectnet perbin dx")
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        if q.grad is not None and float(q.grad.abs().max()) > 0:
+            scale_close(p.grad, q.grad, GRAD_TOL, "objectnet perbin grad " + n)
+
+
+def head_onehot(label, n):
+    from bdpose import head
+    return head.onehot(label, n)
