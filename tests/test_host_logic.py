@@ -98,3 +98,21 @@ def test_reference_error_conventions():
     from bdpose import ops
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.bd_loss_raw(torch.zeros(4, 8), torch.zeros(4, dtype=torch.long), None, None, None, 0, False)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under multi-modal-regression_b200/ may import it
+    (only tests/, __graft_entry__.smoke() and bench.py's CPU legs do), and there is no CPU fallback
+    module to route through."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "multi-modal-regression_b200")
+    bad = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                if re.search(r"^\s*(import|from)\s+(bdpose_oracle|lloyd_host|oracle)\b", src, re.M):
+                    bad.append(os.path.join(d, f))
+    assert not bad, "product files import the oracle: %s" % bad
