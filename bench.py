@@ -423,11 +423,11 @@ def main():
                     "h2d_bytes_per_step": N_ROT * 12, "d2h_bytes_per_step": N_ROT * 20},
             "gpu_launches": 4 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": 278.6e6, "peak_source": peak_src,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": 277.4e6, "peak_source": peak_src,
                          "kernel": "assign_grid_kernel<float,3,false>", "kernel_ms": kernel_s * 1e3,
                          "algorithmic_bytes_per_launch": N_ROT * BYTES_PER_ROT,
                          "note": "32 B/rotation x 10M rotations per launch; traffic = dram read+write of "
-                                 "one launch from profiles/r1c_ncu_assign.csv; the step also runs the 3 "
+                                 "one launch from profiles/r1d_ncu_assign.csv; the step also runs the 3 "
                                  "key-grid build launches (~50 us)" +
                                  ("; brute-force scan of the same step: %.2f ms" % brute_ms if brute_ms else "")},
             "cpu_baseline": cpu,
