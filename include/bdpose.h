@@ -170,6 +170,13 @@ int bdp_riemannian_residual(const void* x, int x_dtype, int64_t N, const double*
  * may be NULL. */
 int bdp_convert_axis_angle(const double* aa, int64_t N, double* rotmat, double* quat, void* stream);
 
+/* Pose targets from Euler angles: euler_deg [N,3] fp64 = (azimuth, elevation, camera tilt) in degrees
+ * -> R = Rz(ct) Rx(el) Rz(az) (helperFunctions.rotation_matrix, helperFunctions.py:37-48) -> axis-angle
+ * [N,3] fp64 (axisAngle.get_y, axisAngle.py:19-29) and / or unit quaternion [N,4] fp64
+ * (quaternion.get_y, quaternion.py:18-29).  Either output may be NULL.  The reference runs this per
+ * image in python (learnKmeansDictionary.py:31-37, dataGenerators.py:55-69); rendered images pass -ct. */
+int bdp_euler_to_pose(const double* euler_deg, int64_t N, double* aa, double* quat, void* stream);
+
 /*
  * One Lloyd iteration, E-step + M-step accumulation (sklearn lloyd_iter_chunked_dense):
  *   labels[n] = argmin_k ||x_n - c_k||^2 (fp64-faithful, lowest index on ties); the per-cluster

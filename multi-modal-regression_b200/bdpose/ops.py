@@ -414,6 +414,20 @@ def assign_quatdot(q, keys):
     return b, res
 
 
+def euler_to_pose(euler_deg, want_aa=True, want_quat=False):
+    """(az, el, ct) in degrees [N,3] -> axis-angle [N,3] and / or quaternion [N,4], fp64
+    (helperFunctions.rotation_matrix + axisAngle.get_y / quaternion.get_y)."""
+    _need_cuda(euler_deg)
+    e = euler_deg.double().reshape(-1, 3).contiguous()
+    N = e.shape[0]
+    aa = torch.empty((N, 3), dtype=torch.float64, device=e.device) if want_aa else None
+    q = torch.empty((N, 4), dtype=torch.float64, device=e.device) if want_quat else None
+    with torch.cuda.device(e.device):
+        st = L.lib().bdp_euler_to_pose(L.ptr(e), N, L.ptr(aa), L.ptr(q), L.stream_ptr())
+    L.check(st, "bdp_euler_to_pose")
+    return aa, q
+
+
 def riemannian_residual(x, key_rot=None, bins=None, want_rot=True):
     """ydata_rot = get_R(x) and res = get_y(R_key[bin]^T R) (binDeltaGenerators.py:131-137)."""
     _need_cuda(x, key_rot, bins)

@@ -144,21 +144,26 @@ def _images_all():
 def _pose_targets(ds):
     """Pose target of every image of an ImagesAll dataset, as the float32 rows its __getitem__
     produces (dataGenerators.py:55-69), grouped per class."""
-    from helperFunctions import parse_name, rotation_matrix
-    import axisAngle
-    import quaternion
-    to_y = axisAngle.get_y if ds.ydata_type == 'axis_angle' else quaternion.get_y
+    from helperFunctions import parse_name
     if ds.db_type not in ('real', 'render'):
         raise NameError('Unknown db_type passed')
+    if ds.ydata_type not in ('axis_angle', 'quaternion'):
+        raise NameError('Uknown ydata_type passed')
     sign = 1.0 if ds.db_type == 'real' else -1.0
-    out = []
-    for names in ds.list_image_names:
-        rows = np.zeros((len(names), 3 if ds.ydata_type == 'axis_angle' else 4), dtype=np.float32)
-        for j, name in enumerate(names):
+    sizes = [len(names) for names in ds.list_image_names]
+    eul = np.zeros((sum(sizes), 3))
+    r = 0
+    for names in ds.list_image_names:          # string parsing stays on the host
+        for name in names:
             _, _, az, el, ct, _ = parse_name(name)
-            rows[j] = to_y(rotation_matrix(az, el, sign * ct))
-        out.append(rows)
-    return out
+            eul[r] = (az, el, sign * ct)
+            r += 1
+    # Euler -> R -> log map for the whole dataset in one launch (the reference: per image in python)
+    quat = ds.ydata_type == 'quaternion'
+    aa, q = ops.euler_to_pose(torch.from_numpy(eul).cuda(), want_aa=not quat, want_quat=quat)
+    y = (q if quat else aa).float().cpu().numpy()        # `.float()` as dataGenerators.py:70
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    return [y[off[i]:off[i + 1]] for i in range(len(sizes))]
 
 
 class _LabelTable:

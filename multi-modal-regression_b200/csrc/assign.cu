@@ -1217,6 +1217,54 @@ __global__ void __launch_bounds__(128) convert_aa_kernel(const double* __restric
   }
 }
 
+// ---- pose targets from Euler angles -------------------------------------------
+// helperFunctions.rotation_matrix (37-48): R = Rz(ct) Rx(el) Rz(az), degrees; then axisAngle.get_y
+// (19-29) and / or quaternion.get_y (18-29).  The reference does this per image in python
+// (learnKmeansDictionary.py:31-37, dataGenerators.py:55-69).
+__global__ void __launch_bounds__(128) euler_pose_kernel(const double* __restrict__ euler, int64_t N,
+                                                         double* __restrict__ aa,
+                                                         double* __restrict__ quat) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double d2r = 0.017453292519943295;
+  double sa, ca, sb, cb, sc, cc;
+  sincos(euler[i * 3 + 0] * d2r, &sa, &ca);
+  sincos(euler[i * 3 + 1] * d2r, &sb, &cb);
+  sincos(euler[i * 3 + 2] * d2r, &sc, &cc);
+  // Rb Ra, then Rc (Rb Ra): the association order of np.dot(np.dot(Rc, Rb), Ra) differs only by rounding
+  const double Ra[9] = {ca, -sa, 0.0, sa, ca, 0.0, 0.0, 0.0, 1.0};
+  const double Rb[9] = {1.0, 0.0, 0.0, 0.0, cb, -sb, 0.0, sb, cb};
+  const double Rc[9] = {cc, -sc, 0.0, sc, cc, 0.0, 0.0, 0.0, 1.0};
+  double T[9], R[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      T[r * 3 + c] = Rc[r * 3 + 0] * Rb[0 * 3 + c] + Rc[r * 3 + 1] * Rb[1 * 3 + c] + Rc[r * 3 + 2] * Rb[2 * 3 + c];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      R[r * 3 + c] = T[r * 3 + 0] * Ra[0 * 3 + c] + T[r * 3 + 1] * Ra[1 * 3 + c] + T[r * 3 + 2] * Ra[2 * 3 + c];
+  if (aa) {
+    double y[3];
+    rot_log(R, y);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) aa[i * 3 + k] = y[k];
+  }
+  if (quat) {
+    const double tR = 0.5 * (R[0] + R[4] + R[8] - 1.0);
+    double th = acos(fmin(fmax(tR, -1.0), 1.0));
+    double v[3] = {0.5 * (R[7] - R[5]), 0.5 * (R[2] - R[6]), 0.5 * (R[3] - R[1])};
+    const double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (n > 1e-6) { v[0] /= n; v[1] /= n; v[2] /= n; }
+    else { th = 0.0; v[0] = v[1] = v[2] = 0.0; }
+    double s, c;
+    sincos(0.5 * th, &s, &c);
+    quat[i * 4 + 0] = c; quat[i * 4 + 1] = s * v[0]; quat[i * 4 + 2] = s * v[1]; quat[i * 4 + 3] = s * v[2];
+  }
+}
+
 // ---- k-means M-step finalisation ------------------------------------------------------------------
 // (hi, lo) limbs -> correctly rounded double of  hi*2^32 + lo  (|value| < 2^95), then * scale.
 __device__ __forceinline__ double limbs_to_double(long long hi, long long lo, double inv_scale_lo) {
@@ -1556,5 +1604,16 @@ extern "C" int bdp_kmeans_iteration(const double* x, int64_t N, int d, const dou
   if (centers_new)
     return bdp_kmeans_finalize(acc_stats, K, d, fix_hi_bits, centers, centers_new, shift2, n_empty,
                                stream);
+  return BDP_OK;
+}
+
+extern "C" int bdp_euler_to_pose(const double* euler_deg, int64_t N, double* aa, double* quat,
+                                 void* stream) {
+  BDP_REQUIRE(N >= 0, "euler_to_pose: N < 0");
+  if (N == 0) return BDP_OK;
+  BDP_REQUIRE(euler_deg != nullptr && (aa || quat), "euler_to_pose: NULL buffer");
+  euler_pose_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      euler_deg, N, aa, quat);
+  BDP_CUDA_CHECK_LAUNCH("euler_pose_kernel");
   return BDP_OK;
 }

@@ -545,3 +545,30 @@ def test_soft_bin_losses_golden(cuda, golden, tmp_path):
             close(s_.grad, ref_s, rtol=0, atol=1e-5 * float(np.abs(ref_s).max()), msg=tag + " g_score")
             close(r_.grad, ref_r, rtol=0, atol=1e-5 * float(np.abs(ref_r).max()), msg=tag + " g_res")
     BL.FUSE_EXPECTED_POSE = True
+
+
+def test_euler_to_pose_vs_oracle(cuda, golden):
+    """Batched pose targets: Euler angles -> R -> axis-angle / quaternion against the
+    oracle's restatement of helperFunctions.rotation_matrix + axisAngle.get_y / quaternion.get_y,
+    on the golden Euler angles (whose matrices were produced by the reference) and on the special
+    cases (identity -> zero vector, theta = pi -> zero axis-angle by the reference's convention)."""
+    from bdpose import ops
+    g = golden("rotation_helpers")
+    eul = g["euler"]
+    for i in range(len(eul)):                      # the oracle reproduces the reference's matrices
+        assert np.allclose(O.rotation_matrix(*eul[i]), g["R_euler"][i], rtol=0, atol=1e-15)
+    rng = np.random.default_rng(4)
+    extra = np.concatenate([rng.uniform(-180, 360, (500, 3)),
+                            [[0, 0, 0], [180, 0, 0], [0, 180, 0], [90, 0, -90], [30, 1e-7, -30]]])
+    e = np.concatenate([eul, extra])
+    aa, q = ops.euler_to_pose(torch.from_numpy(e).to(cuda), want_aa=True, want_quat=True)
+    ref_aa = np.stack([O.get_y(O.rotation_matrix(*r)) for r in e])
+    ref_q = np.stack([O.quat_get_y(O.rotation_matrix(*r)) for r in e])
+    # near theta = pi the log map divides by a vanishing ||vee(R - R^T)||: compare where it is
+    # well conditioned to 1e-9, everywhere to 1e-6
+    n = np.linalg.norm(ref_aa, axis=1)
+    ok = (n < 3.1) & ((n > 1e-3) | (n == 0))
+    assert np.allclose(aa.cpu().numpy()[ok], ref_aa[ok], rtol=0, atol=1e-9)
+    assert np.allclose(q.cpu().numpy()[ok], ref_q[ok], rtol=0, atol=1e-9)
+    assert np.allclose(aa.cpu().numpy(), ref_aa, rtol=0, atol=1e-6)
+    assert np.array_equal(aa.cpu().numpy()[len(eul) + 500], np.zeros(3))
