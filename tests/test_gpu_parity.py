@@ -572,3 +572,17 @@ def test_euler_to_pose_vs_oracle(cuda, golden):
     assert np.allclose(q.cpu().numpy()[ok], ref_q[ok], rtol=0, atol=1e-9)
     assert np.allclose(aa.cpu().numpy(), ref_aa, rtol=0, atol=1e-6)
     assert np.array_equal(aa.cpu().numpy()[len(eul) + 500], np.zeros(3))
+
+
+def test_learn_dictionary_cli_synthetic(cuda, tmp_path):
+    """bdpose.learn_dictionary (the GPU learnKmeansDictionary.py): fits, pickles an estimator that the
+    loss / generator mirrors can load (n_clusters, cluster_centers_, predict)."""
+    from bdpose import learn_dictionary
+    out = tmp_path / "kmeans_dictionary_axis_angle_32.pkl"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        learn_dictionary.main(["32", "--synthetic", "40000", "--out", str(out), "--n_init", "2"])
+    km = pickle.load(open(out, "rb"))
+    assert km.n_clusters == 32 and km.cluster_centers_.shape == (32, 3)
+    assert np.all(np.linalg.norm(km.cluster_centers_, axis=1) <= np.pi + 1e-9)
+    assert km.predict(km.cluster_centers_.astype(np.float32)).tolist() == list(range(32))
