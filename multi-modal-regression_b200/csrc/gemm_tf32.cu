@@ -62,6 +62,7 @@ struct GemmParams {
   int a_rows;                       // A rows actually fetched per stage (small-M problems)
   int a_bytes;                      // smem reserved for the A tile of one stage (1 KB multiple)
   int acc_stages;                   // TMEM accumulator stages (2 only when a CTA runs >1 tile)
+  int debug;                        // timing experiments only (BDP_GEMM_DEBUG), 0 in production
   int stage_out;                    // 1: epilogue transposes through smem so stores are whole 128-byte row segments
 };
 
@@ -307,7 +308,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < kBK / kUmmaK; ++k) {
           const uint32_t d_hi = tmem_t + hi_col;
-          if (precise) {
+          if (P.debug & 4) {
+          } else if (precise && (P.debug & 2)) {
+            umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0);
+          } else if (precise) {
             if (x_span != 0) {
               const uint32_t d_x = tmem_t + hi_span + x_col;
               umma_tf32(d_x, ad + lo16, bd, idesc, x_fresh <= 0);
@@ -354,7 +358,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           const uint32_t sa = base + stage * stage_bytes;
-          for (int ii = tid; ii < nvec; ii += kSplitThreads) {
+          for (int ii = tid; ii < ((P.debug & 1) ? 0 : nvec); ii += kSplitThreads) {
             const int i = ii < a_vec ? ii : ii - a_vec + static_cast<int>(a_bytes / 16);
             uint32_t x0, x1, x2, x3;
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -371,7 +375,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
           }
           // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (!(P.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(split_bar(stage));
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
@@ -613,6 +617,7 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   P.stage_out = (c_layout == 0 && M >= 64 && N % 4 == 0 && ldc % 4 == 0 && c_gstride % 4 == 0 &&
                  c_sstride % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
   P.precise = precise ? 1 : 0;
+  { const char* e = getenv("BDP_GEMM_DEBUG"); P.debug = e ? atoi(e) : 0; }
   {
     static const int no_rotate = [] { const char* e = getenv("BDP_GEMM_NO_ROTATE"); return (e && e[0] == '1') ? 1 : 0; }();
     P.k_rotate = no_rotate ? 0 : 1;
