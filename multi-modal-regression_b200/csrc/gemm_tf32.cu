@@ -103,24 +103,41 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// One lane of a converged warp (always the same one for a full mask): the warp keeps running
+// uniform code, so descriptors and addresses stay in uniform registers for UTCHMMA / UTMALDG.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
+// `issue` is the elected-lane flag: the instructions are predicated, not branched around, so the
+// warp stays converged and the operands stay in uniform registers.
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(issue) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
+                                          uint32_t idesc, uint32_t accumulate, uint32_t issue) {
   const uint32_t z = 0;
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z), "r"(issue)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -196,7 +213,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t epi_base = bar_base + 8u * (3 * kMaxStages + 4);      // 16-byte aligned
   __shared__ uint32_t s_tmem_base;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches are uniform branches
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const int need_cols = P.acc_stages * P.chains * P.cstride;
   const int tmem_cols = (need_cols <= 32) ? 32 : (need_cols <= 64) ? 64 : (need_cols <= 128) ? 128
                         : (need_cols <= 256) ? 256 : 512;
@@ -223,8 +242,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tiles_per_group = P.m_tiles * P.n_tiles * P.splits;
   const int total_tiles = P.G * tiles_per_group;
 
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
+  if (warp == 0) {
+    // ===== TMA producer (whole warp runs the loop, one elected lane issues) =====
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -248,25 +267,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = base + stage * stage_bytes;
         const uint32_t sb = sa + a_bytes;
-        mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
         const int k0 = kb * kBK;
-        if (!P.a_mn) {
-          tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, g * P.a_g);    // box = a_rows x 32
-        } else {
-          for (int j = 0; j < P.a_rows / 32; ++j)
-            tma_load_3d(sa + j * 4096, &tmA, full_bar(stage), m0 + 32 * j, k0, g * P.a_g);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
+          if (!P.a_mn) {
+            tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, g * P.a_g);    // box = a_rows x 32
+          } else {
+            for (int j = 0; j < P.a_rows / 32; ++j)
+              tma_load_3d(sa + j * 4096, &tmA, full_bar(stage), m0 + 32 * j, k0, g * P.a_g);
+          }
+          if (!P.b_mn) {
+            tma_load_3d(sb, &tmB, full_bar(stage), k0, n0, g * P.b_g);
+          } else {
+            for (int j = 0; j < P.BN / 32; ++j)
+              tma_load_3d(sb + j * 4096, &tmB, full_bar(stage), n0 + 32 * j, k0, g * P.b_g);
+          }
         }
-        if (!P.b_mn) {
-          tma_load_3d(sb, &tmB, full_bar(stage), k0, n0, g * P.b_g);
-        } else {
-          for (int j = 0; j < P.BN / 32; ++j)
-            tma_load_3d(sb + j * 4096, &tmB, full_bar(stage), n0 + 32 * j, k0, g * P.b_g);
-        }
+        __syncwarp();
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer (single thread) =====
+  } else if (warp == 1) {
+    // ===== MMA issuer (whole warp runs the loop, one elected lane issues) =====
     // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b_format TF32 = 2 (bits 7, 10),
     // a/b major (bits 15, 16), N >> 3 (bits 17..22), M >> 4 (bits 24..28)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
@@ -286,6 +308,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t hi_span = static_cast<uint32_t>(P.chains_hi) * cstride;
     const uint32_t x_span = static_cast<uint32_t>(chains_x) * cstride;
     const int precise = P.precise;
+    const uint32_t leader = elect_one() ? 1u : 0u;
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -310,23 +333,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t d_hi = tmem_t + hi_col;
           if (P.debug & 4) {
           } else if (precise && (P.debug & 2)) {
-            umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0);
+            umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
           } else if (precise) {
             if (x_span != 0) {
               const uint32_t d_x = tmem_t + hi_span + x_col;
-              umma_tf32(d_x, ad + lo16, bd, idesc, x_fresh <= 0);
-              umma_tf32(d_x, ad, bd + lo16, idesc, 1u);
-              umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0);
+              umma_tf32(d_x, ad + lo16, bd, idesc, x_fresh <= 0, leader);
+              umma_tf32(d_x, ad, bd + lo16, idesc, 1u, leader);
+              umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
               --x_fresh;
               x_col += cstride;
               if (x_col == x_span) x_col = 0;
             } else {                                     // a single chain takes everything
-              umma_tf32(d_hi, ad + lo16, bd, idesc, hi_fresh <= 0);
-              umma_tf32(d_hi, ad, bd + lo16, idesc, 1u);
-              umma_tf32(d_hi, ad, bd, idesc, 1u);
+              umma_tf32(d_hi, ad + lo16, bd, idesc, hi_fresh <= 0, leader);
+              umma_tf32(d_hi, ad, bd + lo16, idesc, 1u, leader);
+              umma_tf32(d_hi, ad, bd, idesc, 1u, leader);
             }
           } else {
-            umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0);
+            umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
           }
           --hi_fresh;
           hi_col += cstride;
@@ -334,8 +357,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ad += a_kstep16;
           bd += b_kstep16;
         }
-        umma_commit(empty_bar(stage));                 // frees the smem slot when the MMAs retire
-        if (kb == kb1 - 1) umma_commit(tfull_bar(as)); // accumulator complete -> epilogue
+        umma_commit(empty_bar(stage), leader);                 // frees the smem slot when the MMAs retire
+        if (kb == kb1 - 1) umma_commit(tfull_bar(as), leader); // accumulator complete -> epilogue
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
       if (++as == P.acc_stages) { as = 0; aphase ^= 1u; }
