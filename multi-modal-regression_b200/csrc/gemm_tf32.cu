@@ -381,21 +381,35 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           const uint32_t sa = base + stage * stage_bytes;
-          for (int ii = tid; ii < ((P.debug & 1) ? 0 : nvec); ii += kSplitThreads) {
-            const int i = ii < a_vec ? ii : ii - a_vec + static_cast<int>(a_bytes / 16);
-            uint32_t x0, x1, x2, x3;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sa + 16u * i));
-            // the tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32
-            // left in place IS the hi part; only lo = tf32(x - hi) is written
-            const uint32_t h0 = x0 & 0xFFFFE000u, h1 = x1 & 0xFFFFE000u, h2 = x2 & 0xFFFFE000u,
-                           h3 = x3 & 0xFFFFE000u;
-            const uint32_t l0 = __float_as_uint(__uint_as_float(x0) - __uint_as_float(h0)) & 0xFFFFE000u;
-            const uint32_t l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1)) & 0xFFFFE000u;
-            const uint32_t l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2)) & 0xFFFFE000u;
-            const uint32_t l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3)) & 0xFFFFE000u;
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + tile_bytes + 16u * i),
-                         "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+          // four vectors per thread in flight: the loop is latency-bound (shared-memory round trip
+          // per iteration), not bandwidth-bound
+          for (int i0 = tid; i0 < ((P.debug & 1) ? 0 : nvec); i0 += 4 * kSplitThreads) {
+            uint32_t x[4][4];
+            uint32_t off[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int ii = i0 + u * kSplitThreads;
+              const int i = ii < a_vec ? ii : ii - a_vec + static_cast<int>(a_bytes / 16);
+              off[u] = 16u * static_cast<uint32_t>(i);
+              if (ii < nvec)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(x[u][0]), "=r"(x[u][1]), "=r"(x[u][2]), "=r"(x[u][3]) : "r"(sa + off[u]));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (i0 + u * kSplitThreads < nvec) {
+                // the tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32
+                // left in place IS the hi part; only lo = tf32(x - hi) is written
+                uint32_t l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t h = x[u][j] & 0xFFFFE000u;
+                  l[j] = __float_as_uint(__uint_as_float(x[u][j]) - __uint_as_float(h)) & 0xFFFFE000u;
+                }
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + tile_bytes + off[u]),
+                             "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+              }
+            }
           }
           // generic-proxy writes -> visible to the tensor core's async-proxy reads
           if (!(P.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -632,6 +646,7 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
     const long long cost = ((tiles + sms - 1) / sms) * (cand + 16);
     if (bn == 0 || cost < best_cost) { bn = cand; best_cost = cost; }
   }
+  { const char* e = getenv("BDP_GEMM_BN"); if (e && atoi(e) >= bn_step && atoi(e) <= 256) bn = atoi(e) / bn_step * bn_step; }   // timing experiments
   P.BN = bn;
   P.n_tiles = (int)((N + bn - 1) / bn);
   P.a_g = (a_gstride != 0 || G == 1) ? 1 : 0;
