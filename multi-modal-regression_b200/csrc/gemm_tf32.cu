@@ -45,6 +45,7 @@ constexpr int kABytes = kBM * kBK * 4;     // 16 KB per stage
 constexpr int kMaxStages = 10;
 constexpr int kEpiPitch = 36;        // floats per staged row (32 + 4: conflict-free float4 rows)
 constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;   // 4 epilogue warps x 32 rows
+constexpr int kStackEpiBytes = 64 * kEpiPitch * 4;  // stacked mode: the lo rows' partial sums of one 32-column chunk
 
 struct GemmParams {
   int M, N, K, G;
@@ -62,6 +63,7 @@ struct GemmParams {
   int a_rows;                       // A rows actually fetched per stage (small-M problems)
   int a_bytes;                      // smem reserved for the A tile of one stage (1 KB multiple)
   int acc_stages;                   // TMEM accumulator stages (2 only when a CTA runs >1 tile)
+  int stack;                        // precise mode, batch-side A with <= 64 rows: A_lo rows stacked under A_hi (2 MMAs per k-step)
   int debug;                        // timing experiments only (BDP_GEMM_DEBUG), 0 in production
   int stage_out;                    // 1: epilogue transposes through smem so stores are whole 128-byte row segments
 };
@@ -203,7 +205,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t a_bytes = static_cast<uint32_t>(P.a_bytes);
   const uint32_t tile_bytes = a_bytes + b_bytes;                 // operand footprint of one stage
   const uint32_t a_tx = static_cast<uint32_t>(P.a_rows) * kBK * 4;   // A bytes TMA really delivers
-  const uint32_t stage_bytes = P.precise ? 2u * tile_bytes : tile_bytes;   // + the lo copies
+  // lo copies (precise mode): of the whole [A | B] footprint right after it, or — stacked mode — the
+  // A_lo rows directly under the A_hi rows (inside a_bytes) and B_lo after B
+  const uint32_t stage_bytes = P.stack ? a_bytes + 2u * b_bytes : P.precise ? 2u * tile_bytes : tile_bytes;
+  const uint32_t a_lo_off = P.stack ? a_tx : tile_bytes;      // from the A tile
+  const uint32_t b_lo_off = P.stack ? b_bytes : tile_bytes;   // from the B tile
   const uint32_t bar_base = base + P.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -304,6 +310,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t a_kstep16 = (P.a_mn ? 1024u : kUmmaK * 4u) >> 4;   // descriptor address units
     const uint32_t b_kstep16 = (P.b_mn ? 1024u : kUmmaK * 4u) >> 4;
     const uint32_t lo16 = tile_bytes >> 4;               // hi -> lo copy of the same operand
+    const uint32_t b_lo16 = b_lo_off >> 4;
     const uint32_t cstride = static_cast<uint32_t>(P.cstride);
     const uint32_t hi_span = static_cast<uint32_t>(P.chains_hi) * cstride;
     const uint32_t x_span = static_cast<uint32_t>(chains_x) * cstride;
@@ -334,6 +341,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (P.debug & 4) {
           } else if (precise && (P.debug & 2)) {
             umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
+          } else if (P.stack) {
+            // A = [A_hi rows ; A_lo rows]: lanes < a_rows get A_hi*B, lanes a_rows.. get A_lo*B
+            if (x_span != 0) {
+              const uint32_t d_x = tmem_t + hi_span + x_col;
+              umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
+              umma_tf32(d_x, ad, bd + b_lo16, idesc, x_fresh <= 0, leader);
+              --x_fresh;
+              x_col += cstride;
+              if (x_col == x_span) x_col = 0;
+            } else {
+              umma_tf32(d_hi, ad, bd + b_lo16, idesc, hi_fresh <= 0, leader);
+              umma_tf32(d_hi, ad, bd, idesc, 1u, leader);
+            }
           } else if (precise) {
             if (x_span != 0) {
               const uint32_t d_x = tmem_t + hi_span + x_col;
@@ -385,12 +405,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // per iteration), not bandwidth-bound
           for (int i0 = tid; i0 < ((P.debug & 1) ? 0 : nvec); i0 += 4 * kSplitThreads) {
             uint32_t x[4][4];
-            uint32_t off[4];
+            uint32_t off[4], lo_off[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int ii = i0 + u * kSplitThreads;
               const int i = ii < a_vec ? ii : ii - a_vec + static_cast<int>(a_bytes / 16);
               off[u] = 16u * static_cast<uint32_t>(i);
+              lo_off[u] = off[u] + (ii < a_vec ? a_lo_off : b_lo_off);
               if (ii < nvec)
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(x[u][0]), "=r"(x[u][1]), "=r"(x[u][2]), "=r"(x[u][3]) : "r"(sa + off[u]));
@@ -406,7 +427,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   const uint32_t h = x[u][j] & 0xFFFFE000u;
                   l[j] = __float_as_uint(__uint_as_float(x[u][j]) - __uint_as_float(h)) & 0xFFFFE000u;
                 }
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + tile_bytes + off[u]),
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + lo_off[u]),
                              "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
               }
             }
@@ -456,6 +477,33 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int nb = n0 + c * 32;
         const int wcols = full ? 32 : 16;
+        if (P.stack) {
+          // rows a_rows .. 2*a_rows-1 hold A_lo * (B_hi + B_lo): hand them to the rows above through
+          // shared memory (the two row sets can sit in different warps)
+          const int rr = q * 32 + lane;
+          if (rr >= P.a_rows && rr < 2 * P.a_rows) {
+            const uint32_t dst = epi_base + static_cast<uint32_t>((rr - P.a_rows) * kEpiPitch) * 4;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * j),
+                           "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (rr < P.a_rows) {
+            const uint32_t src = epi_base + static_cast<uint32_t>(rr * kEpiPitch) * 4;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t o0, o1, o2, o3;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(src + 16 * j));
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + __uint_as_float(o0));
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + __uint_as_float(o1));
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + __uint_as_float(o2));
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + __uint_as_float(o3));
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // the buffer is rewritten by the next chunk
+        }
         if (P.stage_out) {
           // Big outputs (wgrad: 197 MB): lane r holds 32 columns of ROW r, so a direct store writes
           // 32 scattered 16-byte pieces per instruction and every 32-byte sector twice.  Transposed
@@ -663,7 +711,14 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   // small-M problems (M = batch) fetch only the rows that exist
   if (P.m_tiles == 1) P.a_rows = a_major ? (int)((M + 31) / 32 * 32) : (int)((M + 7) / 8 * 8);
   else P.a_rows = kBM;
-  P.a_bytes = a_major ? (P.a_rows / 32) * 4096 : (P.a_rows * kBK * 4 + 1023) / 1024 * 1024;
+  // 3xTF32 with a batch-side A of <= 64 rows: the A_lo rows ride in the same MMA as the A_hi rows
+  // (TMEM lanes a_rows..2*a_rows-1), so a k-step is 2 MMAs instead of 3 — the precise mode is bound
+  // by the tensor core's shared-memory operand reads (every MMA re-reads 128 A rows + BN B rows)
+  P.stack = (precise && !a_major && P.m_tiles == 1 && P.a_rows <= 64) ? 1 : 0;
+  { const char* e = getenv("BDP_GEMM_NO_STACK"); if (e && e[0] == '1') P.stack = 0; }
+  P.a_bytes = a_major ? (P.a_rows / 32) * 4096
+                      : ((P.stack ? 2 : 1) * P.a_rows * kBK * 4 + 1023) / 1024 * 1024;
+  if (P.stack) P.stage_out = 0;
   const long long total = (long long)G * P.m_tiles * P.n_tiles * P.splits;
   long long grid = sms;
   if (grid > total) grid = total;
@@ -676,11 +731,12 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   if (P.chains > 8) P.chains = 8;
   P.chains_hi = (precise && P.chains >= 2) ? P.chains - (P.chains >= 4 ? P.chains / 4 : 1) : P.chains;
 
-  const size_t stage_bytes = ((size_t)P.a_bytes + (size_t)bn * kBK * 4) * (precise ? 2 : 1);
+  const size_t stage_bytes = P.stack ? (size_t)P.a_bytes + 2 * (size_t)bn * kBK * 4
+                                     : ((size_t)P.a_bytes + (size_t)bn * kBK * 4) * (precise ? 2 : 1);
   // The MMA always reads 128 A rows from shared memory (rows >= a_rows produce discarded D rows), so
   // a shrunk A reservation is followed by `slack` bytes that keep those reads inside the allocation.
   const size_t slack = (size_t)(kABytes - P.a_bytes);
-  const size_t fixed = 1024 + 8 * (3 * kMaxStages + 4) + slack + (P.stage_out ? kEpiBytes : 0);
+  const size_t fixed = 1024 + 8 * (3 * kMaxStages + 4) + slack + (P.stage_out ? kEpiBytes : P.stack ? kStackEpiBytes : 0);
   int stages = (int)((224 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   { const char* e = getenv("BDP_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
