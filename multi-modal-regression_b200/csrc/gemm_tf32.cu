@@ -7,8 +7,8 @@
 // Either operand may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); both are
 // legal tcgen05 TF32 shared-memory layouts, so one kernel serves fprop (W x^T), dgrad (W^T dy) and
 // wgrad (dy a^T) of nn.Linear (binDeltaModels.py:71-75, 87-91) without any transpose pass:
-//   rows of D (m)  -> the 128 TMEM lanes  (always the "feature" side: swap-AB, batch is the N side)
-//   cols of D (n)  -> TMEM columns, BN <= 256 per tile
+//   rows of D (m)  -> the 128 TMEM lanes  (fprop / dgrad: the batch, only the rows that exist are fetched)
+//   cols of D (n)  -> TMEM columns, BN <= 256 per tile (fprop / dgrad: the streamed weight rows)
 //
 // Warp roles (512 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> global),
@@ -22,6 +22,12 @@
 // and lo = tf32(x - hi), and D += Ahi*Bhi + Ahi*Blo + Alo*Bhi; the dropped
 // terms are ~2^-20 relative, i.e. fp32-class results (needed for parity: at 1e-3 a few ReLU masks
 // flip and gradients drift by percents).  The weights still stream from HBM exactly once.
+// Stacked form (K-major A of <= 64 rows, i.e. every fprop / dgrad at the reference's batch sizes):
+// the A_lo rows are written directly under the A_hi rows of the same operand tile, so ONE MMA
+// computes Ahi*B (TMEM lanes 0..a_rows-1) and Alo*B (lanes a_rows..2*a_rows-1); a k-step is
+// [Ahi;Alo]*Bhi + [Ahi;Alo]*Blo = 2 MMAs instead of 3, and the epilogue adds the lo lanes to the hi
+// lanes.  The precise mode is bound by shared-memory traffic (every MMA re-reads its operands), so
+// one MMA less per k-step is ~30 % of the kernel time.
 //
 // Accumulator chains.  The tensor core adds each K=8 partial sum into the fp32 accumulator with
 // truncation, so one long chain drifts by ~(#k-steps) * ulp(acc)/2 (measured: 1.6e-5 of the result
@@ -302,9 +308,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                            (static_cast<uint32_t>(P.b_mn) << 16) |
                            (static_cast<uint32_t>(P.BN >> 3) << 17) |
                            (static_cast<uint32_t>(kBM >> 4) << 24);
-    // Everything that does not change per k-step is hoisted: this single thread issues up to 12 MMAs
-    // per k-block and its scalar instruction stream is the pacing item in precise mode (runtime
-    // modulos and 64-bit descriptor assembly per MMA cost ~2500 cycles per k-block).
+    // Everything that does not change per k-step is hoisted: up to 12 MMAs are issued per k-block and
+    // the scalar instruction stream around them paces the precise mode (runtime modulos and 64-bit
+    // descriptor assembly per MMA cost ~2500 cycles per k-block; a single divergent issuing lane
+    // ~145 cycles per MMA in R2UR moves and elect loops — hence the converged warp).
     const uint64_t a_desc0 = umma_desc(0, P.a_mn ? 4096u : 16u, P.a_mn ? 512u : 1024u, P.a_mn ? 1u : 2u);
     const uint64_t b_desc0 = umma_desc(0, P.b_mn ? 4096u : 16u, P.b_mn ? 512u : 1024u, P.b_mn ? 1u : 2u);
     const uint32_t a_kstep16 = (P.a_mn ? 1024u : kUmmaK * 4u) >> 4;   // descriptor address units
