@@ -1119,7 +1119,8 @@ def bench_dp(dev, world):
 
 
 def profile(dev):
-    """One tf32 training step of the Pascal head for ncu (profiles/prof_targets.py head)."""
+    """One training step of the Pascal head per precision mode (tf32, then 3xTF32) for ncu
+    (profiles/prof_targets.py head)."""
     from . import ops
     m = _pascal_model().train()
     B, K = 32, 200
@@ -1128,10 +1129,11 @@ def profile(dev):
     bins = torch.randint(0, K, (B,), device=dev)
     tgt = torch.randn(B, 3, device=dev)
     keys = torch.randn(K, 3, device=dev)
-    set_precision("tf32")
     try:
-        y1, y2 = m(x, lab)
-        lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
-        (lc + lr).backward()
+        for mode in ("tf32", "fp32"):
+            set_precision(mode)
+            y1, y2 = m(x, lab)
+            lc, lr, _ = ops.bd_loss(y1, bins, y2, tgt, keys, L.POSE_GEODESIC_AA, True)
+            (lc + lr).backward()
     finally:
         set_precision("fp32")
