@@ -687,11 +687,13 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   // the tile width: `need` chains of roundup32(BN) columns must fit the 512 TMEM columns.
   const int steps = P.kb_per_split * (kBK / kUmmaK);
   int need = 1;
-  if (precise) {
+  if (precise && 3 * steps > 64) {
     int need_hi = (steps + 63) / 64;
     if (need_hi > 6) need_hi = 6;
     need = need_hi + 1;                               // + one chain for the hi*lo cross terms
   }
+  // (short K — the wgrads, K = batch: all 3 * steps MMAs fit one chain's drift budget, and one chain
+  // of 256 columns leaves room for two accumulator stages, so epilogue and mainloop overlap)
   int bn = 0;
   long long best_cost = 0;
   for (int cand = 256; cand >= bn_step; cand -= bn_step) {
