@@ -712,6 +712,9 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   P.stage_out = (c_layout == 0 && M >= 64 && N % 4 == 0 && ldc % 4 == 0 && c_gstride % 4 == 0 &&
                  c_sstride % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
   P.precise = precise ? 1 : 0;
+  // Timing experiments (results are WRONG with any bit set; DESIGN.md 4.1 uses them to attribute the
+  // per-k-block time): 1 = splitters skip their loads/stores, 2 = 3xTF32 issues only the hi*hi MMA,
+  // 4 = no MMAs at all (TMA + barriers only), 8 = splitters skip the async-proxy fence.
   { const char* e = getenv("BDP_GEMM_DEBUG"); P.debug = e ? atoi(e) : 0; }
   {
     static const int no_rotate = [] { const char* e = getenv("BDP_GEMM_NO_ROTATE"); return (e && e[0] == '1') ? 1 : 0; }();
