@@ -46,7 +46,7 @@ constexpr int kBM = 128;            // tile rows = TMEM lanes
 constexpr int kBK = 32;             // fp32 per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;           // K of one tcgen05.mma.kind::tf32
 constexpr int kGemmThreads = 512;
-constexpr int kSplitThreads = 256;   // warps 8-15
+constexpr int kSplitThreads = 256;   // warps 8-15 (precise mode)
 constexpr int kABytes = kBM * kBK * 4;     // 16 KB per stage
 constexpr int kMaxStages = 10;
 constexpr int kEpiPitch = 36;        // floats per staged row (32 + 4: conflict-free float4 rows)
@@ -70,6 +70,8 @@ struct GemmParams {
   int a_bytes;                      // smem reserved for the A tile of one stage (1 KB multiple)
   int acc_stages;                   // TMEM accumulator stages (2 only when a CTA runs >1 tile)
   int stack;                        // precise mode, batch-side A with <= 64 rows: A_lo rows stacked under A_hi (2 MMAs per k-step)
+  int split_warps;                  // operand-splitter warps: 8 (warps 8-15) in precise mode, else 0
+  int n_epi;                        // epilogue warps per TMEM lane quarter: warps 4-7, plus the warps after the splitters
   int debug;                        // timing experiments only (BDP_GEMM_DEBUG), 0 in production
   int stage_out;                    // 1: epilogue transposes through smem so stores are whole 128-byte row segments
 };
@@ -201,6 +203,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+template <int V> struct Mode { static constexpr int value = V; };
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams P) {
@@ -232,6 +236,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tmem_cols = (need_cols <= 32) ? 32 : (need_cols <= 64) ? 64 : (need_cols <= 128) ? 128
                         : (need_cols <= 256) ? 256 : 512;
   const int chains_x = P.chains - P.chains_hi;       // chains reserved for the cross terms
+  // tf32 mode: the splitter warps have nothing to split and join the epilogue (three warps per TMEM
+  // lane quarter take the 32-column chunks round-robin; the epilogue is a latency chain per chunk)
+  const int n_epi = P.n_epi;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < P.stages; ++s) {
@@ -239,7 +246,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(empty_bar(s), 1);
       mbar_init(split_bar(s), kSplitThreads / 32);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * n_epi); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -323,76 +330,89 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t x_span = static_cast<uint32_t>(chains_x) * cstride;
     const int precise = P.precise;
     const uint32_t leader = elect_one() ? 1u : 0u;
-    int stage = 0, as = 0;
-    uint32_t phase = 0, aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int r = t % tiles_per_group;
-      const int sp = r % P.splits;
-      const int kb0 = sp * P.kb_per_split;
-      const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
-      mbar_wait(tempty_bar(as), aphase ^ 1u);
-      tc_fence_after();
-      const uint32_t tmem_t = tmem_base + static_cast<uint32_t>(as * P.chains) * cstride;
-      // chains are visited round-robin; a chain accumulates from its second visit on
-      uint32_t hi_col = 0, x_col = 0;
-      int hi_fresh = P.chains_hi, x_fresh = chains_x;   // chains not yet written in this tile
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(precise ? split_bar(stage) : full_bar(stage), phase);
+    // The loop is instantiated once per mode: every uniform branch inside the k-block loop sits on
+    // the kernel's critical path (the issue loop paces the tf32 mode — a four-way mode test per
+    // k-step cost 15 % of the fc1 time).  MODE 0: tf32, 1: 3xTF32, 2: 3xTF32 with stacked A,
+    // 3: generic with the BDP_GEMM_DEBUG experiment bits.
+    auto issue_loop = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int r = t % tiles_per_group;
+        const int sp = r % P.splits;
+        const int kb0 = sp * P.kb_per_split;
+        const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t sa = base + stage * stage_bytes;
-        uint64_t ad = a_desc0 | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
-        uint64_t bd = b_desc0 | static_cast<uint64_t>(((sa + a_bytes) & 0x3FFFFu) >> 4);
+        const uint32_t tmem_t = tmem_base + static_cast<uint32_t>(as * P.chains) * cstride;
+        // chains are visited round-robin; a chain accumulates from its second visit on
+        uint32_t hi_col = 0, x_col = 0;
+        int hi_fresh = P.chains_hi, x_fresh = chains_x;   // chains not yet written in this tile
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait((MODE == 0 || (MODE == 3 && !precise)) ? full_bar(stage) : split_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * stage_bytes;
+          uint64_t ad = a_desc0 | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
+          uint64_t bd = b_desc0 | static_cast<uint64_t>(((sa + a_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint32_t d_hi = tmem_t + hi_col;
-          if (P.debug & 4) {
-          } else if (precise && (P.debug & 2)) {
-            umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
-          } else if (P.stack) {
-            // A = [A_hi rows ; A_lo rows]: lanes < a_rows get A_hi*B, lanes a_rows.. get A_lo*B
-            if (x_span != 0) {
-              const uint32_t d_x = tmem_t + hi_span + x_col;
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint32_t d_hi = tmem_t + hi_col;
+            const bool stacked = MODE == 2 || (MODE == 3 && P.stack);
+            const bool three = MODE == 1 || (MODE == 3 && precise && !P.stack);
+            if (MODE == 3 && (P.debug & 4)) {
+            } else if (MODE == 3 && precise && (P.debug & 2)) {
               umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
-              umma_tf32(d_x, ad, bd + b_lo16, idesc, x_fresh <= 0, leader);
-              --x_fresh;
-              x_col += cstride;
-              if (x_col == x_span) x_col = 0;
+            } else if (stacked) {
+              // A = [A_hi rows ; A_lo rows]: lanes < a_rows get A_hi*B, lanes a_rows.. get A_lo*B
+              if (x_span != 0) {
+                const uint32_t d_x = tmem_t + hi_span + x_col;
+                umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
+                umma_tf32(d_x, ad, bd + b_lo16, idesc, x_fresh <= 0, leader);
+                --x_fresh;
+                x_col += cstride;
+                if (x_col == x_span) x_col = 0;
+              } else {
+                umma_tf32(d_hi, ad, bd + b_lo16, idesc, hi_fresh <= 0, leader);
+                umma_tf32(d_hi, ad, bd, idesc, 1u, leader);
+              }
+            } else if (three) {
+              if (x_span != 0) {
+                const uint32_t d_x = tmem_t + hi_span + x_col;
+                umma_tf32(d_x, ad + lo16, bd, idesc, x_fresh <= 0, leader);
+                umma_tf32(d_x, ad, bd + lo16, idesc, 1u, leader);
+                umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
+                --x_fresh;
+                x_col += cstride;
+                if (x_col == x_span) x_col = 0;
+              } else {                                     // a single chain takes everything
+                umma_tf32(d_hi, ad + lo16, bd, idesc, hi_fresh <= 0, leader);
+                umma_tf32(d_hi, ad, bd + lo16, idesc, 1u, leader);
+                umma_tf32(d_hi, ad, bd, idesc, 1u, leader);
+              }
             } else {
-              umma_tf32(d_hi, ad, bd + b_lo16, idesc, hi_fresh <= 0, leader);
-              umma_tf32(d_hi, ad, bd, idesc, 1u, leader);
-            }
-          } else if (precise) {
-            if (x_span != 0) {
-              const uint32_t d_x = tmem_t + hi_span + x_col;
-              umma_tf32(d_x, ad + lo16, bd, idesc, x_fresh <= 0, leader);
-              umma_tf32(d_x, ad, bd + lo16, idesc, 1u, leader);
               umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
-              --x_fresh;
-              x_col += cstride;
-              if (x_col == x_span) x_col = 0;
-            } else {                                     // a single chain takes everything
-              umma_tf32(d_hi, ad + lo16, bd, idesc, hi_fresh <= 0, leader);
-              umma_tf32(d_hi, ad, bd + lo16, idesc, 1u, leader);
-              umma_tf32(d_hi, ad, bd, idesc, 1u, leader);
             }
-          } else {
-            umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
+            --hi_fresh;
+            hi_col += cstride;
+            if (hi_col == hi_span) hi_col = 0;
+            ad += a_kstep16;
+            bd += b_kstep16;
           }
-          --hi_fresh;
-          hi_col += cstride;
-          if (hi_col == hi_span) hi_col = 0;
-          ad += a_kstep16;
-          bd += b_kstep16;
+          umma_commit(empty_bar(stage), leader);                 // frees the smem slot when the MMAs retire
+          if (kb == kb1 - 1) umma_commit(tfull_bar(as), leader); // accumulator complete -> epilogue
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage), leader);                 // frees the smem slot when the MMAs retire
-        if (kb == kb1 - 1) umma_commit(tfull_bar(as), leader); // accumulator complete -> epilogue
-        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        if (++as == P.acc_stages) { as = 0; aphase ^= 1u; }
       }
-      if (++as == P.acc_stages) { as = 0; aphase ^= 1u; }
-    }
-  } else if (warp >= 8) {
+    };
+    if (P.debug) issue_loop(Mode<3>{});
+    else if (!precise) issue_loop(Mode<0>{});
+    else if (P.stack) issue_loop(Mode<2>{});
+    else issue_loop(Mode<1>{});
+  } else if (warp >= 8 && warp < 8 + P.split_warps) {
     // ===== operand splitters (precise mode): x -> hi = tf32(x) in place, lo = tf32(x - hi) =====
-    if (P.precise) {
+    {
       const int tid = threadIdx.x - 8 * 32;
       int stage = 0;
       uint32_t phase = 0;
@@ -447,9 +467,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if ((warp >= 4 && warp < 8) ||
+             (warp >= 8 + P.split_warps && warp < 8 + P.split_warps + 4 * (P.n_epi - 1))) {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;                            // TMEM lane quarter of this warp
+    const int e = warp < 8 ? 0 : 1 + ((warp - 8 - P.split_warps) >> 2);   // which of the quarter's n_epi warps
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -470,7 +492,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          (kBK / kUmmaK);
       const int used_hi = min(P.chains_hi, nsteps);
       const int used_x = (P.precise && chains_x > 0) ? min(chains_x, nsteps) : 0;
-      for (int c = 0; c * 32 < P.BN; ++c) {
+      for (int c = e; c * 32 < P.BN; c += n_epi) {
         if (n0 + c * 32 >= P.N) break;                 // warp-uniform
         const bool full = c * 32 + 32 <= P.BN;         // else: 16-column tail (BN = odd multiple of 16)
         uint32_t v[32];
@@ -515,7 +537,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // Big outputs (wgrad: 197 MB): lane r holds 32 columns of ROW r, so a direct store writes
           // 32 scattered 16-byte pieces per instruction and every 32-byte sector twice.  Transposed
           // through shared memory each instruction writes four whole 128-byte row segments.
-          const uint32_t tile = epi_base + static_cast<uint32_t>(q) * (32 * kEpiPitch * 4);
+          const uint32_t tile = epi_base + static_cast<uint32_t>(e * 4 + q) * (32 * kEpiPitch * 4);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (lane * kEpiPitch + 4 * j) * 4),
@@ -731,6 +753,14 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   P.a_bytes = a_major ? (P.a_rows / 32) * 4096
                       : ((P.stack ? 2 : 1) * P.a_rows * kBK * 4 + 1023) / 1024 * 1024;
   if (P.stack) P.stage_out = 0;
+  // Warps 8-15: operand splitters in precise mode, otherwise free.  The epilogue is a latency chain
+  // per 32-column chunk (tcgen05.ld -> shared-memory transpose -> stores), so in tf32 mode four of the
+  // free warps take every second chunk of their TMEM lane quarter (fc1 wgrad 52 -> 37 us on the same
+  // box; a third set did not add anything).  In precise mode the second staging buffer does not fit
+  // next to two 96 KB operand stages, so the epilogue stays with warps 4-7.
+  P.split_warps = precise ? 8 : 0;
+  P.n_epi = precise ? 1 : 2;
+  { const char* e = getenv("BDP_GEMM_EPI_WARPS"); if (e && e[0] == '1') P.n_epi = 1; }   // experiments
   const long long total = (long long)G * P.m_tiles * P.n_tiles * P.splits;
   long long grid = sms;
   if (grid > total) grid = total;
@@ -748,7 +778,7 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   // The MMA always reads 128 A rows from shared memory (rows >= a_rows produce discarded D rows), so
   // a shrunk A reservation is followed by `slack` bytes that keep those reads inside the allocation.
   const size_t slack = (size_t)(kABytes - P.a_bytes);
-  const size_t fixed = 1024 + 8 * (3 * kMaxStages + 4) + slack + (P.stage_out ? kEpiBytes : P.stack ? kStackEpiBytes : 0);
+  const size_t fixed = 1024 + 8 * (3 * kMaxStages + 4) + slack + (P.stage_out ? kEpiBytes * P.n_epi : P.stack ? kStackEpiBytes : 0);
   int stages = (int)((224 * 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   { const char* e = getenv("BDP_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }
