@@ -70,9 +70,7 @@ struct GemmParams {
   int a_bytes;                      // smem reserved for the A tile of one stage (1 KB multiple)
   int acc_stages;                   // TMEM accumulator stages (2 only when a CTA runs >1 tile)
   int stack;                        // precise mode, batch-side A with <= 64 rows: A_lo rows stacked under A_hi (2 MMAs per k-step)
-  int split_warps;                  // operand-splitter warps: 8 (warps 8-15) in precise mode, else 0
   int n_epi;                        // epilogue warps per TMEM lane quarter: warps 4-7, plus the warps after the splitters
-  int debug;                        // timing experiments only (BDP_GEMM_DEBUG), 0 in production
   int stage_out;                    // 1: epilogue transposes through smem so stores are whole 128-byte row segments
 };
 
@@ -203,8 +201,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-template <int V> struct Mode { static constexpr int value = V; };
-
+// One kernel per mode (MODE 0: tf32, 1: 3xTF32, 2: 3xTF32 with stacked A): each carries only its own
+// roles and loops.  The producer / issuer / splitter / epilogue warps run different code at the same
+// time, and both the uniform mode tests inside the k-block loop and the sheer code size of a single
+// generic kernel showed up in the timings (tf32 fc1 45 us generic vs 37 us specialised).
+template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams P) {
@@ -217,9 +218,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t a_tx = static_cast<uint32_t>(P.a_rows) * kBK * 4;   // A bytes TMA really delivers
   // lo copies (precise mode): of the whole [A | B] footprint right after it, or — stacked mode — the
   // A_lo rows directly under the A_hi rows (inside a_bytes) and B_lo after B
-  const uint32_t stage_bytes = P.stack ? a_bytes + 2u * b_bytes : P.precise ? 2u * tile_bytes : tile_bytes;
-  const uint32_t a_lo_off = P.stack ? a_tx : tile_bytes;      // from the A tile
-  const uint32_t b_lo_off = P.stack ? b_bytes : tile_bytes;   // from the B tile
+  constexpr bool kPrecise = MODE != 0, kStack = MODE == 2;
+  const uint32_t stage_bytes = kStack ? a_bytes + 2u * b_bytes : kPrecise ? 2u * tile_bytes : tile_bytes;
+  const uint32_t a_lo_off = kStack ? a_tx : tile_bytes;      // from the A tile
+  const uint32_t b_lo_off = kStack ? b_bytes : tile_bytes;   // from the B tile
   const uint32_t bar_base = base + P.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -328,14 +330,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t cstride = static_cast<uint32_t>(P.cstride);
     const uint32_t hi_span = static_cast<uint32_t>(P.chains_hi) * cstride;
     const uint32_t x_span = static_cast<uint32_t>(chains_x) * cstride;
-    const int precise = P.precise;
     const uint32_t leader = elect_one() ? 1u : 0u;
-    // The loop is instantiated once per mode: every uniform branch inside the k-block loop sits on
-    // the kernel's critical path (the issue loop paces the tf32 mode — a four-way mode test per
-    // k-step cost 15 % of the fc1 time).  MODE 0: tf32, 1: 3xTF32, 2: 3xTF32 with stacked A,
-    // 3: generic with the BDP_GEMM_DEBUG experiment bits.
-    auto issue_loop = [&](auto mode_tag) {
-      constexpr int MODE = decltype(mode_tag)::value;
+    {
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -350,7 +346,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t hi_col = 0, x_col = 0;
         int hi_fresh = P.chains_hi, x_fresh = chains_x;   // chains not yet written in this tile
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait((MODE == 0 || (MODE == 3 && !precise)) ? full_bar(stage) : split_bar(stage), phase);
+          mbar_wait(kPrecise ? split_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + stage * stage_bytes;
           uint64_t ad = a_desc0 | static_cast<uint64_t>((sa & 0x3FFFFu) >> 4);
@@ -358,12 +354,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint32_t d_hi = tmem_t + hi_col;
-            const bool stacked = MODE == 2 || (MODE == 3 && P.stack);
-            const bool three = MODE == 1 || (MODE == 3 && precise && !P.stack);
-            if (MODE == 3 && (P.debug & 4)) {
-            } else if (MODE == 3 && precise && (P.debug & 2)) {
-              umma_tf32(d_hi, ad, bd, idesc, hi_fresh <= 0, leader);
-            } else if (stacked) {
+            if (kStack) {
               // A = [A_hi rows ; A_lo rows]: lanes < a_rows get A_hi*B, lanes a_rows.. get A_lo*B
               if (x_span != 0) {
                 const uint32_t d_x = tmem_t + hi_span + x_col;
@@ -376,7 +367,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_tf32(d_hi, ad, bd + b_lo16, idesc, hi_fresh <= 0, leader);
                 umma_tf32(d_hi, ad, bd, idesc, 1u, leader);
               }
-            } else if (three) {
+            } else if (kPrecise) {
               if (x_span != 0) {
                 const uint32_t d_x = tmem_t + hi_span + x_col;
                 umma_tf32(d_x, ad + lo16, bd, idesc, x_fresh <= 0, leader);
@@ -405,12 +396,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (++as == P.acc_stages) { as = 0; aphase ^= 1u; }
       }
-    };
-    if (P.debug) issue_loop(Mode<3>{});
-    else if (!precise) issue_loop(Mode<0>{});
-    else if (P.stack) issue_loop(Mode<2>{});
-    else issue_loop(Mode<1>{});
-  } else if (warp >= 8 && warp < 8 + P.split_warps) {
+    }
+  } else if (kPrecise && warp >= 8) {
     // ===== operand splitters (precise mode): x -> hi = tf32(x) in place, lo = tf32(x - hi) =====
     {
       const int tid = threadIdx.x - 8 * 32;
@@ -430,7 +417,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sa = base + stage * stage_bytes;
           // four vectors per thread in flight: the loop is latency-bound (shared-memory round trip
           // per iteration), not bandwidth-bound
-          for (int i0 = tid; i0 < ((P.debug & 1) ? 0 : nvec); i0 += 4 * kSplitThreads) {
+          for (int i0 = tid; i0 < nvec; i0 += 4 * kSplitThreads) {
             uint32_t x[4][4];
             uint32_t off[4], lo_off[4];
 #pragma unroll
@@ -460,18 +447,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          if (!(P.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(split_bar(stage));
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if ((warp >= 4 && warp < 8) ||
-             (warp >= 8 + P.split_warps && warp < 8 + P.split_warps + 4 * (P.n_epi - 1))) {
+  } else if ((warp >= 4 && warp < 8) || (!kPrecise && warp >= 8 && warp < 8 + 4 * (P.n_epi - 1))) {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;                            // TMEM lane quarter of this warp
-    const int e = warp < 8 ? 0 : 1 + ((warp - 8 - P.split_warps) >> 2);   // which of the quarter's n_epi warps
+    const int e = warp < 8 ? 0 : 1 + ((warp - 8) >> 2);   // which of the quarter's n_epi warps
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -491,7 +477,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int nsteps = (min(P.kb_total, sp * P.kb_per_split + P.kb_per_split) - sp * P.kb_per_split) *
                          (kBK / kUmmaK);
       const int used_hi = min(P.chains_hi, nsteps);
-      const int used_x = (P.precise && chains_x > 0) ? min(chains_x, nsteps) : 0;
+      const int used_x = (kPrecise && chains_x > 0) ? min(chains_x, nsteps) : 0;
       for (int c = e; c * 32 < P.BN; c += n_epi) {
         if (n0 + c * 32 >= P.N) break;                 // warp-uniform
         const bool full = c * 32 + 32 <= P.BN;         // else: 16-column tail (BN = odd multiple of 16)
@@ -506,7 +492,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int nb = n0 + c * 32;
         const int wcols = full ? 32 : 16;
-        if (P.stack) {
+        if (kStack) {
           // rows a_rows .. 2*a_rows-1 hold A_lo * (B_hi + B_lo): hand them to the rows above through
           // shared memory (the two row sets can sit in different warps)
           const int rr = q * 32 + lane;
@@ -734,10 +720,6 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   P.stage_out = (c_layout == 0 && M >= 64 && N % 4 == 0 && ldc % 4 == 0 && c_gstride % 4 == 0 &&
                  c_sstride % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
   P.precise = precise ? 1 : 0;
-  // Timing experiments (results are WRONG with any bit set; DESIGN.md 4.1 uses them to attribute the
-  // per-k-block time): 1 = splitters skip their loads/stores, 2 = 3xTF32 issues only the hi*hi MMA,
-  // 4 = no MMAs at all (TMA + barriers only), 8 = splitters skip the async-proxy fence.
-  { const char* e = getenv("BDP_GEMM_DEBUG"); P.debug = e ? atoi(e) : 0; }
   {
     static const int no_rotate = [] { const char* e = getenv("BDP_GEMM_NO_ROTATE"); return (e && e[0] == '1') ? 1 : 0; }();
     P.k_rotate = no_rotate ? 0 : 1;
@@ -758,7 +740,6 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   // free warps take every second chunk of their TMEM lane quarter (fc1 wgrad 52 -> 37 us on the same
   // box; a third set did not add anything).  In precise mode the second staging buffer does not fit
   // next to two 96 KB operand stages, so the epilogue stays with warps 4-7.
-  P.split_warps = precise ? 8 : 0;
   P.n_epi = precise ? 1 : 2;
   { const char* e = getenv("BDP_GEMM_EPI_WARPS"); if (e && e[0] == '1') P.n_epi = 1; }   // experiments
   const long long total = (long long)G * P.m_tiles * P.n_tiles * P.splits;
@@ -798,17 +779,19 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   else st = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, gb, (uint64_t)b_ld, b_gs, 32, kBK, true);
   if (st != BDP_OK) return st;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  const int mode = !precise ? 0 : P.stack ? 2 : 1;
+  void (*kern)(CUtensorMap, CUtensorMap, GemmParams) =
+      mode == 0 ? gemm_tf32_kernel<0> : mode == 1 ? gemm_tf32_kernel<1> : gemm_tf32_kernel<2>;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[mode]) {
     cudaFuncAttributes fa;
-    BDP_CUDA_CALL(cudaFuncGetAttributes(&fa, gemm_tf32_kernel));
+    BDP_CUDA_CALL(cudaFuncGetAttributes(&fa, kern));
     // opt-in limit is 227 KB per block INCLUDING the kernel's static shared memory
-    BDP_CUDA_CALL(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BDP_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024 - (int)fa.sharedSizeBytes));
-    attr_set = true;
+    attr_set[mode] = true;
   }
-  gemm_tf32_kernel<<<(unsigned)grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tmA, tmB, P);
+  kern<<<(unsigned)grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, P);
   BDP_CUDA_CHECK_LAUNCH("gemm_tf32_kernel");
   return BDP_OK;
 }
