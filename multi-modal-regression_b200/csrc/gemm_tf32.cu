@@ -752,6 +752,10 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   P.chains = 512 / (P.acc_stages * P.cstride);
   if (P.chains < 1) P.chains = 1;
   if (P.chains > 8) P.chains = 8;
+  // tf32 mode rounds the operands to 10 mantissa bits (~1e-3): the accumulator drift of a single
+  // chain (1.6e-5 of the result scale at K = 2048) is irrelevant there, and one chain means one
+  // tcgen05.ld per chunk in the epilogue instead of up to five
+  { const char* e = getenv("BDP_GEMM_TF32_CHAINS"); if (!precise && !(e && e[0] == '1')) P.chains = 1; }
   P.chains_hi = (precise && P.chains >= 2) ? P.chains - (P.chains >= 4 ? P.chains / 4 : 1) : P.chains;
 
   const size_t stage_bytes = P.stack ? (size_t)P.a_bytes + 2 * (size_t)bn * kBK * 4
