@@ -156,6 +156,16 @@ int bdp_assign_nearest(const void* x, int x_dtype, int64_t N, int d, const doubl
 int bdp_assign_quatdot(const void* q, int q_dtype, int64_t N, const double* keys, int K,
                        int64_t* bin, float* residual, void* stream);
 
+/* Soft assignment: p[n,k] = exp(-gamma ||x_n - c_k||^2) / sum_j exp(-gamma ||x_n - c_j||^2)
+ * (exp / normalise without max subtraction, as numpy does it in the reference), residual[n] =
+ * x_n - sum_k p[n,k] c_k; evaluated in fp64, stored as fp32.
+ * x [N,d] fp32|fp64 (x_dtype), d = 3|4, centers [K,d] fp64 -> p [N,K] fp32 (NULL: skip),
+ * residual [N,d] fp32 (NULL: skip).
+ * binDeltaGenerators.py:104-108 (XPBDGeneratorQ, gamma = 10); dataGenerators.py:155-157, 166;
+ * ablationFunctions.py:146-150 */
+int bdp_assign_soft(const void* x, int x_dtype, int64_t N, int d, const double* centers, int K,
+                    double gamma, float* p, float* residual, void* stream);
+
 /* Riemannian residual of RBDGenerator: rot[n] = exp([x_n]x) (axisAngle.get_R), residual[n] =
  * log(key_rot[bin_n]^T rot[n]) (axisAngle.get_y, zero vector when the axis norm <= 1e-6), all
  * evaluated in fp64 and stored as fp32 (the reference's `.float()`).

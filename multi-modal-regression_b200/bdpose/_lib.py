@@ -22,6 +22,7 @@ _p = C.c_void_p
 _i64 = C.c_int64
 _int = C.c_int
 _f32 = C.c_float
+_f64 = C.c_double
 
 # name -> (restype, argtypes): one entry per symbol declared in include/bdpose.h
 SIGNATURES = {
@@ -38,6 +39,7 @@ SIGNATURES = {
     "bdp_error_stats": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p, _p, _i64, _p]),
     "bdp_assign_nearest": (_int, [_p, _int, _i64, _int, _p, _int, _p, _p, _p, _p, _p]),
     "bdp_assign_quatdot": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p]),
+    "bdp_assign_soft": (_int, [_p, _int, _i64, _int, _p, _int, _f64, _p, _p, _p]),
     "bdp_riemannian_residual": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p, _p]),
     "bdp_convert_axis_angle": (_int, [_p, _i64, _p, _p, _p]),
     "bdp_euler_to_pose": (_int, [_p, _i64, _p, _p, _p]),

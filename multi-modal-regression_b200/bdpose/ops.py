@@ -414,6 +414,25 @@ def assign_quatdot(q, keys):
     return b, res
 
 
+def assign_soft(x, centers, gamma=10.0, want_p=True, want_residual=True):
+    """p = softmax_k(-gamma ||x - c_k||^2) (exp / normalise in fp64), residual = x - p @ centers
+    (binDeltaGenerators.py:104-108).  x [N,d] fp32|fp64, d = 3|4 -> (p [N,K] fp32, residual [N,d] fp32)."""
+    _need_cuda(x, centers)
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.double()
+    centers = centers.double().contiguous()
+    K, d = centers.shape
+    x = x.reshape(-1, d).contiguous()
+    N = x.shape[0]
+    p = torch.empty((N, K), dtype=torch.float32, device=x.device) if want_p else None
+    res = torch.empty((N, d), dtype=torch.float32, device=x.device) if want_residual else None
+    with torch.cuda.device(x.device):
+        st = L.lib().bdp_assign_soft(L.ptr(x), _dtype_code(x), N, d, L.ptr(centers), K, float(gamma),
+                                     L.ptr(p), L.ptr(res), L.stream_ptr())
+    L.check(st, "bdp_assign_soft")
+    return p, res
+
+
 def euler_to_pose(euler_deg, want_aa=True, want_quat=False):
     """(az, el, ct) in degrees [N,3] -> axis-angle [N,3] and / or quaternion [N,4], fp64
     (helperFunctions.rotation_matrix + axisAngle.get_y / quaternion.get_y)."""

@@ -115,13 +115,11 @@ def assign_labels_riemannian(y, centers, key_rot=None):
 
 def assign_soft_labels(y, centers, gamma=10.0):
     """XPBDGeneratorQ targets (binDeltaGenerators.py:104-108): p = softmax_k(-gamma ||y-c_k||^2)
-    (the reference's exp/normalise), res = y - p @ centers.  fp64 on the device, [N,K] output."""
-    y = _cuda(y, torch.float64)
+    (the reference's exp/normalise), res = y - p @ centers.  One fused kernel (bdp_assign_soft):
+    fp64 arithmetic on the device, (p [N,K] fp32, res [N,d] fp32) out."""
+    y = _cuda(y)
     c = _cuda(centers, torch.float64)
-    d2 = ((y[:, None, :] - c[None, :, :]) ** 2).sum(2)
-    p = torch.exp(-gamma * d2)
-    p = p / p.sum(1, keepdim=True)
-    return p.float(), (y - p @ c).float()
+    return ops.assign_soft(y, c, gamma)
 
 
 def _cuda(a, dtype=None):

@@ -1617,3 +1617,99 @@ extern "C" int bdp_euler_to_pose(const double* euler_deg, int64_t N, double* aa,
   BDP_CUDA_CHECK_LAUNCH("euler_pose_kernel");
   return BDP_OK;
 }
+
+// ---- (c4) soft assignment -------------------------------------------------------------------------
+// p[n,k] = exp(-gamma ||x_n - c_k||^2) / sum_j exp(-gamma ||x_n - c_j||^2), res[n] = x_n - sum_k p[n,k] c_k,
+// all in fp64 like numpy/scipy in the reference (exp/normalise without max subtraction:
+// binDeltaGenerators.py:104-108; dataGenerators.py:155-157, 166), stored as fp32 (`.float()`).
+// One warp per row, lanes over the keys: the [N,K] output goes out as whole 128-byte lines, the
+// weights are recomputed in the second pass instead of being parked (K can be 4096).
+namespace {
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) soft_assign_kernel(const T* __restrict__ x,
+                                                          const double* __restrict__ centers,
+                                                          int64_t N, int K, double gamma, int c_in_smem,
+                                                          float* __restrict__ p, float* __restrict__ res) {
+  extern __shared__ __align__(16) unsigned char soft_smem[];
+  double* s_c = reinterpret_cast<double*>(soft_smem);
+  if (c_in_smem) {
+    for (int i = threadIdx.x; i < K * D; i += blockDim.x) s_c[i] = __ldg(centers + i);
+    __syncthreads();
+  }
+  const double* c = c_in_smem ? s_c : centers;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < N; row += warps) {
+    double y[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) y[k] = (double)x[row * D + k];
+    double sum = 0.0;
+    for (int j = lane; j < K; j += 32) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double df = y[k] - c[(int64_t)j * D + k];
+        d2 += df * df;
+      }
+      sum += exp(-gamma * d2);
+    }
+    sum = warp_sum(sum);                                // butterfly: the same value in every lane
+    double acc[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] = 0.0;
+    for (int j = lane; j < K; j += 32) {
+      double d2 = 0.0;
+      double cj[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        cj[k] = c[(int64_t)j * D + k];
+        const double df = y[k] - cj[k];
+        d2 += df * df;
+      }
+      const double pk = exp(-gamma * d2) / sum;
+      if (p) p[row * K + j] = (float)pk;
+#pragma unroll
+      for (int k = 0; k < D; ++k) acc[k] += pk * cj[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] = warp_sum(acc[k]);
+    if (res && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) res[row * D + k] = (float)(y[k] - acc[k]);
+    }
+  }
+}
+
+template <typename T, int D>
+int launch_soft_assign(const void* x, const double* centers, int64_t N, int K, double gamma, float* p,
+                       float* res, cudaStream_t st) {
+  int64_t blocks = ceil_div64(N, 8);                    // 8 warps (rows) per block
+  const int64_t cap = (int64_t)bdp_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  const size_t bytes = (size_t)K * D * sizeof(double);
+  const int in_smem = bytes <= 48 * 1024 ? 1 : 0;       // larger dictionaries are read through L1/L2
+  soft_assign_kernel<T, D><<<(unsigned)blocks, 256, in_smem ? bytes : 0, st>>>(
+      reinterpret_cast<const T*>(x), centers, N, K, gamma, in_smem, p, res);
+  BDP_CUDA_CHECK_LAUNCH("soft_assign_kernel");
+  return BDP_OK;
+}
+
+}  // namespace
+
+extern "C" int bdp_assign_soft(const void* x, int x_dtype, int64_t N, int d, const double* centers, int K,
+                               double gamma, float* p, float* residual, void* stream) {
+  BDP_REQUIRE(N >= 0, "assign_soft: N < 0");
+  if (N == 0) return BDP_OK;
+  BDP_REQUIRE(x && centers, "assign_soft: NULL input");
+  BDP_REQUIRE(d == 3 || d == 4, "assign_soft: d must be 3 or 4 (got %d)", d);
+  BDP_REQUIRE(K >= 1 && K <= 65536, "assign_soft: K out of range (%d)", K);
+  BDP_REQUIRE(x_dtype == BDP_F32 || x_dtype == BDP_F64, "assign_soft: x_dtype %d", x_dtype);
+  BDP_REQUIRE(p || residual, "assign_soft: no output requested");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x_dtype == BDP_F32)
+    return d == 3 ? launch_soft_assign<float, 3>(x, centers, N, K, gamma, p, residual, st)
+                  : launch_soft_assign<float, 4>(x, centers, N, K, gamma, p, residual, st);
+  return d == 3 ? launch_soft_assign<double, 3>(x, centers, N, K, gamma, p, residual, st)
+                : launch_soft_assign<double, 4>(x, centers, N, K, gamma, p, residual, st);
+}

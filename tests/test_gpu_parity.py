@@ -586,3 +586,23 @@ def test_learn_dictionary_cli_synthetic(cuda, tmp_path):
     assert km.n_clusters == 32 and km.cluster_centers_.shape == (32, 3)
     assert np.all(np.linalg.norm(km.cluster_centers_, axis=1) <= np.pi + 1e-9)
     assert km.predict(km.cluster_centers_.astype(np.float32)).tolist() == list(range(32))
+
+
+@pytest.mark.parametrize("N,K,d,dt", [(5000, 1000, 3, np.float32), (777, 16, 4, np.float64),
+                                      (300, 3000, 4, np.float32), (1, 1, 3, np.float32)])
+def test_soft_assignment_vs_oracle(cuda, N, K, d, dt):
+    """Row c4: p = exp(-g d^2) / sum, res = y - p @ C (binDeltaGenerators.py:104-108) against the
+    numpy restatement; K = 3000, d = 4 takes the path that reads the dictionary from global memory."""
+    from bdpose import ops
+    rng = np.random.RandomState(N + K)
+    c = rng.randn(K, d) * 0.7
+    y = (c[rng.randint(0, K, N)] + 0.2 * rng.randn(N, d)).astype(dt)
+    p_ref, r_ref = O.soft_assign(y, c, gamma=10.0)
+    p, r = ops.assign_soft(torch.from_numpy(y).to(cuda), torch.from_numpy(c).to(cuda), 10.0)
+    assert p.dtype == torch.float32 and r.dtype == torch.float32
+    close(p, np.asarray(p_ref, dtype=np.float32), rtol=1e-5, atol=1e-30)
+    close(r, np.asarray(r_ref, dtype=np.float32), rtol=1e-5, atol=1e-6)
+    close(p.sum(1), np.ones(N), rtol=1e-5)
+    # residual only / probabilities only
+    p2, r2 = ops.assign_soft(torch.from_numpy(y).to(cuda), torch.from_numpy(c).to(cuda), 10.0, want_p=False)
+    assert p2 is None and torch.equal(r2, r)
