@@ -786,14 +786,18 @@ extern "C" int bdp_gemm_tf32(const float* A, int a_major, int64_t a_ld, int64_t 
   const int mode = !precise ? 0 : P.stack ? 2 : 1;
   void (*kern)(CUtensorMap, CUtensorMap, GemmParams) =
       mode == 0 ? gemm_tf32_kernel<0> : mode == 1 ? gemm_tf32_kernel<1> : gemm_tf32_kernel<2>;
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[mode]) {
+  // the opt-in is per device: a process that drives several GPUs sets it once on each
+  static bool attr_set[3][64] = {};
+  int dev = 0;
+  BDP_CUDA_CALL(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  if (!tracked || !attr_set[mode][dev]) {
     cudaFuncAttributes fa;
     BDP_CUDA_CALL(cudaFuncGetAttributes(&fa, kern));
     // opt-in limit is 227 KB per block INCLUDING the kernel's static shared memory
     BDP_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024 - (int)fa.sharedSizeBytes));
-    attr_set[mode] = true;
+    if (tracked) attr_set[mode][dev] = true;
   }
   kern<<<(unsigned)grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, P);
   BDP_CUDA_CHECK_LAUNCH("gemm_tf32_kernel");
