@@ -578,8 +578,9 @@ class HeadFamily:
     storage) and mode, that head's parameters untouched since the run.  BDPOSE_HEAD_MEMO=0 turns this off (every call then runs as a one-head
     stack)."""
 
-    def __init__(self, lists):
+    def __init__(self, lists, two_layer=False):
         self.lists = lists                 # the nn.ModuleLists, in fc3-group order
+        self.two_layer = two_layer         # res_2layer siblings (Mlp2Stack) instead of 3-layer heads
         self._stack = None
         self._key = None
         self._x_ref = None
@@ -590,17 +591,20 @@ class HeadFamily:
 
     def __deepcopy__(self, memo):
         import copy
-        return HeadFamily([copy.deepcopy(l, memo) for l in self.lists])
+        new = HeadFamily.__new__(HeadFamily)
+        memo[id(self)] = new        # the member modules point back at the family: one copy for all
+        new.__init__([copy.deepcopy(l, memo) for l in self.lists], self.two_layer)
+        return new
 
     def __reduce__(self):
-        return (HeadFamily, (self.lists,))
+        return (HeadFamily, (self.lists, self.two_layer))
 
     def stack(self):
         groups = [list(l) for l in self.lists]
         st = self._stack
         flat = [m for g in groups for m in g]
         if st is None or len(st.heads) != len(flat) or any(a is not b for a, b in zip(st.heads, flat)):
-            st = HeadStack(groups)
+            st = Mlp2Stack(flat) if self.two_layer else HeadStack(groups)
             self._stack = st
             self._key = None
         return st
@@ -621,11 +625,15 @@ class HeadFamily:
             self._pver.get(id(module)) != self._versions(module)
         if fresh:
             st = self.stack()          # membership / storage checks: once per round, not per head
-            self._outs = run_heads_all(st, x, training)
+            if self.two_layer:
+                self._outs = (run_mlp2_all(st, x, training),)
+                self._where = {id(m): (0, j) for j, m in enumerate(st.heads)}
+            else:
+                self._outs = run_heads_all(st, x, training)
+                self._where = {id(m): (gi, j) for gi, g in enumerate(st.groups) for j, m in enumerate(g)}
             self._key, self._x_ref = key, x
             self._pver = {id(m): self._versions(m) for m in st.heads}
             self._served = set()
-            self._where = {id(m): (gi, j) for gi, g in enumerate(st.groups) for j, m in enumerate(g)}
         self._served.add(id(module))
         gi, j = self._where[id(module)]
         return self._outs[gi][:, j, :]

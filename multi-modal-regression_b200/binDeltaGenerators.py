@@ -139,29 +139,45 @@ def _images_all():
     return ImagesAll
 
 
+def euler_from_name(image_name):
+    """(azimuth, elevation, camera tilt) in degrees from an image name of the form
+    <synset>_<model>_a<az>_e<el>_t<ct>_d<dist> — the three angle fields helperFunctions.parse_name
+    returns (helperFunctions.py:24-33): the text between the 2nd..5th underscores, minus the one-letter
+    tag in front of each number."""
+    parts = str(image_name).split('_')
+    if len(parts) < 6:
+        raise ValueError("image name %r does not carry _a<az>_e<el>_t<ct>_d<dist>" % (image_name,))
+    return float(parts[2][1:]), float(parts[3][1:]), float(parts[4][1:])
+
+
+def pose_targets_from_names(list_image_names, tilt_sign=1.0, quaternion=False, dtype=torch.float32):
+    """Pose targets of whole lists of image names: the Euler angles are parsed on the host (strings),
+    Euler -> R -> log map runs for all of them in ONE launch (bdp_euler_to_pose; the reference does it
+    per image in python: dataGenerators.py:55-69).  Returns one [n_i, 3|4] numpy array per list, in
+    `dtype` (float32 = the `.float()` of dataGenerators.py:70)."""
+    sizes = [len(names) for names in list_image_names]
+    eul = np.zeros((sum(sizes), 3))
+    r = 0
+    for names in list_image_names:
+        for name in names:
+            az, el, ct = euler_from_name(name)
+            eul[r] = (az, el, tilt_sign * ct)
+            r += 1
+    aa, q = ops.euler_to_pose(torch.from_numpy(eul).cuda(), want_aa=not quaternion, want_quat=quaternion)
+    y = (q if quaternion else aa).to(dtype).cpu().numpy()
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return [y[off[i]:off[i + 1]] for i in range(len(sizes))]
+
+
 def _pose_targets(ds):
     """Pose target of every image of an ImagesAll dataset, as the float32 rows its __getitem__
     produces (dataGenerators.py:55-69), grouped per class."""
-    from helperFunctions import parse_name
     if ds.db_type not in ('real', 'render'):
         raise NameError('Unknown db_type passed')
     if ds.ydata_type not in ('axis_angle', 'quaternion'):
         raise NameError('Uknown ydata_type passed')
-    sign = 1.0 if ds.db_type == 'real' else -1.0
-    sizes = [len(names) for names in ds.list_image_names]
-    eul = np.zeros((sum(sizes), 3))
-    r = 0
-    for names in ds.list_image_names:          # string parsing stays on the host
-        for name in names:
-            _, _, az, el, ct, _ = parse_name(name)
-            eul[r] = (az, el, sign * ct)
-            r += 1
-    # Euler -> R -> log map for the whole dataset in one launch (the reference: per image in python)
-    quat = ds.ydata_type == 'quaternion'
-    aa, q = ops.euler_to_pose(torch.from_numpy(eul).cuda(), want_aa=not quat, want_quat=quat)
-    y = (q if quat else aa).float().cpu().numpy()        # `.float()` as dataGenerators.py:70
-    off = np.concatenate([[0], np.cumsum(sizes)])
-    return [y[off[i]:off[i + 1]] for i in range(len(sizes))]
+    return pose_targets_from_names(ds.list_image_names, 1.0 if ds.db_type == 'real' else -1.0,
+                                   ds.ydata_type == 'quaternion')
 
 
 class _LabelTable:

@@ -259,7 +259,9 @@ class RelaXedProbabilisticMultiresLossQ(RelaXedProbabilisticLossQ):
 
 
 class loss_m2(nn.Module):
-    """CE + alpha * MSE(residual, ydata_res[:, :, argmax score]) — binDeltaLosses.py:280-297"""
+    """CE + alpha * MSE(residual, ydata_res[b, argmax score_b, :]) — binDeltaLosses.py:280-297: the
+    reference's `bmm(ytrue[1].permute(0, 2, 1), onehot[B, K, 1])` picks, per sample, the row of the
+    per-bin residual targets ytrue[1] [B, K, ndim] that belongs to the PREDICTED bin."""
 
     def __init__(self, alpha, num_clusters):
         super().__init__()
@@ -268,7 +270,7 @@ class loss_m2(nn.Module):
 
     def forward(self, ypred, ytrue):
         lc, _, ind = ops.bd_loss(ypred[0], ytrue[0], None, None, None, L.POSE_NONE, False)
-        yres = ytrue[1].gather(2, ind.view(-1, 1, 1).expand(-1, ytrue[1].shape[1], 1)).squeeze(2)
+        yres = ytrue[1].gather(1, ind.view(-1, 1, 1).expand(-1, 1, ytrue[1].shape[2])).squeeze(1)
         lr = ops.pose_loss(ypred[1], yres, L.POSE_MSE)
         return lc + self.alpha * lr
 

@@ -64,7 +64,20 @@ class _mlp2(nn.Module):
         self.fc2 = nn.Linear(N1, Nout)
 
     def forward(self, x):
+        # the C*K sibling delta heads of OneDeltaPerBinModel, called one by one by a script-defined
+        # forward (learnJointCatPoseModel_weighted.py:117-118), run as one fused two-layer stack
+        fam = self.__dict__.get('_family')
+        if fam is not None and _head.MEMO and x.is_cuda:
+            return fam.output_of(self, x, self.training)
         return self.fc2(F.relu(self.bn1(self.fc1(x))))
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
 
 class bin_2layer(_mlp2):
@@ -199,26 +212,32 @@ class OneDeltaPerBinModel(nn.Module):
             self.feature_model = fm
         self.bin_models = nn.ModuleList([bin_3layer(N0, N1, N2, num_clusters) for i in range(self.num_classes)]).cuda()
         self.res_models = nn.ModuleList([res_2layer(N0, N3, ndim) for i in range(self.num_classes * self.num_clusters)]).cuda()
-        object.__setattr__(self, '_stack', None)
-        object.__setattr__(self, '_stack2', None)
+        # sibling families: a script-defined forward that calls the heads one by one
+        # (learnJointCatPoseModel_weighted.py:116-118) still runs each list as one fused stack
+        self._families()
+
+    def _families(self):
+        bins, ress = list(self.bin_models), list(self.res_models)
+        fb = bins[0].__dict__.get('_family') if bins else None
+        if fb is None or len(fb.lists) != 1 or fb.lists[0] is not self.bin_models:
+            fb = _head.HeadFamily([self.bin_models])
+            for m in bins:
+                object.__setattr__(m, '_family', fb)
+        fr = ress[0].__dict__.get('_family') if ress else None
+        if fr is None or len(fr.lists) != 1 or fr.lists[0] is not self.res_models:
+            fr = _head.HeadFamily([self.res_models], two_layer=True)
+            for m in ress:
+                object.__setattr__(m, '_family', fr)
+        return fb, fr
 
     def _bin_scores(self, x, mix):
-        st = self.__dict__.get('_stack')
-        bins = list(self.bin_models)
-        if st is None or any(a is not b for a, b in zip(st.heads, bins)) or len(st.heads) != len(bins):
-            st = _head.HeadStack([bins])
-            object.__setattr__(self, '_stack', st)
-        return _head.run_heads(st, x, mix, self.training)[0]
+        return _head.run_heads(self._families()[0].stack(), x, mix, self.training)[0]
 
     def _class_deltas(self, x, class_label):
         """All K per-bin deltas of every sample's own class: [B, K, ndim].  The C*K two-layer heads
         run fused (one fc1 GEMM over the stacked 2048 -> C*K*N3 weights, BatchNorm, batched output
         layer); the reference's one-hot matmul select (binDeltaModels.py:141-145) is a gather."""
-        st = self.__dict__.get('_stack2')
-        heads = list(self.res_models)
-        if st is None or len(st.heads) != len(heads) or any(a is not b for a, b in zip(st.heads, heads)):
-            st = _head.Mlp2Stack(heads)
-            object.__setattr__(self, '_stack2', st)
+        st = self._families()[1].stack()
         y = _head.run_mlp2_all(st, x, self.training)                     # [B, C*K, ndim]
         y = y.view(y.shape[0], self.num_classes, self.num_clusters, self.ndim)
         idx = class_label.reshape(-1, 1, 1, 1).expand(-1, 1, self.num_clusters, self.ndim)

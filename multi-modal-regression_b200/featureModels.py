@@ -2,8 +2,11 @@
 """Feature trunks with the reference's constructor strings, NameError behaviour and attribute names
 (`features`, `avgpool`, `classifier`, `original_model` — they are state_dict keys of saved
 checkpoints; reference featureModels.py:11-67).  Stock torchvision / cuDNN: outside the kernel claim.
-Pretrained weights are used when they can be loaded, random initialisation otherwise (the
-benchmark box has no network)."""
+Pretrained weights are required, as in the reference (`pretrained=True`); a box without network
+access (the benchmark box) opts into random initialisation with BDPOSE_ALLOW_RANDOM_TRUNK=1."""
+import os
+import warnings
+
 from torch import nn
 
 _RESNET_DEPTH = {'layer2': (6, 28), 'layer3': (7, 14), 'layer4': (8, 7)}   # children kept, pool size
@@ -14,7 +17,13 @@ def _torchvision(name):
     ctor = getattr(tv, name)
     try:
         return ctor(weights='DEFAULT')
-    except Exception:
+    except Exception as e:
+        if os.environ.get('BDPOSE_ALLOW_RANDOM_TRUNK', '0') != '1':
+            raise RuntimeError("featureModels: pretrained %s weights could not be loaded (%s); set "
+                               "BDPOSE_ALLOW_RANDOM_TRUNK=1 to train from a randomly initialised "
+                               "trunk" % (name, e)) from e
+        warnings.warn("featureModels: pretrained %s weights unavailable (%s) - RANDOM trunk "
+                      "initialisation (BDPOSE_ALLOW_RANDOM_TRUNK=1)" % (name, e))
         return ctor(weights=None)
 
 

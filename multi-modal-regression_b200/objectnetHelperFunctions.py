@@ -1,9 +1,18 @@
 # -*- coding: utf-8 -*-
-"""Drop-in for the MODEL classes of the reference's objectnetHelperFunctions module
-(objectnetHelperFunctions.py:110-231): ObjectNet3D heads take cat(features, onehot(label)) as input
-and use ONE bin / res MLP pair for all 100 categories.  The pair runs as a two-head stack on the
-tcgen05 head kernels.  The dataset classes of that module (TrainImages / TestImages: disk I/O) stay
-the reference's own."""
+"""Drop-in for the reference's objectnetHelperFunctions module (objectnetHelperFunctions.py:1-231).
+
+MODEL classes (110-231): ObjectNet3D heads take cat(features, onehot(label)) as input and use ONE
+bin / res MLP pair for all 100 categories.  The pair runs as a two-head stack on the tcgen05 head
+kernels.
+
+DATASET classes (TrainImages / TestImages, 23-107): same constructor, item layout and
+`shuffle_images()` as the reference; the pose targets, bins and residuals of the WHOLE dataset are
+computed once at construction on the GPU (bdp_euler_to_pose + bdp_assign_nearest) instead of per item
+in the DataLoader workers (sklearn predict on a [C,3] array per item).  Only the image read stays per
+item (PIL, disk I/O — outside the kernel scope)."""
+import os
+import pickle
+
 import numpy as np
 import torch
 from torch import nn
@@ -34,6 +43,117 @@ class res_2layer(_bdm.res_2layer):
 
     def __init__(self, n0, n1, dim):
         super().__init__(n0, n1, dim)
+
+
+def _preprocess():
+    """objectnetHelperFunctions.py:19-20 (built lazily: torchvision is only needed for image items)"""
+    from torchvision import transforms
+    normalize = transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    return transforms.Compose([transforms.Resize([224, 224]), transforms.ToTensor(), normalize])
+
+
+def __getattr__(name):
+    if name == 'preprocess':        # module-level transform of the reference (PEP 562, lazy)
+        return _preprocess()
+    raise AttributeError("module 'objectnetHelperFunctions' has no attribute %r" % name)
+
+
+def _load_image_lists(data_path, classes):
+    import scipy.io as spio
+    out = []
+    for c in classes:
+        tmp = spio.loadmat(os.path.join(data_path, c + '_info'), squeeze_me=True)
+        out.append(np.atleast_1d(tmp['image_names']))
+    return out
+
+
+class TrainImages(torch.utils.data.Dataset):
+    """objectnetHelperFunctions.py:23-66: item = one image per class; ydata [C,3] fp32, label [C,1],
+    ydata_bin [C] int64 = kmeans.predict(ydata), ydata_res [C,3] = ydata - centers[bin]."""
+
+    def __init__(self, data_path, classes, dict_size=16):
+        import binDeltaGenerators as G
+        self.db_path = data_path
+        self.classes = classes
+        self.num_classes = len(self.classes)
+        self.list_image_names = _load_image_lists(data_path, classes)
+        self.num_images = np.array([len(self.list_image_names[i]) for i in range(self.num_classes)])
+        self.image_names = self.list_image_names
+        kmeans_file = 'data/kmeans_dictionary_axis_angle_' + str(dict_size) + '.pkl'
+        with open(kmeans_file, 'rb') as f:
+            self.kmeans = pickle.load(f)
+        # every label of the dataset in two launches (float32 targets, as the per-item code: 54-60)
+        per_class = G.pose_targets_from_names(self.list_image_names, 1.0, False, torch.float32)
+        y = torch.from_numpy(np.concatenate(per_class))
+        b, r = G.assign_labels(y, np.asarray(self.kmeans.cluster_centers_))
+        off = np.concatenate([[0], np.cumsum(self.num_images)])
+        b, r = b.cpu(), r.cpu()
+        self._y = [y[off[i]:off[i + 1]] for i in range(self.num_classes)]
+        self._bin = [b[off[i]:off[i + 1]] for i in range(self.num_classes)]
+        self._res = [r[off[i]:off[i + 1]] for i in range(self.num_classes)]
+        self._index = [{n: j for j, n in enumerate(names)} for names in self.list_image_names]
+        self._pre = None
+
+    def __len__(self):
+        return np.amax(self.num_images)
+
+    def _image(self, cls, image_name):
+        from PIL import Image
+        if self._pre is None:
+            self._pre = _preprocess()
+        return self._pre(Image.open(os.path.join(self.db_path, self.classes[cls], image_name + '.png')))
+
+    def __getitem__(self, idx):
+        xdata, rows, label = [], [], []
+        for i in range(self.num_classes):
+            image_name = self.image_names[i][idx % self.num_images[i]]
+            label.append(i * torch.ones(1).long())
+            xdata.append(self._image(i, image_name))
+            rows.append(self._index[i][image_name])
+        return {'xdata': torch.stack(xdata),
+                'ydata': torch.stack([self._y[i][j] for i, j in enumerate(rows)]),
+                'label': torch.stack(label),
+                'ydata_bin': torch.stack([self._bin[i][j] for i, j in enumerate(rows)]),
+                'ydata_res': torch.stack([self._res[i][j] for i, j in enumerate(rows)])}
+
+    def shuffle_images(self):
+        self.image_names = [np.random.permutation(self.list_image_names[i]) for i in range(self.num_classes)]
+
+
+class TestImages(torch.utils.data.Dataset):
+    """objectnetHelperFunctions.py:69-107: item = one image; the bin and the residual are computed
+    from the float64 pose target (100-101), ydata is its float32 copy."""
+
+    def __init__(self, data_path, classes, dict_size=16):
+        import binDeltaGenerators as G
+        self.db_path = data_path
+        self.classes = classes
+        self.num_classes = len(self.classes)
+        self.list_image_names = _load_image_lists(data_path, classes)
+        self.list_labels = [i * np.ones(len(n), dtype='int') for i, n in enumerate(self.list_image_names)]
+        self.image_names = np.concatenate(self.list_image_names)
+        self.labels = np.concatenate(self.list_labels)
+        kmeans_file = 'data/kmeans_dictionary_axis_angle_' + str(dict_size) + '.pkl'
+        with open(kmeans_file, 'rb') as f:
+            self.kmeans = pickle.load(f)
+        y64 = torch.from_numpy(G.pose_targets_from_names([self.image_names], 1.0, False, torch.float64)[0])
+        b, r = G.assign_labels(y64, np.asarray(self.kmeans.cluster_centers_))
+        self._y, self._bin, self._res = y64.float(), b.cpu(), r.cpu()
+        self._pre = None
+
+    def __len__(self):
+        return len(self.image_names)
+
+    def __getitem__(self, idx):
+        from PIL import Image
+        if self._pre is None:
+            self._pre = _preprocess()
+        image_name = self.image_names[idx]
+        label = self.labels[idx]
+        img = Image.open(os.path.join(self.db_path, self.classes[label], image_name + '.png'))
+        return {'xdata': self._pre(img), 'ydata': self._y[idx],
+                'label': int(label) * torch.ones(1).long(),
+                'ydata_bin': self._bin[idx].reshape(1), 'ydata_res': self._res[idx]}
 
 
 def _cat_onehot(feat, label, num_classes):

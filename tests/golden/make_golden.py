@@ -351,6 +351,299 @@ def main_problosses():
     print("losses_prob.npz written")
 
 
+def _fake_dataset(root, classes, counts, rng, png=True):
+    """A synthetic dataset directory in the reference's on-disk layout (dataGenerators.py:34-37,
+    53): <class>_info.mat with `image_names`, <class>/<name>.png.  Names carry the Euler angles the
+    way parse_name reads them (helperFunctions.py:24-33): syn_model_a<az>_e<el>_t<ct>_d<dist>."""
+    import scipy.io as spio
+    from PIL import Image
+    names_all = []
+    for c, n in zip(classes, counts):
+        names = []
+        for j in range(n):
+            az, el, ct = rng.uniform(0, 360), rng.uniform(-60, 60), rng.uniform(-40, 40)
+            if j == 0:
+                az, el, ct = 0.0, 0.0, 0.0                       # identity rotation: get_y -> 0
+            names.append("%s_m%02d_a%.4f_e%.4f_t%.4f_d%.3f" % (c[:3], j, az, el, ct, rng.uniform(1, 3)))
+        spio.savemat(os.path.join(root, c + "_info.mat"), {"image_names": np.array(names, dtype=object)})
+        os.makedirs(os.path.join(root, c), exist_ok=True)
+        if png:
+            for nme in names:
+                Image.fromarray(rng.integers(0, 255, (8, 8, 3), dtype=np.uint8)).save(
+                    os.path.join(root, c, nme + ".png"))
+        names_all.append(names)
+    return names_all
+
+
+def main_generators():
+    """generators.npz: the reference's Dataset classes END TO END on a synthetic dataset directory —
+    dataGenerators.ImagesAll (names -> Euler -> R -> pose target) under binDeltaGenerators.GBDGenerator /
+    GBDGeneratorQ / XPBDGeneratorQ / RBDGenerator (real and render), and objectnetHelperFunctions.
+    TrainImages / TestImages.  Run with `python tests/golden/make_golden.py generators`."""
+    install_shims()
+    import helperFunctions as ref_h
+    import binDeltaGenerators as ref_gen
+    import objectnetHelperFunctions as ref_on
+    from sklearn.cluster import KMeans as SKK
+    rng = np.random.default_rng(31)
+    orig_predict = SKK.predict
+
+    def predict64(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        self.n_features_in_ = X.shape[1]
+        return orig_predict(self, X)
+
+    SKK.predict = predict64
+    root = tempfile.mkdtemp()
+    classes = list(ref_h.classes)
+    counts = [5, 7, 6, 5, 7, 6, 5, 7, 6, 5, 7, 4]
+    names = _fake_dataset(root, classes, counts, rng)
+    Kd = 16
+    train, _ = rand_rotations(rng, 3000)
+    sk = SKK(n_clusters=Kd, init=train[:Kd].copy(), n_init=1, max_iter=300, tol=1e-4,
+             algorithm="lloyd").fit(train)
+    os.makedirs(os.path.join(root, "data"), exist_ok=True)
+    dfile = os.path.join(root, "data", "kmeans_dictionary_axis_angle_16.pkl")
+    with open(dfile, "wb") as f:
+        pickle.dump(sk, f)
+    out = dict(centers=sk.cluster_centers_, counts=np.array(counts), classes=np.array(classes),
+               names=np.array([n for per in names for n in per]))
+    n_items = max(counts)
+    for cls, key, kinds in ((ref_gen.GBDGenerator, "gbd", ("real", "render")),
+                            (ref_gen.GBDGeneratorQ, "gbdq", ("real",)),
+                            (ref_gen.XPBDGeneratorQ, "xpbdq", ("render",)),
+                            (ref_gen.RBDGenerator, "rbd", ("real",))):
+        for kind in kinds:
+            with open(dfile, "wb") as f:          # GBDGeneratorQ mutates the estimator it loads
+                pickle.dump(sk, f)
+            g = cls(root, kind, dfile)
+            assert len(g) == n_items
+            items = [g[i] for i in range(n_items)]
+            k = "%s_%s" % (key, kind)
+            out[k + "_ydata"] = np.stack([s["ydata"].numpy() for s in items])
+            out[k + "_label"] = np.stack([s["label"].numpy() for s in items])
+            out[k + "_bin"] = np.stack([s["ydata_bin"].numpy() for s in items])
+            out[k + "_res"] = np.stack([s["ydata_res"].numpy() for s in items])
+            out[k + "_xmean"] = np.stack([s["xdata"].mean(dim=(1, 2, 3)).numpy() for s in items])
+            if "ydata_rot" in items[0]:
+                out[k + "_rot"] = np.stack([s["ydata_rot"].numpy() for s in items])
+    # ObjectNet datasets (objectnetHelperFunctions.py:23-107): the dictionary path is relative
+    with open(dfile, "wb") as f:
+        pickle.dump(sk, f)
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        tr = ref_on.TrainImages(root, classes[:5], dict_size=16)
+        items = [tr[i] for i in range(len(tr))]
+        for fld in ("ydata", "label", "ydata_bin", "ydata_res"):
+            out["on_train_" + fld] = np.stack([s[fld].numpy() for s in items])
+        # numpy >= 2 refuses `0-d ndarray * Tensor` (objectnetHelperFunctions.py:102 was written for
+        # numpy 1.x, where it gave a [1] long tensor): np.squeeze of the one-element prediction is
+        # handed over as a python int, which indexes and multiplies the same way
+        class _NP:
+            def __getattr__(self, k):
+                return getattr(np, k)
+
+            @staticmethod
+            def squeeze(a):
+                return int(np.squeeze(a))
+        ref_on.np = _NP()
+        te = ref_on.TestImages(root, classes[:5], dict_size=16)
+        items = [te[i] for i in range(len(te))]
+        for fld in ("ydata", "label", "ydata_bin", "ydata_res"):
+            out["on_test_" + fld] = np.stack([s[fld].numpy() for s in items])
+    finally:
+        os.chdir(cwd)
+    np.savez(os.path.join(OUT, "generators.npz"), **out)
+    print("generators.npz written")
+
+
+def _reference_class(path, name, namespace):
+    """Compile ONE class definition of a reference script (the scripts run argparse + training at
+    import, so they cannot be imported) in `namespace`; nothing is written to disk."""
+    import ast
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == name)
+    mod = ast.Module(body=[node], type_ignores=[])
+    exec(compile(mod, path, "exec"), namespace)
+    return namespace[name]
+
+
+def main_joint():
+    """joint.npz: the reference's JointCatPoseModel (learnJointCatPoseModel_weighted.py:94-126),
+    compiled from the script's own class statement, re-parenting a reference OneBinDeltaModel
+    (multires False) and OneDeltaPerBinModel (multires True): forward in train mode + gradients of a
+    seeded linear functional, BatchNorm statistics, eval forward.
+    Run with `python tests/golden/make_golden.py joint`."""
+    install_shims()
+    import torch.nn.functional as F
+    from torch.autograd import Variable
+    import binDeltaModels as ref_models
+    ref_models.resnet_model = lambda *a, **k: nn.Identity()
+    Cc, Kc, N0, N1, N2, N3, nd, Bh = 3, 4, 64, 40, 24, 12, 3, 10
+    out = dict(dims=np.array([Cc, Kc, N0, N1, N2, N3, nd, Bh]))
+    for multires in (False, True):
+        torch.manual_seed(41 + int(multires))
+        tag = "mr/" if multires else "sr/"
+        args = types.SimpleNamespace(multires=multires)
+        ns = dict(torch=torch, nn=nn, F=F, Variable=Variable, args=args, N0=N0, num_classes=Cc)
+        cls = _reference_class(os.path.join(REF, "learnJointCatPoseModel_weighted.py"),
+                               "JointCatPoseModel", ns)
+        if multires:
+            base = ref_models.OneDeltaPerBinModel("resnet", Cc, Kc, N0, N1, N2, N3, nd)
+        else:
+            base = ref_models.OneBinDeltaModel("resnet", Cc, Kc, N0, N1, N2, nd)
+        for m in base.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                m.weight.data.uniform_(0.5, 1.5)
+                m.bias.data.uniform_(-0.3, 0.3)
+                m.running_mean.uniform_(-0.2, 0.2)
+                m.running_var.uniform_(0.5, 2.0)
+        model = cls(base)
+        for k, v in model.state_dict().items():
+            out[tag + "sd0/" + k] = v.clone().numpy()
+        x = torch.randn(Bh, N0)
+        out[tag + "x"] = x.numpy()
+        model.train()
+        xr = x.clone().requires_grad_(True)
+        y0, y1, y2 = model(xr)
+        ws = [torch.randn_like(y) for y in (y0, y1, y2)]
+        sum((y * w).sum() for y, w in zip((y0, y1, y2), ws)).backward()
+        for i, (y, w) in enumerate(zip((y0, y1, y2), ws)):
+            out[tag + "train_y%d" % i] = y.detach().numpy()
+            out[tag + "w%d" % i] = w.numpy()
+        out[tag + "train_gx"] = xr.grad.numpy()
+        for k, p in model.named_parameters():
+            out[tag + "train_grad/" + k] = p.grad.numpy()
+        for k, v in model.state_dict().items():
+            if "running" in k or "num_batches" in k:
+                out[tag + "train_sd/" + k] = v.clone().numpy()
+        model.eval()
+        with torch.no_grad():
+            e = model(x)
+        for i, y in enumerate(e):
+            out[tag + "eval_y%d" % i] = y.numpy()
+    np.savez(os.path.join(OUT, "joint.npz"), **out)
+    print("joint.npz written")
+
+
+def main_objectnet():
+    """objectnet_head.npz: objectnetHelperFunctions.OneBinDeltaModel (155-172) of the reference on
+    small layer sizes: train forward + gradients, BatchNorm statistics, eval forward.
+    Run with `python tests/golden/make_golden.py objectnet`."""
+    install_shims()
+    import objectnetHelperFunctions as ref_on
+    ref_on.resnet_model = lambda *a, **k: nn.Identity()
+    torch.manual_seed(51)
+    C, K, n0, n1, n2, nd, B = 5, 16, 59, 40, 24, 3, 12          # n0 + C = 64 input columns
+    model = ref_on.OneBinDeltaModel(C, K, n0, n1, n2, nd)
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm1d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.5, 2.0)
+    out = dict(dims=np.array([C, K, n0, n1, n2, nd, B]))
+    for k, v in model.state_dict().items():
+        out["sd0/" + k] = v.clone().numpy()
+    x = torch.randn(B, n0)
+    label = torch.randint(0, C, (B, 1))
+    out.update(x=x.numpy(), label=label.numpy())
+    model.train()
+    xr = x.clone().requires_grad_(True)
+    y1, y2 = model(xr, label)
+    w1, w2 = torch.randn_like(y1), torch.randn_like(y2)
+    ((y1 * w1).sum() + (y2 * w2).sum()).backward()
+    out.update(train_y1=y1.detach().numpy(), train_y2=y2.detach().numpy(), w1=w1.numpy(), w2=w2.numpy(),
+               train_gx=xr.grad.numpy())
+    for k, p in model.named_parameters():
+        out["train_grad/" + k] = p.grad.numpy()
+    for k, v in model.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            out["train_sd/" + k] = v.clone().numpy()
+    model.eval()
+    with torch.no_grad():
+        e1, e2 = model(x, label)
+    out.update(eval_y1=e1.numpy(), eval_y2=e2.numpy())
+    np.savez(os.path.join(OUT, "objectnet_head.npz"), **out)
+    print("objectnet_head.npz written")
+
+
+def main_misc():
+    """misc_r2.npz: loss_m2 (binDeltaLosses.py:280-297), get_gamma (helperFunctions.py:51-58), the
+    prediction compositions of the scripts' testing() loops (learnGeodesicBDModel.py:217-219,
+    learnGeodesicBDModel_quaternion.py:217-218, learnRiemannianBDModel.py:247 — the script lines are
+    evaluated here with the reference's get_y / get_R), the mySGD cyclical-LR optimizer
+    (helperFunctions.py:62-120) and get_accuracy (123-130).
+    Run with `python tests/golden/make_golden.py misc`."""
+    install_shims()
+    import axisAngle as ref_aa
+    import binDeltaLosses as ref_losses
+    import helperFunctions as ref_h
+    rng = np.random.default_rng(61)
+    torch.manual_seed(61)
+    out = {}
+    # loss_m2: per-bin residual targets [B, K, ndim], the row of the ARGMAX bin is regressed
+    B, K, nd = 9, 7, 3
+    score = torch.randn(B, K)
+    score[2, 1] = score[2, 4] = score[2].max() + 1.0               # tie -> lowest index
+    res = 0.3 * torch.randn(B, nd)
+    bins = torch.randint(0, K, (B,))
+    res_true = 0.3 * torch.randn(B, K, nd)
+    s_ = score.clone().requires_grad_(True)
+    r_ = res.clone().requires_grad_(True)
+    loss = ref_losses.loss_m2(0.6, K)([s_, r_], [bins, res_true])
+    loss.backward()
+    out.update(m2_score=score.numpy(), m2_res=res.numpy(), m2_bins=bins.numpy(),
+               m2_res_true=res_true.numpy(), m2_alpha=0.6, m2_loss=loss.detach().numpy(),
+               m2_g_score=s_.grad.numpy(), m2_g_res=r_.grad.numpy())
+    # get_gamma
+    cen = rand_rotations(rng, 40)[0]
+    out.update(gamma_centers=cen, gamma=ref_h.get_gamma(cen))
+    # testing() compositions
+    N, Kt = 50, 12
+    kdict = rand_rotations(rng, Kt)[0]
+    sc = rng.standard_normal((N, Kt)).astype(np.float32)
+    sc[5, 2] = sc[5, 9] = sc[5].max() + 1
+    rs = (0.3 * rng.standard_normal((N, 3))).astype(np.float32)
+    rs[7] = 0.0
+    ybin = np.argmax(sc, axis=1)
+    out.update(t_dict=kdict, t_score=sc, t_res=rs, t_add=kdict[ybin, :] + rs)
+    qdict = rand_rotations(rng, Kt)[1]
+    rs4 = (0.3 * rng.standard_normal((N, 4))).astype(np.float32)
+    y = qdict[ybin, :] + rs4
+    out.update(t_qdict=qdict, t_res4=rs4, t_quat=y / np.maximum(np.linalg.norm(y, 2, 1, True), 1e-10))
+    rot_dict = np.stack([ref_aa.get_R(kdict[i]) for i in range(Kt)])
+    out.update(t_rotdict=rot_dict, t_riem=np.stack(
+        [ref_aa.get_y(np.dot(rot_dict[ybin[j]], ref_aa.get_R(rs[j]))) for j in range(N)]))
+    # mySGD: 7 steps of the cyclical learning rate on a two-tensor problem (c = 4)
+    import warnings
+    warnings.simplefilter("ignore")
+    p1 = torch.randn(5, 3).requires_grad_(True)
+    p2 = torch.randn(4).requires_grad_(True)
+    out.update(sgd_p1=p1.detach().numpy().copy(), sgd_p2=p2.detach().numpy().copy())
+    tgt1, tgt2 = torch.randn(5, 3), torch.randn(4)
+    out.update(sgd_t1=tgt1.numpy(), sgd_t2=tgt2.numpy())
+    for name, kw in (("plain", {}), ("mom", dict(momentum=0.9, weight_decay=1e-2)),
+                     ("nest", dict(momentum=0.8, nesterov=True, dampening=0.0))):
+        q1 = p1.detach().clone().requires_grad_(True)
+        q2 = p2.detach().clone().requires_grad_(True)
+        opt = ref_h.mySGD([q1, q2], c=4, alpha1=1e-1, alpha2=1e-3, **kw)
+        traj = []
+        for it in range(7):
+            opt.zero_grad()
+            (((q1 - tgt1) ** 2).sum() + ((q2 - tgt2) ** 4).sum()).backward()
+            opt.step()
+            traj.append(np.concatenate([q1.detach().numpy().ravel(), q2.detach().numpy().ravel()]))
+        out["sgd_traj_" + name] = np.stack(traj)
+    yt = rng.integers(0, 5, 200)
+    yp = np.where(rng.uniform(size=200) < 0.7, yt, rng.integers(0, 5, 200))
+    out.update(acc_true=yt, acc_pred=yp, acc=ref_h.get_accuracy(yt, yp, 5))
+    np.savez(os.path.join(OUT, "misc_r2.npz"), **out)
+    print("misc_r2.npz written")
+
+
 class _PickleDict:
     """Minimal stand-in for the pickled estimator the reference losses load: they only read
     `.cluster_centers_` and `.n_clusters` (binDeltaLosses.py:35-36, 138-139)."""
@@ -365,5 +658,8 @@ if __name__ == "__main__":
         main_perbin()
     elif len(sys.argv) > 1 and sys.argv[1] == "problosses":
         main_problosses()
+    elif len(sys.argv) > 1 and sys.argv[1] in ("generators", "joint", "objectnet", "misc"):
+        {"generators": main_generators, "joint": main_joint, "objectnet": main_objectnet,
+         "misc": main_misc}[sys.argv[1]]()
     else:
         main()

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree n
 
 # module -> names the mirror deliberately leaves to the reference (datasets / disk I/O)
 LEFT_TO_REFERENCE = {
-    "objectnetHelperFunctions": {"TrainImages", "TestImages", "preprocess_real", "preprocess_render"},
+    "objectnetHelperFunctions": set(),
     "binDeltaGenerators": set(),
     "binDeltaModels": set(), "binDeltaLosses": set(), "poseModels": set(),
     "axisAngle": set(), "quaternion": set(), "featureModels": set(),
