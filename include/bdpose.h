@@ -255,6 +255,57 @@ int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
                         const double* centers_old, double* centers_new, double* shift2,
                         int64_t* n_empty, void* stream);
 
+/*
+ * Multi-GPU Lloyd iterations with the exchange fused into the M-step finalisation — no collective
+ * library call, no memset and no host round trip inside the iteration loop.
+ * Replaces learnKmeansDictionary.py:41-42 (KMeans.fit) at 1/2/4/8 GPUs.
+ *
+ * Exchange buffer (one per rank, bdp_kmeans_xchg_bytes(K, d) bytes, ZERO-initialised, 16-byte aligned,
+ * allocated in memory every rank of the node can address — CUDA VMM / IPC / torch symmetric memory):
+ *     int64 acc[2][K*(2d+1) + 2]     two accumulators {cluster sums, counts, changed, unused},
+ *                                    used alternately by even and odd iterations
+ *     uint64 flags[BDP_KMEANS_MAX_RANKS]   flags[r] = last iteration rank r has published here
+ * xchg[r] is THIS process's address of rank r's buffer (xchg[rank] is the local one); xchg_multicast
+ * is an NVLS multicast mapping of the same buffers (sums are then taken by one in-switch
+ * multimem.ld_reduce per word) or NULL (one load per rank and word over NVLink).
+ *
+ * Control block: bdp_kmeans_ctl_bytes() zero-initialised device bytes; its head is a
+ * struct bdp_kmeans_status the caller may read back (after synchronising the stream).
+ *
+ * bdp_kmeans_exchange_finalize   the exchange step of ONE iteration: publish this rank's accumulator
+ *     acc[parity], wait for the peers', sum them (integer sums: bit-identical on every rank and for
+ *     every world size), centers_new = sum / count, shift^2, empty-cluster census, stopping decision
+ *     (check != 0: scikit-learn's rules — labels unchanged, or shift^2 <= tol_abs); zeroes
+ *     acc[parity ^ 1].  flag_value = 1-based global iteration index (strictly increasing per fit).
+ * bdp_kmeans_run   n_iters iterations back to back on one stream: iteration i = iter0 + k reads
+ *     centers2[i & 1] ([2][K,d] fp64 ping-pong), rebuilds the key grid (grid == NULL: brute-force
+ *     scan), runs the E+M step on this rank's rows into acc[i & 1] and calls the exchange step, which
+ *     writes centers2[(i & 1) ^ 1].  Once the status leaves BDP_KMEANS_RUNNING the remaining launches
+ *     do nothing; status.iter_done tells which centres buffer is current.
+ *     BDP_KMEANS_NEEDS_HOST: an empty cluster appeared; the caller relocates (scikit-learn
+ *     _relocate_empty_clusters_dense) on the summed accumulator, finalises with bdp_kmeans_finalize,
+ *     clears status.state and resumes with iter0 = status.iter_done.
+ */
+#define BDP_KMEANS_MAX_RANKS 8
+enum { BDP_KMEANS_RUNNING = 0, BDP_KMEANS_STRICT = 1, BDP_KMEANS_TOL = 2, BDP_KMEANS_NEEDS_HOST = 3 };
+typedef struct bdp_kmeans_status {
+  int32_t state, reserved;
+  int64_t iter_done; /* iterations completed */
+  int64_t changed;   /* labels changed in the last completed iteration, all ranks */
+  int64_t n_empty;   /* empty clusters in the last completed iteration */
+  double shift2;     /* sum ||c_new - c_old||^2 of the last completed iteration */
+} bdp_kmeans_status;
+int64_t bdp_kmeans_ctl_bytes(void);
+int64_t bdp_kmeans_xchg_bytes(int K, int d);
+int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_multicast, int world, int rank,
+                                 int K, int d, int fix_hi_bits, int parity, int64_t flag_value,
+                                 int check, double tol_abs, const double* centers_old,
+                                 double* centers_new, void* ctl, void* stream);
+int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers2, int K, void* grid,
+                   int64_t grid_bytes, int32_t* labels, void* const* xchg,
+                   const void* xchg_multicast, int world, int rank, int fix_hi_bits, int64_t iter0,
+                   int n_iters, int check, double tol_abs, void* ctl, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (a) category-conditioned bin-delta heads.
  *   bin_3layer / res_3layer           binDeltaModels.py:62-91 (fc1, bn1, relu, fc2, bn2, relu, fc3)

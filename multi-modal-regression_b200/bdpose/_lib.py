@@ -52,6 +52,12 @@ SIGNATURES = {
     "bdp_kmeans_iteration": (_int, [_p, _i64, _int, _p, _int, _p, _i64, _p, _p, _int, _p, _int, _p, _p,
                                     _p, _p]),
     "bdp_kmeans_finalize": (_int, [_p, _int, _int, _int, _p, _p, _p, _p, _p]),
+    "bdp_kmeans_ctl_bytes": (_i64, []),
+    "bdp_kmeans_xchg_bytes": (_i64, [_int, _int]),
+    "bdp_kmeans_exchange_finalize": (_int, [_p, _p, _int, _int, _int, _int, _int, _int, _i64, _int, _f64,
+                                            _p, _p, _p, _p]),
+    "bdp_kmeans_run": (_int, [_p, _i64, _int, _p, _int, _p, _i64, _p, _p, _p, _int, _int, _int, _i64,
+                              _int, _int, _f64, _p, _p]),
     "bdp_gemm_tf32": (_int, [_p, _int, _i64, _i64, _p, _int, _i64, _i64, _p, _int, _i64, _i64, _i64,
                              _i64, _i64, _int, _int, _i64, _int, _p]),
     "bdp_gemm_tf32_splits": (_int, [_i64, _int]),
@@ -70,6 +76,15 @@ SIGNATURES = {
 }
 
 HEAD_MAX_GROUPS = 4
+KMEANS_MAX_RANKS = 8
+KMEANS_RUNNING, KMEANS_STRICT, KMEANS_TOL, KMEANS_NEEDS_HOST = range(4)
+
+
+class KMeansStatus(C.Structure):
+    """struct bdp_kmeans_status (include/bdpose.h): head of the device control block"""
+    _fields_ = [("state", C.c_int32), ("reserved", C.c_int32), ("iter_done", C.c_int64),
+                ("changed", C.c_int64), ("n_empty", C.c_int64), ("shift2", C.c_double)]
+
 
 
 class HeadDesc(C.Structure):

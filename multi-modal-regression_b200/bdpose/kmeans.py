@@ -5,13 +5,23 @@ Semantics follow scikit-learn 1.9.0 Lloyd (`_kmeans_single_lloyd`, `lloyd_iter_c
 mean-centre X, E-step argmin ||x-c||^2 with lowest-index ties, M-step mean (sum * (1/count)),
 empty clusters relocated to the points farthest from their centre, stop on unchanged labels or
 sum ||dc||^2 <= tol * mean(var(X)), final E-step when not strictly converged, centres un-centred at
-the end.  Everything runs on the device; the only host traffic is one 3-number read per iteration
-for the convergence test.
+the end.
 
-Multi-GPU: rows are sharded over ranks, centres replicated.  The per-iteration exchange is ONE
-all-reduce(SUM) of the int64 fixed-point accumulators [K, 2d+1] plus the changed-label counter.
-Integer sums are order-independent, so every rank (and every world size) derives bit-identical centres.
+The iteration loop runs on the device: `bdp_kmeans_run` queues [key-grid build, E+M step,
+exchange + finalise] for a batch of iterations; the stopping rules are evaluated by the finalise
+kernel and a stopped fit turns the rest of the batch into no-ops, so the host reads one 40-byte
+status per batch (none at all with `fixed_iters`).
+
+Multi-GPU: rows are sharded over ranks, centres replicated.  The per-iteration exchange is fused
+into the finalise kernel: every rank's int64 fixed-point accumulators [K, 2d+1] (+ the changed-label
+counter) live in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM handles mapped
+into every process of the node) and each rank sums all peers' words straight over NVLink behind a
+flag handshake — no NCCL call in the loop.  Integer sums are order-independent, so every rank (and
+every world size) derives bit-identical centres.  Where symmetric memory cannot be set up the
+exchange falls back to one NCCL all-reduce per iteration (`exchange="nccl"`).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -78,12 +88,14 @@ def lloyd_iteration(x, centers, centers_new, state, fix_hi_bits, grid=None, do_f
     L.check(st, "bdp_kmeans_iteration")
 
 
-def finalize(state, centers_old, centers_new, fix_hi_bits):
+def finalize(state, centers_old, centers_new, fix_hi_bits, shift2=None, n_empty=None):
     K, d = centers_old.shape
+    shift2 = state.shift2 if shift2 is None else shift2
+    n_empty = state.n_empty if n_empty is None else n_empty
     with torch.cuda.device(centers_old.device):
         st = L.lib().bdp_kmeans_finalize(L.ptr(state.acc), K, d, fix_hi_bits, L.ptr(centers_old),
-                                         L.ptr(centers_new), L.ptr(state.shift2),
-                                         L.ptr(state.n_empty), L.stream_ptr())
+                                         L.ptr(centers_new), L.ptr(shift2), L.ptr(n_empty),
+                                         L.stream_ptr())
     L.check(st, "bdp_kmeans_finalize")
 
 
@@ -143,6 +155,194 @@ def _relocate_empty(x, centers_old, state, fix_hi_bits, group):
         acc[new_id, 0:2 * d:2] = hi
         acc[new_id, 1:2 * d:2] = lo
         acc[new_id, 2 * d] = 1
+
+
+class Exchange:
+    """The exchange buffer of this rank ([2][K(2d+1)+2] int64 accumulators + flags, see
+    include/bdpose.h) and this process's addresses of every peer's buffer."""
+    _cache = {}
+
+    def __init__(self, K, d, dev, group):
+        import torch.distributed as dist
+        lib = L.lib()
+        self.K, self.d = K, d
+        self.A = K * (2 * d + 1) + 2
+        self.nbytes = lib.bdp_kmeans_xchg_bytes(K, d)
+        if self.nbytes < 0:
+            raise RuntimeError("kmeans: unsupported dictionary shape [%d, %d]" % (K, d))
+        self.world = dist.get_world_size(group) if _dist_on(group) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.mode, self.why = "local", None
+        self.mc = None
+        n = self.nbytes // 8
+        if self.world > 1:
+            if self.world > L.KMEANS_MAX_RANKS:
+                self.mode, self.why = "nccl", "more than %d ranks" % L.KMEANS_MAX_RANKS
+            elif os.environ.get("BDPOSE_KMEANS_EXCHANGE", "p2p") == "nccl":
+                self.mode, self.why = "nccl", "BDPOSE_KMEANS_EXCHANGE=nccl"
+            else:
+                try:
+                    import torch.distributed._symmetric_memory as symm
+                    pg = group if group is not None else dist.group.WORLD
+                    self.buf = symm.empty(n, dtype=torch.int64, device=dev)
+                    self.handle = symm.rendezvous(self.buf, pg)
+                    ptrs = [int(p) for p in self.handle.buffer_ptrs]
+                    if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+                        raise RuntimeError("rendezvous returned %r" % (ptrs,))
+                    self.ptrs = ptrs
+                    if os.environ.get("BDPOSE_KMEANS_NVLS", "0") == "1":
+                        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+                        self.mc = mc if mc else None
+                    self.mode = "p2p-nvls" if self.mc else "p2p"
+                except Exception as e:      # no VMM / fabric / pidfd support on this box
+                    self.mode, self.why = "nccl", "symmetric memory unavailable: %s" % (e,)
+            # every rank must take the same path
+            flag = torch.tensor([1 if self.mode == "nccl" else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag) and self.mode != "nccl":
+                self.mode, self.why = "nccl", "a peer has no symmetric memory"
+        if self.mode in ("local", "nccl"):
+            self.buf = torch.zeros(n, dtype=torch.int64, device=dev)
+            self.ptrs = [self.buf.data_ptr()]
+        self.group = group
+        self.reset()
+
+    def reset(self):
+        """Zero accumulators and flags; with peers: nobody may publish before everybody has zeroed."""
+        import torch.distributed as dist
+        self.buf.zero_()
+        if self.world > 1:
+            torch.cuda.synchronize(self.buf.device)
+            dist.barrier(group=self.group)
+
+    def acc(self, parity):
+        return self.buf[parity * self.A:(parity + 1) * self.A]
+
+    def ptr_array(self):
+        import ctypes as C
+        if self.mode in ("local", "nccl"):
+            return (C.c_void_p * 1)(self.ptrs[0]), 1, 0
+        return (C.c_void_p * self.world)(*self.ptrs), self.world, self.rank
+
+    @classmethod
+    def get(cls, K, d, dev, group):
+        key = (K, d, dev.index, id(group) if group is not None else None)
+        ex = cls._cache.get(key)
+        if ex is None:
+            ex = cls._cache[key] = cls(K, d, dev, group)
+        else:
+            ex.reset()
+        return ex
+
+
+def _read_status(ctl):
+    raw = bytes(ctl[:40].cpu().numpy())
+    return L.KMeansStatus.from_buffer_copy(raw)
+
+
+def _kmeans_device_loop(x, centers, labels, hb, grid, group, iters, check, tol_abs, batch=8):
+    """Lloyd iterations through bdp_kmeans_run.  Returns (centers, n_iter, strict, exchange mode)."""
+    import torch.distributed as dist
+    lib = L.lib()
+    dev = x.device
+    N, d = x.shape
+    K = centers.shape[0]
+    ex = Exchange.get(K, d, dev, group)
+    ctl = torch.zeros(lib.bdp_kmeans_ctl_bytes(), dtype=torch.uint8, device=dev)
+    ctl_i32 = ctl.view(torch.int32)
+    c2 = torch.stack([centers, centers]).contiguous()
+    ptrs, world, rank = ex.ptr_array()
+    gbuf, gbytes = (None, 0) if grid is None else (grid.buf.data_ptr(), grid.nbytes)
+    tmp_shift = torch.zeros(1, dtype=torch.float64, device=dev)
+    tmp_empty = torch.zeros(1, dtype=torch.int64, device=dev)
+    it0, strict = 0, False
+
+    def run(i0, n):
+        with torch.cuda.device(dev):
+            st = lib.bdp_kmeans_run(x.data_ptr(), N, d, c2.data_ptr(), K, gbuf, gbytes,
+                                    labels.data_ptr(), ptrs, ex.mc, world, rank, hb, i0, n,
+                                    1 if check else 0, tol_abs, ctl.data_ptr(), L.stream_ptr())
+        L.check(st, "bdp_kmeans_run")
+
+    def run_nccl(i0):
+        # exchange fallback: the same kernels, the sums taken by one NCCL all-reduce per iteration
+        cur = i0 & 1
+        acc = ex.acc(cur)
+        with torch.cuda.device(dev):
+            if N > 0:
+                if grid is not None:
+                    grid.rebuild(c2[cur])
+                    st = lib.bdp_kmeans_lloyd_step_grid(x.data_ptr(), N, d, c2[cur].data_ptr(), K, gbuf,
+                                                        gbytes, labels.data_ptr(), acc.data_ptr(), hb,
+                                                        acc[ex.A - 2:].data_ptr(), None, 1, L.stream_ptr())
+                else:
+                    st = lib.bdp_kmeans_lloyd_step(x.data_ptr(), N, d, c2[cur].data_ptr(), K,
+                                                   labels.data_ptr(), acc.data_ptr(), hb,
+                                                   acc[ex.A - 2:].data_ptr(), None, 1, L.stream_ptr())
+                L.check(st, "bdp_kmeans_lloyd_step")
+            dist.all_reduce(acc, group=group)
+            st = lib.bdp_kmeans_exchange_finalize(ptrs, None, 1, 0, K, d, hb, cur, i0 + 1,
+                                                  1 if check else 0, tol_abs, c2[cur].data_ptr(),
+                                                  c2[cur ^ 1].data_ptr(), ctl.data_ptr(), L.stream_ptr())
+        L.check(st, "bdp_kmeans_exchange_finalize")
+
+    while it0 < iters:
+        n = min(batch, iters - it0) if check else iters - it0
+        if ex.mode == "nccl":
+            n = 1
+            run_nccl(it0)
+        else:
+            run(it0, n)
+        if not check:
+            # fixed work: no stopping rules; the only way out of RUNNING is an empty cluster, which
+            # the status read after the whole batch reports
+            st = _read_status(ctl) if (it0 + n >= iters or ex.mode == "nccl") else None
+            if st is None or st.state == L.KMEANS_RUNNING:
+                it0 += n
+                continue
+        else:
+            st = _read_status(ctl)
+        if st.state == L.KMEANS_RUNNING:
+            it0 += n
+            continue
+        if st.state == L.KMEANS_NEEDS_HOST:
+            # an empty cluster (rare): scikit-learn relocates it to the point farthest from its
+            # centre.  Host-driven, on the globally summed accumulator of that iteration.
+            g = int(st.iter_done) - 1
+            p = g & 1
+            acc = ex.acc(p)
+            if ex.world > 1 and ex.mode != "nccl":
+                dist.all_reduce(acc, group=group)
+            view = _AccView(acc[:ex.A - 2], labels)
+            _relocate_empty(x, c2[p], view, hb, group)
+            finalize(view, c2[p], c2[p ^ 1], hb, shift2=tmp_shift, n_empty=tmp_empty)
+            shift2 = float(tmp_shift)
+            ctl_i32[0] = L.KMEANS_RUNNING
+            it0 = g + 1
+            if ex.world > 1 and ex.mode != "nccl":
+                # the summed accumulator must not be read as a partial sum by a late peer: all ranks
+                # leave the host path together
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=group)
+            if check and int(st.changed) == 0:
+                strict = True
+                break
+            if check and shift2 <= tol_abs:
+                break
+            continue
+        strict = st.state == L.KMEANS_STRICT
+        it0 = int(st.iter_done)
+        break
+    n_iter = it0
+    return c2[n_iter & 1].clone(), n_iter, strict, ex.mode
+
+
+class _AccView:
+    """The (acc, labels) pair the relocation / finalise helpers take."""
+
+    def __init__(self, acc, labels):
+        self.acc, self.labels = acc, labels
+        self.shift2 = self.n_empty = None
 
 
 def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, center=True,
@@ -210,6 +410,11 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     strict = False
     n_iter = 0
     iters = fixed_iters if fixed_iters is not None else max_iter
+    exchange = "host-loop"
+    if _backend is None:
+        centers, n_iter, strict, exchange = _kmeans_device_loop(
+            x, centers, state.labels, hb, grid, group, iters, fixed_iters is None, tol_abs)
+        iters = 0
     for it in range(iters):
         if _backend is None:
             lloyd_iteration(x, centers, centers_new, state, hb, grid=grid, do_finalize=not distributed)
@@ -249,7 +454,8 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
         inertia = allreduce(((x - centers[lab]) ** 2).sum().reshape(1))
     if center:
         centers = centers + mean
-    return dict(centers=centers, labels=state.labels, inertia=float(inertia), n_iter=n_iter)
+    return dict(centers=centers, labels=state.labels, inertia=float(inertia), n_iter=n_iter,
+                exchange=exchange)
 
 
 def kmeans_plusplus(x, K, seed=0, n_local_trials=None):

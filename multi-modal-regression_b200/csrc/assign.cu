@@ -62,6 +62,8 @@ struct AssignParams {
   // key grid (candidate pruning); NULL for the brute-force kernel
   const struct GridHdr* ghdr;
   const unsigned short* gfine;
+  // device flag of a k-means run (bdp_kmeans_run): non-zero = the fit has stopped, do nothing
+  const int* stop;
 };
 
 template <typename T, int D>
@@ -114,6 +116,7 @@ __device__ __forceinline__ void emit_point(const AssignParams& P, int64_t i, con
 
 template <typename T, int D, bool LLOYD>
 __global__ void __launch_bounds__(kThreads) assign_kernel(const AssignParams P) {
+  if (P.stop != nullptr && *reinterpret_cast<const volatile int*>(P.stop) != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [chunk float4 recs][chunk float norms (D==4)][recheck list ints][acc (lloyd)]
   float4* s_rec = reinterpret_cast<float4*>(smem_raw);
@@ -580,7 +583,9 @@ template <int D>
 __global__ void __launch_bounds__(256) keygrid_super_kernel(const double* __restrict__ centers, int K,
                                                             int G, double margin_frac,
                                                             GridHdr* __restrict__ hdr,
-                                                            unsigned short* __restrict__ super) {
+                                                            unsigned short* __restrict__ super,
+                                                            const int* stop) {
+  if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
   __shared__ GridHdr s_hdr;
   compute_header<D>(centers, K, G, margin_frac, &s_hdr);
   if (blockIdx.x == 0 && threadIdx.x == 0) *hdr = s_hdr;
@@ -603,7 +608,9 @@ template <int D>
 __global__ void __launch_bounds__(256) keygrid_coarse_kernel(const double* __restrict__ centers,
                                                              int K, const GridHdr* __restrict__ hdr,
                                                              const unsigned short* __restrict__ super,
-                                                             unsigned short* __restrict__ coarse) {
+                                                             unsigned short* __restrict__ coarse,
+                                                             const int* stop) {
+  if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
   const int lane = threadIdx.x & 31;
   const int Gc = hdr->G / 4, Gs = (Gc + 3) / 4;
   const int64_t n_cells = ipow64(Gc, D);
@@ -634,7 +641,9 @@ template <int D>
 __global__ void __launch_bounds__(256) keygrid_fine_kernel(const double* __restrict__ centers, int K,
                                                            const GridHdr* __restrict__ hdr,
                                                            const unsigned short* __restrict__ coarse,
-                                                           unsigned short* __restrict__ fine) {
+                                                           unsigned short* __restrict__ fine,
+                                                           const int* stop) {
+  if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
   constexpr int kChildren = D == 3 ? 64 : 256;
   const int G = hdr->G, Gc = G / 4;
   const int64_t n_fine = ipow64(G, D);
@@ -725,6 +734,7 @@ __device__ __forceinline__ void flush_acc32(unsigned* s_acc32, int K, unsigned l
 
 template <typename T, int D, bool LLOYD>
 __global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignParams P) {
+  if (P.stop != nullptr && *reinterpret_cast<const volatile int*>(P.stop) != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [K float4 recs][K float norms (D==4)][warp stages][chunk accumulators (lloyd)]
   float4* s_rec = reinterpret_cast<float4*>(smem_raw);
@@ -1265,107 +1275,6 @@ __global__ void __launch_bounds__(128) euler_pose_kernel(const double* __restric
   }
 }
 
-// ---- k-means M-step finalisation ------------------------------------------------------------------
-// (hi, lo) limbs -> correctly rounded double of  hi*2^32 + lo  (|value| < 2^95), then * scale.
-__device__ __forceinline__ double limbs_to_double(long long hi, long long lo, double inv_scale_lo) {
-  // value = hi*2^32 + lo as a signed 128-bit integer (lo >= 0)
-  __int128 v = ((__int128)hi << 32) + (__int128)lo;
-  const bool neg = v < 0;
-  unsigned __int128 m = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
-  if (m == 0) return 0.0;
-  // normalise to 64 significant bits + sticky, then let the u64 -> double conversion round once
-  int shift = 0;
-  unsigned long long top = (unsigned long long)(m >> 64);
-  double r;
-  if (top == 0) {
-    const unsigned long long low = (unsigned long long)m;
-    // u64 -> double is correctly rounded (round to nearest even) by the hardware conversion
-    r = __ull2double_rn(low);
-  } else {
-    const int lz = __clzll((long long)top);
-    shift = 64 - lz;                                  // bits to drop so that 64 remain
-    unsigned long long kept = (unsigned long long)(m >> shift);
-    const unsigned __int128 dropped = m & ((((unsigned __int128)1) << shift) - 1);
-    if (dropped != 0) kept |= 1ull;                   // sticky: kept has 64 bits, 11 of them are
-                                                      // below the double mantissa, so OR-ing the
-                                                      // lowest one cannot change a tie wrongly
-    r = __ull2double_rn(kept) * exp2((double)shift);
-  }
-  r *= inv_scale_lo;                                  // power of two: exact
-  return neg ? -r : r;
-}
-
-template <int D>
-__global__ void __launch_bounds__(256) kmeans_finalize_kernel(const long long* __restrict__ acc,
-                                                              int K, double inv_scale_lo,
-                                                              const double* __restrict__ c_old,
-                                                              double* __restrict__ c_new,
-                                                              double* __restrict__ shift2,
-                                                              long long* __restrict__ n_empty) {
-  // single block: K is a dictionary size (<= a few thousand)
-  __shared__ long long s_best_cnt[8];
-  __shared__ int s_best_idx[8];
-  __shared__ double s_red[8];
-  __shared__ int s_cnt_empty[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // pass 1: argmax count (first maximum, np.argmax) and number of empty clusters
-  long long bc = -1;
-  int bi = 0x7fffffff, ne = 0;
-  for (int j = threadIdx.x; j < K; j += blockDim.x) {
-    const long long c = acc[(size_t)j * (2 * D + 1) + 2 * D];
-    if (c > bc) { bc = c; bi = j; }
-    ne += (c == 0);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const long long oc = __shfl_xor_sync(BDP_FULL_MASK, bc, o);
-    const int oi = __shfl_xor_sync(BDP_FULL_MASK, bi, o);
-    if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
-  }
-  ne = warp_sum(ne);
-  if (lane == 0) { s_best_cnt[warp] = bc; s_best_idx[warp] = bi; s_cnt_empty[warp] = ne; }
-  __syncthreads();
-  bc = s_best_cnt[0]; bi = s_best_idx[0]; ne = s_cnt_empty[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-    if (s_best_cnt[w] > bc || (s_best_cnt[w] == bc && s_best_idx[w] < bi)) {
-      bc = s_best_cnt[w]; bi = s_best_idx[w];
-    }
-    ne += s_cnt_empty[w];
-  }
-  const int big = bi;
-  // pass 2: centres.  sklearn _average_centers: alpha = 1/w; c *= alpha.  An empty cluster j copies
-  // row `big` as it stands when the in-order loop reaches j: already averaged if big < j, still the
-  // raw SUM if big > j (only reachable when relocation bailed out; kept for fidelity).
-  double sh = 0.0;
-  for (int j = threadIdx.x; j < K; j += blockDim.x) {
-    const long long* a = acc + (size_t)j * (2 * D + 1);
-    const long long cnt = a[2 * D];
-    const long long* src = cnt > 0 ? a : acc + (size_t)big * (2 * D + 1);
-    const long long scnt = src[2 * D];
-    double alpha = 1.0;
-    if (cnt > 0) alpha = 1.0 / (double)cnt;
-    else if (big < j && scnt > 0) alpha = 1.0 / (double)scnt;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      const double sum = limbs_to_double(src[2 * k], src[2 * k + 1], inv_scale_lo);
-      const double c = sum * alpha;
-      c_new[(size_t)j * D + k] = c;
-      const double df = c - c_old[(size_t)j * D + k];
-      sh += df * df;
-    }
-  }
-  sh = warp_sum(sh);
-  __syncthreads();
-  if (lane == 0) s_red[warp] = sh;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-    if (shift2) *shift2 = t;
-    if (n_empty) *n_empty = ne;
-  }
-}
-
 }  // namespace
 
 extern "C" int bdp_assign_nearest(const void* x, int x_dtype, int64_t N, int d,
@@ -1384,9 +1293,9 @@ extern "C" int bdp_assign_nearest(const void* x, int x_dtype, int64_t N, int d,
   return dispatch_assign<false>(P, x_dtype, d, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int bdp_kmeans_lloyd_step(const double* x, int64_t N, int d, const double* centers,
-                                     int K, int32_t* labels, int64_t* acc, int fix_hi_bits,
-                                     int64_t* stats, double* inertia, int update, void* stream) {
+int bdpi_lloyd_step(const double* x, int64_t N, int d, const double* centers, int K,
+                    int32_t* labels, int64_t* acc, int fix_hi_bits, int64_t* stats, double* inertia,
+                    int update, const int* stop, cudaStream_t st) {
   BDP_REQUIRE(N >= 0 && N < (1ll << 30), "kmeans_lloyd_step: N out of range");
   if (N == 0) return BDP_OK;
   BDP_REQUIRE(x && centers && labels && stats, "kmeans_lloyd_step: NULL buffer");
@@ -1400,28 +1309,15 @@ extern "C" int bdp_kmeans_lloyd_step(const double* x, int64_t N, int d, const do
   P.acc = reinterpret_cast<unsigned long long*>(acc);
   P.scale_hi = ldexp(1.0, fix_hi_bits);
   P.stats = reinterpret_cast<unsigned long long*>(stats);
-  P.inertia = inertia; P.update = update;
-  return dispatch_assign<true>(P, BDP_F64, d, reinterpret_cast<cudaStream_t>(stream));
+  P.inertia = inertia; P.update = update; P.stop = stop;
+  return dispatch_assign<true>(P, BDP_F64, d, st);
 }
 
-extern "C" int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
-                                   const double* centers_old, double* centers_new, double* shift2,
-                                   int64_t* n_empty, void* stream) {
-  BDP_REQUIRE(acc && centers_old && centers_new, "kmeans_finalize: NULL buffer");
-  BDP_REQUIRE(d == 3 || d == 4, "kmeans_finalize: d must be 3 or 4");
-  BDP_REQUIRE(K >= 1, "kmeans_finalize: K must be >= 1");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const double inv = ldexp(1.0, -(fix_hi_bits + 32));
-  if (d == 3)
-    kmeans_finalize_kernel<3><<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(acc), K, inv,
-                                                 centers_old, centers_new, shift2,
-                                                 reinterpret_cast<long long*>(n_empty));
-  else
-    kmeans_finalize_kernel<4><<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(acc), K, inv,
-                                                 centers_old, centers_new, shift2,
-                                                 reinterpret_cast<long long*>(n_empty));
-  BDP_CUDA_CHECK_LAUNCH("kmeans_finalize_kernel");
-  return BDP_OK;
+extern "C" int bdp_kmeans_lloyd_step(const double* x, int64_t N, int d, const double* centers,
+                                     int K, int32_t* labels, int64_t* acc, int fix_hi_bits,
+                                     int64_t* stats, double* inertia, int update, void* stream) {
+  return bdpi_lloyd_step(x, N, d, centers, K, labels, acc, fix_hi_bits, stats, inertia, update,
+                         nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bdp_assign_quatdot(const void* q, int q_dtype, int64_t N, const double* keys, int K,
@@ -1494,13 +1390,12 @@ extern "C" int64_t bdp_keygrid_bytes(int K, int d) {
          keygrid_super_cells(G, d) * (K + 1) * 2;
 }
 
-extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
-                                 void* stream) {
+int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
+                       const int* stop, cudaStream_t st) {
   BDP_REQUIRE(centers != nullptr, "keygrid_build: NULL centers");
   BDP_REQUIRE(d == 3 || d == 4, "keygrid_build: d must be 3 or 4 (got %d)", d);
   int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_build");
   if (rc != BDP_OK) return rc;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const GridHdr* hdr; const unsigned short *coarse, *fine, *super;
   keygrid_pointers(grid, K, d, &hdr, &coarse, &fine, &super);
   GridHdr* h = const_cast<GridHdr*>(hdr);
@@ -1520,16 +1415,22 @@ extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid
   };
   const unsigned fine_blocks = (unsigned)ceil_div64(n_fine, 256);
   if (d == 3) {
-    keygrid_super_kernel<3><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, h, su);
-    keygrid_coarse_kernel<3><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, su, co);
-    keygrid_fine_kernel<3><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi);
+    keygrid_super_kernel<3><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, h, su, stop);
+    keygrid_coarse_kernel<3><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, su, co, stop);
+    keygrid_fine_kernel<3><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi, stop);
   } else {
-    keygrid_super_kernel<4><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, h, su);
-    keygrid_coarse_kernel<4><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, su, co);
-    keygrid_fine_kernel<4><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi);
+    keygrid_super_kernel<4><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, h, su, stop);
+    keygrid_coarse_kernel<4><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, su, co, stop);
+    keygrid_fine_kernel<4><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi, stop);
   }
   BDP_CUDA_CHECK_LAUNCH("keygrid kernels");
   return BDP_OK;
+}
+
+extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
+                                 void* stream) {
+  return bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr,
+                            reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bdp_assign_nearest_grid(const void* x, int x_dtype, int64_t N, int d,
@@ -1551,11 +1452,10 @@ extern "C" int bdp_assign_nearest_grid(const void* x, int x_dtype, int64_t N, in
   return dispatch_assign_grid<false>(P, x_dtype, d, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, const double* centers,
-                                          int K, const void* grid, int64_t grid_bytes,
-                                          int32_t* labels, int64_t* acc, int fix_hi_bits,
-                                          int64_t* stats, double* inertia, int update,
-                                          void* stream) {
+int bdpi_lloyd_step_grid(const double* x, int64_t N, int d, const double* centers, int K,
+                         const void* grid, int64_t grid_bytes, int32_t* labels, int64_t* acc,
+                         int fix_hi_bits, int64_t* stats, double* inertia, int update,
+                         const int* stop, cudaStream_t st) {
   BDP_REQUIRE(N >= 0 && N < (1ll << 30), "kmeans_lloyd_step_grid: N out of range");
   if (N == 0) return BDP_OK;
   BDP_REQUIRE(x && centers && labels && stats, "kmeans_lloyd_step_grid: NULL buffer");
@@ -1570,41 +1470,19 @@ extern "C" int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, con
   P.acc = reinterpret_cast<unsigned long long*>(acc);
   P.scale_hi = ldexp(1.0, fix_hi_bits);
   P.stats = reinterpret_cast<unsigned long long*>(stats);
-  P.inertia = inertia; P.update = update;
+  P.inertia = inertia; P.update = update; P.stop = stop;
   const unsigned short* coarse;
   keygrid_pointers(grid, K, d, &P.ghdr, &coarse, &P.gfine);
-  return dispatch_assign_grid<true>(P, BDP_F64, d, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch_assign_grid<true>(P, BDP_F64, d, st);
 }
 
-// One Lloyd iteration as a single launch sequence: zero the accumulators, rebuild the key grid for
-// the current centres, E+M step, and (single rank) the M-step finalisation.  With several ranks the
-// caller all-reduces acc_stats between this call (centers_new == NULL) and bdp_kmeans_finalize.
-extern "C" int bdp_kmeans_iteration(const double* x, int64_t N, int d, const double* centers, int K,
-                                    void* grid, int64_t grid_bytes, int32_t* labels,
-                                    int64_t* acc_stats, int fix_hi_bits, double* inertia, int update,
-                                    double* centers_new, double* shift2, int64_t* n_empty,
-                                    void* stream) {
-  BDP_REQUIRE(acc_stats != nullptr, "kmeans_iteration: acc_stats is NULL");
-  BDP_REQUIRE(d == 3 || d == 4, "kmeans_iteration: d must be 3 or 4 (got %d)", d);
-  BDP_REQUIRE(K >= 1, "kmeans_iteration: K must be >= 1");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t n_acc = (size_t)K * (2 * d + 1);
-  BDP_CUDA_CALL(cudaMemsetAsync(acc_stats, 0, (n_acc + 2) * sizeof(int64_t), st));
-  int rc;
-  if (grid) {
-    rc = bdp_keygrid_build(centers, K, d, grid, grid_bytes, stream);
-    if (rc != BDP_OK) return rc;
-    rc = bdp_kmeans_lloyd_step_grid(x, N, d, centers, K, grid, grid_bytes, labels, acc_stats,
-                                    fix_hi_bits, acc_stats + n_acc, inertia, update, stream);
-  } else {
-    rc = bdp_kmeans_lloyd_step(x, N, d, centers, K, labels, acc_stats, fix_hi_bits,
-                               acc_stats + n_acc, inertia, update, stream);
-  }
-  if (rc != BDP_OK) return rc;
-  if (centers_new)
-    return bdp_kmeans_finalize(acc_stats, K, d, fix_hi_bits, centers, centers_new, shift2, n_empty,
-                               stream);
-  return BDP_OK;
+extern "C" int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, const double* centers,
+                                          int K, const void* grid, int64_t grid_bytes,
+                                          int32_t* labels, int64_t* acc, int fix_hi_bits,
+                                          int64_t* stats, double* inertia, int update,
+                                          void* stream) {
+  return bdpi_lloyd_step_grid(x, N, d, centers, K, grid, grid_bytes, labels, acc, fix_hi_bits, stats,
+                              inertia, update, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bdp_euler_to_pose(const double* euler_deg, int64_t N, double* aa, double* quat,

@@ -28,6 +28,22 @@ def _data():
     return (q[:, 1:] / q[:, 1:].norm(dim=1, keepdim=True) * (2 * torch.acos(w))).contiguous()
 
 
+CASES = ("converge", "fixed", "nccl", "empty", "nvls")
+
+
+def _fit(kmeans, X, lo, hi, case):
+    init = X[:200].clone()
+    kw = dict(max_iter=12)
+    if case == "fixed":
+        kw = dict(fixed_iters=5)
+    if case == "empty":
+        init[3] = torch.tensor([50.0, 50.0, 50.0], dtype=init.dtype)   # a centre no sample is near
+    os.environ["BDPOSE_KMEANS_EXCHANGE"] = "nccl" if case == "nccl" else "p2p"
+    os.environ["BDPOSE_KMEANS_NVLS"] = "1" if case == "nvls" else "0"
+    kmeans.Exchange._cache.clear()
+    return kmeans.kmeans_lloyd(X[lo:hi].cuda(), init.cuda(), **kw)
+
+
 def _worker(rank, world, store, out):
     _paths()
     torch.cuda.set_device(rank)
@@ -37,25 +53,37 @@ def _worker(rank, world, store, out):
     X = _data()
     n = X.shape[0]
     lo, hi = rank * n // world, (rank + 1) * n // world
-    r = kmeans.kmeans_lloyd(X[lo:hi].cuda(), X[:200].cuda(), max_iter=12)
-    torch.save({"centers": r["centers"].cpu(), "labels": r["labels"].cpu(), "n_iter": r["n_iter"]},
-               os.path.join(out, "r%d.pt" % rank))
+    res = {}
+    for case in CASES:
+        r = _fit(kmeans, X, lo, hi, case)
+        res[case] = {"centers": r["centers"].cpu(), "labels": r["labels"].cpu(), "n_iter": r["n_iter"],
+                     "inertia": r["inertia"], "exchange": r["exchange"]}
+    torch.save(res, os.path.join(out, "r%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_sharded_kmeans_equals_single_gpu():
+    """Sharded fits (fused peer-memory exchange, its NVLS form, the NCCL fallback; stopping rules,
+    fixed iterations, an empty-cluster relocation) against the single-GPU fit of the same data:
+    centres, labels and iteration counts bit for bit."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     _paths()
     from bdpose import kmeans
-    world = 2
+    world = min(torch.cuda.device_count(), 8)
     with tempfile.TemporaryDirectory() as out:
         mp.spawn(_worker, args=(world, os.path.join(out, "store"), out), nprocs=world, join=True)
         parts = [torch.load(os.path.join(out, "r%d.pt" % r)) for r in range(world)]
     X = _data()
-    one = kmeans.kmeans_lloyd(X.cuda(), X[:200].cuda(), max_iter=12)
-    assert parts[0]["n_iter"] == parts[1]["n_iter"] == one["n_iter"]
-    assert torch.equal(parts[0]["centers"], parts[1]["centers"])
-    assert torch.equal(parts[0]["centers"], one["centers"].cpu())
-    assert torch.equal(torch.cat([p["labels"] for p in parts]), one["labels"].cpu())
+    modes = {c: parts[0][c]["exchange"] for c in CASES}
+    print("exchange modes:", modes)
+    assert modes["nccl"] == "nccl"
+    assert modes["converge"] in ("p2p", "nccl"), modes      # nccl only where symmetric memory is absent
+    for case in CASES:
+        one = _fit(kmeans, X, 0, X.shape[0], case)
+        for p in parts:
+            assert p[case]["n_iter"] == one["n_iter"], case
+            assert torch.equal(p[case]["centers"], one["centers"].cpu()), case
+            assert p[case]["inertia"] == pytest.approx(one["inertia"], rel=1e-12), case
+        assert torch.equal(torch.cat([p[case]["labels"] for p in parts]), one["labels"].cpu()), case
