@@ -222,6 +222,11 @@ int bdp_kmeans_lloyd_step(const double* x, int64_t N, int d, const double* cente
  * Replaces the same reference call sites as the brute-force forms (binDeltaGenerators.py:27-30,
  * learnKmeansDictionary.py:41-42).
  */
+/* Diagnostics of a query batch against a built grid: stats [5] int64 (zeroed by the caller) receive
+ * {points, points outside the grid, points in overflowed cells, sum of candidate-list lengths over
+ * the other points, longest list seen}. */
+int bdp_keygrid_stats(const void* x, int x_dtype, int64_t N, int d, int K, const void* grid,
+                      int64_t grid_bytes, int64_t* stats, void* stream);
 int64_t bdp_keygrid_bytes(int K, int d);
 int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
                       void* stream);

@@ -45,6 +45,7 @@ SIGNATURES = {
     "bdp_euler_to_pose": (_int, [_p, _i64, _p, _p, _p]),
     "bdp_kmeans_lloyd_step": (_int, [_p, _i64, _int, _p, _int, _p, _p, _int, _p, _p, _int, _p]),
     "bdp_keygrid_bytes": (_i64, [_int, _int]),
+    "bdp_keygrid_stats": (_int, [_p, _int, _i64, _int, _int, _p, _i64, _p, _p]),
     "bdp_keygrid_build": (_int, [_p, _int, _int, _p, _i64, _p]),
     "bdp_assign_nearest_grid": (_int, [_p, _int, _i64, _int, _p, _int, _p, _i64, _p, _p, _p, _p, _p]),
     "bdp_kmeans_lloyd_step_grid": (_int, [_p, _i64, _int, _p, _int, _p, _i64, _p, _p, _int, _p, _p,

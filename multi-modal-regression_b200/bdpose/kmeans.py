@@ -99,8 +99,13 @@ def finalize(state, centers_old, centers_new, fix_hi_bits, shift2=None, n_empty=
     L.check(st, "bdp_kmeans_finalize")
 
 
+LOCAL = "local"     # group sentinel: this process alone, even when torch.distributed is initialised
+
+
 def _dist_on(group):
     import torch.distributed as dist
+    if isinstance(group, str) and group == LOCAL:
+        return False
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
@@ -226,7 +231,7 @@ class Exchange:
 
     @classmethod
     def get(cls, K, d, dev, group):
-        key = (K, d, dev.index, id(group) if group is not None else None)
+        key = (K, d, dev.index, group if isinstance(group, str) else (id(group) if group is not None else None))
         ex = cls._cache.get(key)
         if ex is None:
             ex = cls._cache[key] = cls(K, d, dev, group)
@@ -235,107 +240,140 @@ class Exchange:
         return ex
 
 
-def _read_status(ctl):
-    raw = bytes(ctl[:40].cpu().numpy())
-    return L.KMeansStatus.from_buffer_copy(raw)
+class LloydLoop:
+    """Lloyd iterations of one fit through bdp_kmeans_run (the device-side loop).
 
+        loop = LloydLoop(x, centers, labels, hb, grid, group, tol_abs)
+        loop.iterate(20)                 # fixed work: no stopping rules, no host synchronisation
+        loop.iterate(300, check=True)    # scikit-learn's stopping rules, one status read per batch
+        loop.centers, loop.n_iter, loop.strict, loop.mode
 
-def _kmeans_device_loop(x, centers, labels, hb, grid, group, iters, check, tol_abs, batch=8):
-    """Lloyd iterations through bdp_kmeans_run.  Returns (centers, n_iter, strict, exchange mode)."""
-    import torch.distributed as dist
-    lib = L.lib()
-    dev = x.device
-    N, d = x.shape
-    K = centers.shape[0]
-    ex = Exchange.get(K, d, dev, group)
-    ctl = torch.zeros(lib.bdp_kmeans_ctl_bytes(), dtype=torch.uint8, device=dev)
-    ctl_i32 = ctl.view(torch.int32)
-    c2 = torch.stack([centers, centers]).contiguous()
-    ptrs, world, rank = ex.ptr_array()
-    gbuf, gbytes = (None, 0) if grid is None else (grid.buf.data_ptr(), grid.nbytes)
-    tmp_shift = torch.zeros(1, dtype=torch.float64, device=dev)
-    tmp_empty = torch.zeros(1, dtype=torch.int64, device=dev)
-    it0, strict = 0, False
+    x [N_local, d] fp64 (this rank's shard, already centred), centers [K, d] fp64, labels [N_local]
+    int32 (previous labels in / new labels out)."""
 
-    def run(i0, n):
-        with torch.cuda.device(dev):
-            st = lib.bdp_kmeans_run(x.data_ptr(), N, d, c2.data_ptr(), K, gbuf, gbytes,
-                                    labels.data_ptr(), ptrs, ex.mc, world, rank, hb, i0, n,
-                                    1 if check else 0, tol_abs, ctl.data_ptr(), L.stream_ptr())
+    def __init__(self, x, centers, labels, hb, grid, group, tol_abs):
+        lib = L.lib()
+        self.x, self.labels, self.hb, self.grid, self.group = x, labels, hb, grid, group
+        self.tol_abs = tol_abs
+        self.dev = x.device
+        self.N, self.d = x.shape
+        self.K = centers.shape[0]
+        self.ex = Exchange.get(self.K, self.d, self.dev, group)
+        self.mode = self.ex.mode
+        self.ctl = torch.zeros(lib.bdp_kmeans_ctl_bytes(), dtype=torch.uint8, device=self.dev)
+        self.c2 = torch.stack([centers, centers]).contiguous()
+        self.ptrs, self.world, self.rank = self.ex.ptr_array()
+        self._tmp_shift = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self._tmp_empty = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.n_iter, self.strict, self.stopped = 0, False, False
+
+    def reset(self, centers):
+        """Start over from `centers` (same data): accumulators, flags, labels and status cleared."""
+        self.c2[0].copy_(centers)
+        self.c2[1].copy_(centers)
+        self.ctl.zero_()
+        self.labels.fill_(-1)
+        self.ex.reset()
+        self.n_iter, self.strict, self.stopped = 0, False, False
+
+    @property
+    def centers(self):
+        return self.c2[self.n_iter & 1]
+
+    def status(self):
+        raw = bytes(self.ctl[:40].cpu().numpy())
+        return L.KMeansStatus.from_buffer_copy(raw)
+
+    def launch(self, i0, n, check):
+        """Queue iterations i0 .. i0+n-1 on the current stream (no host synchronisation)."""
+        lib = L.lib()
+        g = self.grid
+        with torch.cuda.device(self.dev):
+            st = lib.bdp_kmeans_run(self.x.data_ptr(), self.N, self.d, self.c2.data_ptr(), self.K,
+                                    None if g is None else g.buf.data_ptr(), 0 if g is None else g.nbytes,
+                                    self.labels.data_ptr(), self.ptrs, self.ex.mc, self.world, self.rank,
+                                    self.hb, i0, n, 1 if check else 0, self.tol_abs,
+                                    self.ctl.data_ptr(), L.stream_ptr())
         L.check(st, "bdp_kmeans_run")
 
-    def run_nccl(i0):
+    def _launch_nccl(self, i0, check):
         # exchange fallback: the same kernels, the sums taken by one NCCL all-reduce per iteration
+        import torch.distributed as dist
+        lib = L.lib()
+        ex, g, c2 = self.ex, self.grid, self.c2
         cur = i0 & 1
         acc = ex.acc(cur)
-        with torch.cuda.device(dev):
-            if N > 0:
-                if grid is not None:
-                    grid.rebuild(c2[cur])
-                    st = lib.bdp_kmeans_lloyd_step_grid(x.data_ptr(), N, d, c2[cur].data_ptr(), K, gbuf,
-                                                        gbytes, labels.data_ptr(), acc.data_ptr(), hb,
-                                                        acc[ex.A - 2:].data_ptr(), None, 1, L.stream_ptr())
+        with torch.cuda.device(self.dev):
+            if self.N > 0:
+                if g is not None:
+                    g.rebuild(c2[cur])
+                    st = lib.bdp_kmeans_lloyd_step_grid(
+                        self.x.data_ptr(), self.N, self.d, c2[cur].data_ptr(), self.K, g.buf.data_ptr(),
+                        g.nbytes, self.labels.data_ptr(), acc.data_ptr(), self.hb,
+                        acc[ex.A - 2:].data_ptr(), None, 1, L.stream_ptr())
                 else:
-                    st = lib.bdp_kmeans_lloyd_step(x.data_ptr(), N, d, c2[cur].data_ptr(), K,
-                                                   labels.data_ptr(), acc.data_ptr(), hb,
-                                                   acc[ex.A - 2:].data_ptr(), None, 1, L.stream_ptr())
+                    st = lib.bdp_kmeans_lloyd_step(
+                        self.x.data_ptr(), self.N, self.d, c2[cur].data_ptr(), self.K,
+                        self.labels.data_ptr(), acc.data_ptr(), self.hb, acc[ex.A - 2:].data_ptr(), None,
+                        1, L.stream_ptr())
                 L.check(st, "bdp_kmeans_lloyd_step")
-            dist.all_reduce(acc, group=group)
-            st = lib.bdp_kmeans_exchange_finalize(ptrs, None, 1, 0, K, d, hb, cur, i0 + 1,
-                                                  1 if check else 0, tol_abs, c2[cur].data_ptr(),
-                                                  c2[cur ^ 1].data_ptr(), ctl.data_ptr(), L.stream_ptr())
+            dist.all_reduce(acc, group=self.group)
+            st = lib.bdp_kmeans_exchange_finalize(
+                self.ptrs, None, 1, 0, self.K, self.d, self.hb, cur, i0 + 1, 1 if check else 0,
+                self.tol_abs, c2[cur].data_ptr(), c2[cur ^ 1].data_ptr(), self.ctl.data_ptr(),
+                L.stream_ptr())
         L.check(st, "bdp_kmeans_exchange_finalize")
 
-    while it0 < iters:
-        n = min(batch, iters - it0) if check else iters - it0
-        if ex.mode == "nccl":
-            n = 1
-            run_nccl(it0)
-        else:
-            run(it0, n)
-        if not check:
-            # fixed work: no stopping rules; the only way out of RUNNING is an empty cluster, which
-            # the status read after the whole batch reports
-            st = _read_status(ctl) if (it0 + n >= iters or ex.mode == "nccl") else None
-            if st is None or st.state == L.KMEANS_RUNNING:
-                it0 += n
-                continue
-        else:
-            st = _read_status(ctl)
-        if st.state == L.KMEANS_RUNNING:
-            it0 += n
-            continue
-        if st.state == L.KMEANS_NEEDS_HOST:
-            # an empty cluster (rare): scikit-learn relocates it to the point farthest from its
-            # centre.  Host-driven, on the globally summed accumulator of that iteration.
-            g = int(st.iter_done) - 1
-            p = g & 1
-            acc = ex.acc(p)
-            if ex.world > 1 and ex.mode != "nccl":
-                dist.all_reduce(acc, group=group)
-            view = _AccView(acc[:ex.A - 2], labels)
-            _relocate_empty(x, c2[p], view, hb, group)
-            finalize(view, c2[p], c2[p ^ 1], hb, shift2=tmp_shift, n_empty=tmp_empty)
-            shift2 = float(tmp_shift)
-            ctl_i32[0] = L.KMEANS_RUNNING
-            it0 = g + 1
-            if ex.world > 1 and ex.mode != "nccl":
-                # the summed accumulator must not be read as a partial sum by a late peer: all ranks
-                # leave the host path together
-                torch.cuda.synchronize(dev)
-                dist.barrier(group=group)
-            if check and int(st.changed) == 0:
-                strict = True
-                break
-            if check and shift2 <= tol_abs:
-                break
-            continue
-        strict = st.state == L.KMEANS_STRICT
-        it0 = int(st.iter_done)
-        break
-    n_iter = it0
-    return c2[n_iter & 1].clone(), n_iter, strict, ex.mode
+    def _host_relocation(self, st, check):
+        """An empty cluster (rare): scikit-learn relocates it to the point farthest from its centre.
+        Host-driven, on the globally summed accumulator of that iteration."""
+        import torch.distributed as dist
+        ex = self.ex
+        g = int(st.iter_done) - 1
+        p = g & 1
+        acc = ex.acc(p)
+        if ex.world > 1 and ex.mode != "nccl":
+            dist.all_reduce(acc, group=self.group)
+        view = _AccView(acc[:ex.A - 2], self.labels)
+        _relocate_empty(self.x, self.c2[p], view, self.hb, self.group)
+        finalize(view, self.c2[p], self.c2[p ^ 1], self.hb, shift2=self._tmp_shift,
+                 n_empty=self._tmp_empty)
+        shift2 = float(self._tmp_shift)
+        self.ctl.view(torch.int32)[0] = L.KMEANS_RUNNING
+        self.n_iter = g + 1
+        if ex.world > 1 and ex.mode != "nccl":
+            # the summed accumulator must not be read as a partial sum by a late peer: all ranks leave
+            # the host path together
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.group)
+        if check and int(st.changed) == 0:
+            self.strict = self.stopped = True
+        elif check and shift2 <= self.tol_abs:
+            self.stopped = True
 
+    def iterate(self, n, check=False, batch=8):
+        """Up to n more iterations.  check=False: fixed work (the only early exit is an empty cluster,
+        seen when the status is read after the batch).  Returns True when a stopping rule fired."""
+        end = self.n_iter + n
+        while self.n_iter < end and not self.stopped:
+            m = end - self.n_iter
+            if check:
+                m = min(m, batch)
+            if self.mode == "nccl":
+                m = 1
+                self._launch_nccl(self.n_iter, check)
+            else:
+                self.launch(self.n_iter, m, check)
+            st = self.status()       # one small synchronising read per batch (not per iteration)
+            if st.state == L.KMEANS_RUNNING:
+                self.n_iter += m
+            elif st.state == L.KMEANS_NEEDS_HOST:
+                self._host_relocation(st, check)
+            else:
+                self.strict = st.state == L.KMEANS_STRICT
+                self.n_iter = int(st.iter_done)
+                self.stopped = True
+        return self.stopped
 
 class _AccView:
     """The (acc, labels) pair the relocation / finalise helpers take."""
@@ -345,62 +383,77 @@ class _AccView:
         self.shift2 = self.n_empty = None
 
 
+class FitSetup:
+    """What scikit-learn's `fit` does before the first Lloyd iteration, for this rank's shard:
+    global mean / variance (X -= X.mean(0); tol = mean(var(X)) * tol) summed in fixed point — integer
+    sums do not depend on how the rows are split over ranks, so the centred data, and with them every
+    label and centre, are bit-identical for any world size."""
+
+    def __init__(self, x, init, group=None, tol=1e-4, center=True):
+        import torch.distributed as dist
+        x = x.double().contiguous()
+        dev = x.device
+        N, d = x.shape
+        distributed = _dist_on(group)
+
+        def allreduce(t, op=None):
+            if distributed:
+                dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=group)
+            return t
+        MAXOP = dist.ReduceOp.MAX if distributed else None
+        n_tot = allreduce(torch.tensor([N], dtype=torch.int64, device=dev)).double()
+        amax = float(allreduce(x.abs().max().reshape(1) if N else x.new_zeros(1), op=MAXOP))
+        hb0 = _fix_hi_bits(amax)
+        xs = x * float(2.0 ** hb0)
+        fl = torch.floor(xs)
+        limbs = torch.stack([fl.to(torch.int64).sum(0),
+                             torch.trunc((xs - fl) * 4294967296.0).to(torch.int64).sum(0)])
+        del xs, fl
+        allreduce(limbs)
+        mean = (limbs[0].double() * float(2.0 ** -hb0) + limbs[1].double() * float(2.0 ** -(hb0 + 32))) / n_tot
+        d2 = (x - mean) ** 2
+        d2max = float(allreduce(d2.max().reshape(1) if N else x.new_zeros(1), op=MAXOP))
+        sh = 40 if d2max <= 0 else int(max(0, min(40, np.floor(61 - np.log2(d2max * float(n_tot) + 1.0)))))
+        q = allreduce(torch.round(d2 * float(2.0 ** sh)).to(torch.int64).sum(0))
+        del d2
+        var = q.double() * float(2.0 ** -sh) / n_tot
+        self.tol_abs = float(var.mean()) * tol
+        self.mean = mean
+        self.center = center
+        if center:
+            x = x - mean
+            centers = (init.double().to(dev) - mean).contiguous()
+        else:
+            centers = init.double().to(dev).contiguous().clone()
+        max_abs = allreduce(x.abs().max().reshape(1) if N else x.new_zeros(1), op=MAXOP)
+        self.hb = _fix_hi_bits(float(max_abs))
+        self.x, self.centers = x, centers
+        self.group, self.allreduce = group, allreduce
+        self.distributed = distributed
+
+
 def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, center=True,
                  use_grid="auto", _backend=None):
     """Lloyd k-means on this rank's shard `x` [N_local, d] fp64 (CUDA) from explicit centres.
 
-    Returns dict(centers [K,d] fp64, labels [N_local] int32, inertia float, n_iter int).
+    Returns dict(centers [K,d] fp64, labels [N_local] int32, inertia float, n_iter int, exchange).
     With fixed_iters=n the convergence tests are skipped and exactly n E+M iterations run (the
     benchmark's fixed-work mode); otherwise sklearn's stopping rules apply.
     """
-    import torch.distributed as dist
     # _backend: (lloyd_step, finalize) callables standing in for the CUDA entry points — used by the
-    # CPU/gloo tests of this host loop (tests/test_dist_gloo.py); the product path never sets it.
+    # CPU/gloo tests of the host-driven loop (tests/test_dist_gloo.py); the product path never sets it.
     if _backend is None:
         ops._need_cuda(x, init)
         step_fn, finalize_fn = lloyd_step, finalize
     else:
         step_fn, finalize_fn = _backend
         use_grid = False
-    x = x.double().contiguous()
+    fs = FitSetup(x, init, group, tol, center)
+    x, centers, hb, tol_abs, mean = fs.x, fs.centers, fs.hb, fs.tol_abs, fs.mean
+    allreduce = fs.allreduce
     dev = x.device
     N, d = x.shape
     K = init.shape[0]
-    distributed = _dist_on(group)
-
-    def allreduce(t, op=None):
-        if distributed:
-            dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=group)
-        return t
-
-    # global mean / variance of X (sklearn: X -= X.mean(0); tol = mean(var(X)) * tol), summed in
-    # fixed point: integer sums do not depend on how the rows are split over ranks, so the centred
-    # data — and with them every label and centre — are bit-identical for any world size
-    MAXOP = dist.ReduceOp.MAX if distributed else None
-    n_tot = allreduce(torch.tensor([N], dtype=torch.int64, device=dev)).double()
-    amax = float(allreduce(x.abs().max().reshape(1) if N else x.new_zeros(1), op=MAXOP))
-    hb0 = _fix_hi_bits(amax)
-    xs = x * float(2.0 ** hb0)
-    fl = torch.floor(xs)
-    limbs = torch.stack([fl.to(torch.int64).sum(0),
-                         torch.trunc((xs - fl) * 4294967296.0).to(torch.int64).sum(0)])
-    del xs, fl
-    allreduce(limbs)
-    mean = (limbs[0].double() * float(2.0 ** -hb0) + limbs[1].double() * float(2.0 ** -(hb0 + 32))) / n_tot
-    d2 = (x - mean) ** 2
-    d2max = float(allreduce(d2.max().reshape(1) if N else x.new_zeros(1), op=MAXOP))
-    sh = 40 if d2max <= 0 else int(max(0, min(40, np.floor(61 - np.log2(d2max * float(n_tot) + 1.0)))))
-    q = allreduce(torch.round(d2 * float(2.0 ** sh)).to(torch.int64).sum(0))
-    del d2
-    var = q.double() * float(2.0 ** -sh) / n_tot
-    tol_abs = float(var.mean()) * tol
-    if center:
-        x = x - mean
-        centers = (init.double().to(dev) - mean).contiguous()
-    else:
-        centers = init.double().to(dev).contiguous().clone()
-    max_abs = allreduce(x.abs().max().reshape(1), op=MAXOP)
-    hb = _fix_hi_bits(float(max_abs))
 
     state = LloydState(N, K, d, dev)
     centers_new = torch.empty_like(centers)
@@ -412,22 +465,17 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     iters = fixed_iters if fixed_iters is not None else max_iter
     exchange = "host-loop"
     if _backend is None:
-        centers, n_iter, strict, exchange = _kmeans_device_loop(
-            x, centers, state.labels, hb, grid, group, iters, fixed_iters is None, tol_abs)
+        loop = LloydLoop(x, centers, state.labels, hb, grid, group, tol_abs)
+        loop.iterate(iters, check=fixed_iters is None)
+        centers, n_iter, strict, exchange = loop.centers.clone(), loop.n_iter, loop.strict, loop.mode
         iters = 0
     for it in range(iters):
-        if _backend is None:
-            lloyd_iteration(x, centers, centers_new, state, hb, grid=grid, do_finalize=not distributed)
-            if distributed:
-                allreduce(state.acc_stats)
-                finalize_fn(state, centers, centers_new, hb)
-        else:
-            state.acc_stats.zero_()
-            step_fn(x, centers, state, hb, update=True, grid=grid)
-            allreduce(state.acc_stats)
-            finalize_fn(state, centers, centers_new, hb)
+        # host-driven loop (stand-in backends only): one all-reduce + one status read per iteration
+        state.acc_stats.zero_()
+        step_fn(x, centers, state, hb, update=True, grid=grid)
+        allreduce(state.acc_stats)
+        finalize_fn(state, centers, centers_new, hb)
         if fixed_iters is None:
-            # one small D2H read per iteration: {changed, n_empty} and the centre shift
             host = torch.cat([state.stats[:1].double(), state.n_empty.double(), state.shift2]).tolist()
             changed, n_empty, shift2 = int(host[0]), int(host[1]), host[2]
             if n_empty > 0:
@@ -493,7 +541,7 @@ class KMeans:
     labels_, inertia_, n_iter_, fit(X), predict(X).  Pickles hold numpy arrays only."""
 
     def __init__(self, n_clusters=8, init="k-means++", n_init=1, max_iter=300, tol=1e-4,
-                 verbose=0, random_state=0, n_jobs=None, device=None):
+                 verbose=0, random_state=0, n_jobs=None, device=None, group=LOCAL, fixed_iters=None):
         self.n_clusters = n_clusters
         self.init = init
         self.n_init = n_init
@@ -503,6 +551,10 @@ class KMeans:
         self.random_state = random_state
         self.n_jobs = n_jobs          # accepted and ignored (old sklearn API used by the reference)
         self.device = device
+        # extensions: `group` = a torch.distributed process group whose ranks each pass their own rows
+        # to fit() (default: this process alone); `fixed_iters` = run exactly that many iterations
+        self.group = group
+        self.fixed_iters = fixed_iters
 
     def _dev(self):
         return torch.device(self.device) if self.device is not None else torch.device(
@@ -510,7 +562,10 @@ class KMeans:
 
     def fit(self, X, y=None):
         dev = self._dev()
-        x = torch.as_tensor(np.ascontiguousarray(X), dtype=torch.float64).to(dev)
+        if isinstance(X, torch.Tensor):
+            x = X.to(dev, torch.float64, non_blocking=True)
+        else:
+            x = torch.as_tensor(np.ascontiguousarray(X), dtype=torch.float64).to(dev)
         best = None
         n_init = 1 if not isinstance(self.init, str) else max(1, int(self.n_init))
         for trial in range(n_init):
@@ -520,7 +575,8 @@ class KMeans:
                 init = kmeans_plusplus(x, self.n_clusters, seed=int(self.random_state or 0) + trial)
             else:
                 init = torch.as_tensor(np.asarray(self.init), dtype=torch.float64).to(dev)
-            r = kmeans_lloyd(x, init, max_iter=self.max_iter, tol=self.tol)
+            r = kmeans_lloyd(x, init, max_iter=self.max_iter, tol=self.tol, group=self.group,
+                             fixed_iters=self.fixed_iters)
             if self.verbose:
                 print("kmeans trial %d: inertia %.6f after %d iterations" % (trial, r["inertia"],
                                                                              r["n_iter"]))

@@ -332,6 +332,24 @@ class KeyGrid:
         return d in (3, 4) and GRID_MIN_K <= K <= 4096 and N >= GRID_MIN_N
 
 
+def keygrid_stats(grid, x):
+    """Candidate-list statistics of the rotations x [N,d] against a built KeyGrid (diagnostics)."""
+    _need_cuda(x)
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.double()
+    x = x.reshape(x.shape[0], -1).contiguous()
+    st = torch.zeros(5, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.lib().bdp_keygrid_stats(L.ptr(x), _dtype_code(x), x.shape[0], x.shape[1], grid.K,
+                                       L.ptr(grid.buf), grid.nbytes, L.ptr(st), L.stream_ptr())
+    L.check(rc, "bdp_keygrid_stats")
+    n, outside, over, length, mx = [int(v) for v in st.tolist()]
+    fast = max(n - outside - over, 1)
+    return {"points": n, "slow_path_fraction": (outside + over) / max(n, 1),
+            "outside_grid": outside, "overflow_cells": over, "mean_list_length": length / fast,
+            "max_list_length": mx}
+
+
 def _scratch_grid(centers):
     dev = centers.device
     nbytes = L.lib().bdp_keygrid_bytes(centers.shape[0], centers.shape[1])

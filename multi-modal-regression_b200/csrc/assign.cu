@@ -1097,6 +1097,40 @@ void keygrid_pointers(const void* grid, int K, int d, const GridHdr** hdr,
   if (super) *super = *coarse + n_coarse * (kCoarseCap + 1);
 }
 
+// ---- key-grid statistics of a query batch (diagnostics: benchmark / DESIGN numbers) ------------------
+// stats[0] = points, [1] = points outside the grid (slow path), [2] = points in overflowed cells (slow
+// path), [3] = sum of candidate-list lengths over the in-grid points, [4] = max list length seen.
+template <typename T, int D>
+__global__ void __launch_bounds__(256) keygrid_stats_kernel(const T* __restrict__ x, int64_t N,
+                                                            const GridHdr* __restrict__ hdr,
+                                                            const unsigned short* __restrict__ fine,
+                                                            unsigned long long* __restrict__ stats) {
+  const int G = hdr->G;
+  unsigned long long outside = 0, over = 0, len = 0, mx = 0, n = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    bool ok = hdr->enabled != 0;
+    int64_t cidx = 0, mul = 1;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const T org = sizeof(T) == 4 ? (T)hdr->origin32[k] : (T)hdr->origin[k];
+      const T inv = sizeof(T) == 4 ? (T)hdr->inv_cell32[k] : (T)hdr->inv_cell[k];
+      const T t = (x[i * D + k] - org) * inv;
+      ok = ok && (t >= (T)0) && (t < (T)G);
+      cidx += (int64_t)(ok ? (int)t : 0) * mul;
+      mul *= G;
+    }
+    ++n;
+    if (!ok) { ++outside; continue; }
+    const unsigned c = fine[cidx * (kGridCap + 1)];
+    if (c == kGridOverflow) { ++over; continue; }
+    len += c;
+    mx = c > mx ? c : mx;
+  }
+  atomicAdd(stats + 0, n); atomicAdd(stats + 1, outside); atomicAdd(stats + 2, over);
+  atomicAdd(stats + 3, len); atomicMax(stats + 4, mx);
+}
+
 // ---- argmax |<key, q>| -----------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) quatdot_kernel(const T* __restrict__ q, int64_t N,
@@ -1431,6 +1465,30 @@ extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid
                                  void* stream) {
   return bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr,
                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bdp_keygrid_stats(const void* x, int x_dtype, int64_t N, int d, int K, const void* grid,
+                                 int64_t grid_bytes, int64_t* stats, void* stream) {
+  BDP_REQUIRE(N >= 0 && stats, "keygrid_stats: bad arguments");
+  BDP_REQUIRE(d == 3 || d == 4, "keygrid_stats: d must be 3 or 4 (got %d)", d);
+  BDP_REQUIRE(x_dtype == BDP_F32 || x_dtype == BDP_F64, "keygrid_stats: x_dtype %d", x_dtype);
+  int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_stats");
+  if (rc != BDP_OK) return rc;
+  if (N == 0) return BDP_OK;
+  const GridHdr* hdr; const unsigned short *coarse, *fine;
+  keygrid_pointers(grid, K, d, &hdr, &coarse, &fine);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned long long* s = reinterpret_cast<unsigned long long*>(stats);
+  const unsigned blocks = (unsigned)(ceil_div64(N, 256) < 1184 ? ceil_div64(N, 256) : 1184);
+  if (x_dtype == BDP_F32) {
+    if (d == 3) keygrid_stats_kernel<float, 3><<<blocks, 256, 0, st>>>((const float*)x, N, hdr, fine, s);
+    else keygrid_stats_kernel<float, 4><<<blocks, 256, 0, st>>>((const float*)x, N, hdr, fine, s);
+  } else {
+    if (d == 3) keygrid_stats_kernel<double, 3><<<blocks, 256, 0, st>>>((const double*)x, N, hdr, fine, s);
+    else keygrid_stats_kernel<double, 4><<<blocks, 256, 0, st>>>((const double*)x, N, hdr, fine, s);
+  }
+  BDP_CUDA_CHECK_LAUNCH("keygrid_stats_kernel");
+  return BDP_OK;
 }
 
 extern "C" int bdp_assign_nearest_grid(const void* x, int x_dtype, int64_t N, int d,

@@ -36,7 +36,7 @@ if "eval" in which:
         e = ops.geodesic_error_deg(a, b)
         ops.error_stats(e, labels, 12)
 if "head" in which:
-    from bdpose import head
-    head.profile(dev)
+    import bench_head
+    bench_head.profile(dev)
 torch.cuda.synchronize()
 print("done")

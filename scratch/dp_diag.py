@@ -1,7 +1,8 @@
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multi-modal-regression_b200")); sys.path.insert(0, ROOT)
-import torch, torch.distributed as dist
+import torch
+import bench_head, torch.distributed as dist
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
@@ -20,7 +21,7 @@ for n in (1_000_000, 5_403_703, 20_000_000, 62_444_436):
     s = t(lambda: dist.all_reduce(x, op=dist.ReduceOp.SUM))
     if rank == 0: print("allreduce %9d floats: AVG %.3f ms  SUM %.3f ms" % (n, a, s), flush=True)
 from bdpose import head
-r = head.bench_dp(dev, world)
+r = bench_head.bench_dp(dev, world)
 if rank == 0:
     for k, v in r.items(): print(k, v, flush=True)
 # the same step without the collective

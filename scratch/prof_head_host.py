@@ -2,9 +2,10 @@ import os, sys, time, cProfile, pstats
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multi-modal-regression_b200"))
 import torch
+import bench_head
 from bdpose import head, ops, _lib as L
 dev = torch.device("cuda", 0)
-m = head._pascal_model().train()
+m = bench_head._pascal_model().train()
 keys = torch.randn(200, 3, device=dev)
 B = 32
 x = torch.randn(B, 2048, device=dev, requires_grad=True)

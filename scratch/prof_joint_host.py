@@ -2,10 +2,11 @@ import os, sys, cProfile, pstats
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multi-modal-regression_b200"))
 import torch
+import bench_head
 from bdpose import head, ops, _lib as L
 dev = torch.device("cuda", 0)
 C, K, B = 12, 200, 32
-mj = head._pascal_model(C, K).train()
+mj = bench_head._pascal_model(C, K).train()
 fcj = torch.nn.Linear(2048, C).cuda()
 jparams = list(mj.parameters()) + list(fcj.parameters())
 keys = torch.randn(K, 3, device=dev)

@@ -2,9 +2,10 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multi-modal-regression_b200"))
 import torch
+import bench_head
 from bdpose import head, ops, _lib as L
 dev = torch.device("cuda", 0)
-m = head._pascal_model().train()
+m = bench_head._pascal_model().train()
 keys = torch.randn(200, 3, device=dev)
 params = list(m.parameters())
 def t(fn, n=30):

@@ -1,5 +1,6 @@
 """bench.py's reference arm prints ONE JSON line with the contract's keys (CPU only: the arm times the
-reference's own CPU implementation of the path, scikit-learn's KMeans.predict + the residual)."""
+reference's own CPU implementation of the path, scikit-learn's KMeans.fit; the test shrinks the data
+set through BDP_BENCH_REF_ROTATIONS)."""
 import json
 import os
 import subprocess
@@ -11,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600,
-                         cwd=ROOT)
+                         cwd=ROOT, env=dict(os.environ, BDP_BENCH_REF_ROTATIONS="200000"))
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, "exactly one line on stdout, got %d" % len(lines)
@@ -21,7 +22,7 @@ def test_reference_arm_json_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["steps"] == 1 and d["warmup"] == 0 and d["higher_is_better"] is True
-    assert d["value"] > 0 and d["unit"] == "rotations/s"
+    assert d["value"] > 0 and d["unit"] == "rotation-iterations/s"
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
