@@ -412,19 +412,20 @@ def main():
         raise SystemExit("bench.py: the timed fit stopped early (state %d after %d iterations)"
                          % (st.state, st.iter_done))
     centers_timed = loop.centers.clone()
-    clocks = clk.summary()
-    if clocks["samples"] < 3:
-        # the timed region is a few ms: keep the same iterations running for ~0.7 s so that
-        # nvidia-smi sees the clocks and throttle reasons under this load
-        with ClockSampler(local) as clk2:
-            t_end = time.perf_counter() + 0.7
-            while time.perf_counter() < t_end:
-                fit_region(steps)
-        clk2.rows = clk.rows + clk2.rows
-        clocks = clk2.summary()
-        clocks["note"] = "timed region is %.1f ms; sampled over it plus 0.7 s more of the same iterations" % float(ms_total)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    clocks = clk.summary()
+    # the timed region is a few ms: keep the same iterations running for ~0.7 s so that nvidia-smi
+    # sees the clocks and throttle reasons under this load (the SAME number of repetitions on every
+    # rank: each one contains collectives)
+    reps = max(1, min(100, int(700.0 / max(float(ms_total), 1.0))))
+    with ClockSampler(local) as clk2:
+        for _ in range(reps):
+            fit_region(steps)
+    clk2.rows = clk.rows + clk2.rows
+    clocks = clk2.summary()
+    clocks["note"] = ("timed region is %.1f ms; sampled over it plus %d more repetitions of the same "
+                      "iterations" % (float(ms_total), reps))
     ms_step = float(ms_total) / steps
     value = N_ROT / (ms_step * 1e-3)
 

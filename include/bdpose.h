@@ -270,6 +270,8 @@ int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
  *     int64 acc[2][K*(2d+1) + 2]     two accumulators {cluster sums, counts, changed, unused},
  *                                    used alternately by even and odd iterations
  *     uint64 flags[BDP_KMEANS_MAX_RANKS]   flags[r] = last iteration rank r has published here
+ *     uint64 gflags[BDP_KMEANS_MAX_RANKS]  gflags[r] = last iteration whose key-grid slab rank r has
+ *                                    stored into this rank's grid (sharded build)
  * xchg[r] is THIS process's address of rank r's buffer (xchg[rank] is the local one); xchg_multicast
  * is an NVLS multicast mapping of the same buffers (sums are then taken by one in-switch
  * multimem.ld_reduce per word) or NULL (one load per rank and word over NVLink).
@@ -287,6 +289,10 @@ int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
  *     scan), runs the E+M step on this rank's rows into acc[i & 1] and calls the exchange step, which
  *     writes centers2[(i & 1) ^ 1].  Once the status leaves BDP_KMEANS_RUNNING the remaining launches
  *     do nothing; status.iter_done tells which centres buffer is current.
+ *     grid_peers (NULL: every rank builds the whole grid itself) = this process's addresses of
+ *     every rank's key-grid buffer, allocated like the exchange buffers: the build is then SHARDED —
+ *     a rank builds the cells of one slab of the grid and stores them into every rank's buffer over
+ *     NVLink, and the E+M kernel waits until all slabs have arrived (flags in the exchange buffer).
  *     BDP_KMEANS_NEEDS_HOST: an empty cluster appeared; the caller relocates (scikit-learn
  *     _relocate_empty_clusters_dense) on the summed accumulator, finalises with bdp_kmeans_finalize,
  *     clears status.state and resumes with iter0 = status.iter_done.
@@ -307,7 +313,7 @@ int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_multicast, 
                                  int check, double tol_abs, const double* centers_old,
                                  double* centers_new, void* ctl, void* stream);
 int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers2, int K, void* grid,
-                   int64_t grid_bytes, int32_t* labels, void* const* xchg,
+                   int64_t grid_bytes, void* const* grid_peers, int32_t* labels, void* const* xchg,
                    const void* xchg_multicast, int world, int rank, int fix_hi_bits, int64_t iter0,
                    int n_iters, int check, double tol_abs, void* ctl, void* stream);
 

@@ -223,6 +223,23 @@ class Exchange:
     def acc(self, parity):
         return self.buf[parity * self.A:(parity + 1) * self.A]
 
+    def shared_grid(self, nbytes):
+        """A key-grid buffer every rank can store into (sharded build), or None when the exchange
+        is not over peer memory.  Returns (uint8 tensor, ctypes array of every rank's address)."""
+        import ctypes as C
+        if not self.mode.startswith("p2p") or os.environ.get("BDPOSE_KMEANS_SHARD_GRID", "1") == "0":
+            return None
+        cur = getattr(self, "_grid", None)
+        if cur is None or cur[0].numel() < nbytes:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            pg = self.group if self.group is not None else dist.group.WORLD
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=self.buf.device)
+            hdl = symm.rendezvous(buf, pg)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            cur = self._grid = (buf, (C.c_void_p * self.world)(*ptrs), hdl)
+        return cur[0], cur[1]
+
     def ptr_array(self):
         import ctypes as C
         if self.mode in ("local", "nccl"):
@@ -263,6 +280,14 @@ class LloydLoop:
         self.ctl = torch.zeros(lib.bdp_kmeans_ctl_bytes(), dtype=torch.uint8, device=self.dev)
         self.c2 = torch.stack([centers, centers]).contiguous()
         self.ptrs, self.world, self.rank = self.ex.ptr_array()
+        # sharded key-grid build: the grid lives in peer-addressable memory, every rank builds one
+        # slab of it per iteration and stores the slab into every rank's copy
+        self.grid_ptrs = None
+        if grid is not None:
+            sg = self.ex.shared_grid(grid.nbytes)
+            if sg is not None:
+                self.grid = ops.KeyGrid(centers, buf=sg[0], build=False)
+                self.grid_ptrs = sg[1]
         self._tmp_shift = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._tmp_empty = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.n_iter, self.strict, self.stopped = 0, False, False
@@ -291,7 +316,8 @@ class LloydLoop:
         with torch.cuda.device(self.dev):
             st = lib.bdp_kmeans_run(self.x.data_ptr(), self.N, self.d, self.c2.data_ptr(), self.K,
                                     None if g is None else g.buf.data_ptr(), 0 if g is None else g.nbytes,
-                                    self.labels.data_ptr(), self.ptrs, self.ex.mc, self.world, self.rank,
+                                    self.grid_ptrs, self.labels.data_ptr(), self.ptrs, self.ex.mc,
+                                    self.world, self.rank,
                                     self.hb, i0, n, 1 if check else 0, self.tol_abs,
                                     self.ctl.data_ptr(), L.stream_ptr())
         L.check(st, "bdp_kmeans_run")

@@ -304,7 +304,7 @@ _grid_ws = {}     # (device index, stream, bytes) -> grid buffer, reused (rebuil
 class KeyGrid:
     """Device buffer holding the key grid of one dictionary (bdp_keygrid_build)."""
 
-    def __init__(self, centers, buf=None):
+    def __init__(self, centers, buf=None, build=True):
         _need_cuda(centers)
         self.centers = centers.double().contiguous()
         self.K, self.d = self.centers.shape
@@ -315,7 +315,8 @@ class KeyGrid:
         if buf is None or buf.numel() < self.nbytes or buf.device != dev:
             buf = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)
         self.buf = buf
-        self.rebuild()
+        if build:                 # build=False: the owner builds it (sharded multi-GPU build)
+            self.rebuild()
 
     def rebuild(self, centers=None):
         """(Re)build for the current / new centre values (same shape); no host synchronisation."""

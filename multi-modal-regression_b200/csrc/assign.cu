@@ -15,56 +15,13 @@
 // Lloyd accumulation is exact: every coordinate is split into two int64 fixed-point limbs and
 // added with integer atomics (shared memory per block, then global), so the cluster sums do not
 // depend on the order of accumulation, the grid, or how the points are sharded over GPUs.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "assign_common.cuh"
+
+using namespace bdp_assign;
 
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kPts = 4;                 // points per thread
-constexpr int kChunk = 2048;            // dictionary records staged per shared-memory pass
-constexpr int kMaxSmemAccK = 2048;      // largest K whose int64 accumulators live in shared memory
-
-template <int D> struct CenterRec;      // fp32 screening record
-template <> struct CenterRec<3> { float4 v; };                 // (-2c0,-2c1,-2c2,|c|^2)
-template <> struct CenterRec<4> { float4 v; float n; };       // (-2c0..-2c3), |c|^2
-
-template <int D>
-__device__ __forceinline__ float screen_dist(const float* x, const float4& c, float cn) {
-  if (D == 3) return fmaf(x[0], c.x, fmaf(x[1], c.y, fmaf(x[2], c.z, c.w)));
-  return fmaf(x[0], c.x, fmaf(x[1], c.y, fmaf(x[2], c.z, fmaf(x[3], c.w, cn))));
-}
-
-// exact split of x*2^hi_bits into an integer part and 32 fractional bits (truncated below)
-__device__ __forceinline__ void to_limbs(double x, double scale_hi, long long& hi, long long& lo) {
-  const double xs = x * scale_hi;           // power-of-two scale: exact
-  const double f = floor(xs);
-  hi = (long long)f;
-  lo = (long long)((xs - f) * 4294967296.0);  // (xs-f) in [0,1) exact; product exact; trunc
-}
-
-struct GridHdr;
-struct AssignParams {
-  const void* x;
-  int64_t N;
-  const double* centers;   // [K, D] fp64
-  int K;
-  int32_t* labels32;       // out (assign) / in-out (lloyd)
-  int64_t* labels64;
-  float* residual;
-  double* min_sqdist;
-  // lloyd
-  unsigned long long* acc; // [K, 2D+1]
-  double scale_hi;
-  unsigned long long* stats;
-  double* inertia;
-  int update;
-  float err_coef;          // 2^-24 * 2(D+5) * safety
-  // key grid (candidate pruning); NULL for the brute-force kernel
-  const struct GridHdr* ghdr;
-  const unsigned short* gfine;
-  // device flag of a k-means run (bdp_kmeans_run): non-zero = the fit has stopped, do nothing
-  const int* stop;
-};
 
 template <typename T, int D>
 __device__ __forceinline__ void load_point(const T* __restrict__ x, int64_t i, double xd[D],
@@ -312,11 +269,6 @@ int launch_assign(const AssignParams& P, cudaStream_t st) {
 }
 
 
-float screen_err_coef(int D) {
-  // |fl32(dist) - dist| <= (D + 2.1) * 2^-24 * (||x|| + ||c||)^2 (input rounding of x, -2c, ||c||^2
-  // plus one rounding per fma); the best/second GAP carries twice that.  x2 safety on top.
-  return (float)(2.0 * 2.0 * (D + 5) * 5.9604644775390625e-08);
-}
 
 template <bool LLOYD>
 int dispatch_assign(AssignParams& P, int x_dtype, int d, cudaStream_t st) {
@@ -344,27 +296,6 @@ int dispatch_assign(AssignParams& P, int x_dtype, int d, cudaStream_t st) {
 // ~5 candidates per point instead of K — exactly the same fp32-screen / fp64-exact arithmetic as the
 // brute-force kernel, on a superset of the keys that matter, so the labels are identical.  Points
 // outside the grid and cells whose list overflows the 64-byte record take the brute-force slow path.
-constexpr int kGridCap = 31;                 // ids per fine record  (u16 count + 31 u16 ids = 64 B)
-constexpr int kCoarseCap = 255;              // ids per coarse record (512 B)
-constexpr int kGridMaxK = 4096;              // fp32 screening records of the whole dictionary in smem
-constexpr unsigned kGridOverflow = 0xFFFFu;
-// Cell boxes are grown by this fraction of a cell on every side before the bounds are taken, which
-// covers the rounding of the point -> cell mapping in the query (fp32 for fp32 rotations: the cell
-// coordinate is off by < 3e-5 cells; fp64: < 1e-13).
-constexpr double kBoxEps = 1e-3;
-
-struct GridHdr {
-  double origin[4];
-  double cell[4];
-  double inv_cell[4];
-  int G;            // fine cells per dimension (multiple of 4)
-  int enabled;      // 0: degenerate dictionary -> every point takes the slow path
-  int pad[6];
-  float origin32[4];
-  float inv_cell32[4];
-};
-static_assert(sizeof(GridHdr) == 160, "GridHdr layout");
-
 __host__ __device__ inline int64_t ipow64(int64_t b, int e) {
   int64_t r = 1;
   for (int i = 0; i < e; ++i) r *= b;
@@ -584,14 +515,15 @@ __global__ void __launch_bounds__(256) keygrid_super_kernel(const double* __rest
                                                             int G, double margin_frac,
                                                             GridHdr* __restrict__ hdr,
                                                             unsigned short* __restrict__ super,
-                                                            const int* stop) {
+                                                            int super0, const int* stop) {
   if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
   __shared__ GridHdr s_hdr;
   compute_header<D>(centers, K, G, margin_frac, &s_hdr);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *hdr = s_hdr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { s_hdr.side_next = 0u; s_hdr.ticket = 0u; *hdr = s_hdr; }
   const int Gs = (G / 4 + 3) / 4;
   double lo[D], hi[D];
-  int r = blockIdx.x;
+  const int cell = super0 + blockIdx.x;             // this rank's slab of super cells
+  int r = cell;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     const int ck = r % Gs;
@@ -600,7 +532,7 @@ __global__ void __launch_bounds__(256) keygrid_super_kernel(const double* __rest
     lo[k] = s_hdr.origin[k] + (double)(16 * ck) * s_hdr.cell[k] - eps;
     hi[k] = s_hdr.origin[k] + (double)min(16 * ck + 16, G) * s_hdr.cell[k] + eps;
   }
-  filter_box_block<D>(centers, K, lo, hi, super + (int64_t)blockIdx.x * (K + 1));
+  filter_box_block<D>(centers, K, lo, hi, super + (int64_t)cell * (K + 1));
 }
 
 // Coarse cells (4 fine cells per side): one warp filters its super cell's list against one cell.
@@ -609,14 +541,14 @@ __global__ void __launch_bounds__(256) keygrid_coarse_kernel(const double* __res
                                                              int K, const GridHdr* __restrict__ hdr,
                                                              const unsigned short* __restrict__ super,
                                                              unsigned short* __restrict__ coarse,
+                                                             int64_t cell0, int64_t cell1,
                                                              const int* stop) {
   if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
   const int lane = threadIdx.x & 31;
   const int Gc = hdr->G / 4, Gs = (Gc + 3) / 4;
-  const int64_t n_cells = ipow64(Gc, D);
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t cell = warp0; cell < n_cells; cell += n_warps) {
+  for (int64_t cell = cell0 + warp0; cell < cell1; cell += n_warps) {
     double lo[D], hi[D];
     int64_t r = cell, parent = 0, pm = 1;
 #pragma unroll
@@ -635,442 +567,135 @@ __global__ void __launch_bounds__(256) keygrid_coarse_kernel(const double* __res
   }
 }
 
+// Where a build writes its cells: the fine / side arrays of every rank of a multi-GPU fit (peer
+// addresses; world == 1: this grid only) and the flags that tell the peers the slab is complete.
+struct BuildOut {
+  uint4* fine[BDP_KMEANS_MAX_RANKS];
+  unsigned short* side[BDP_KMEANS_MAX_RANKS];
+  unsigned long long* gflags[BDP_KMEANS_MAX_RANKS];
+  int world, rank;
+  unsigned side_per_rank;        // side records each rank may hand out
+  unsigned long long flag_value;
+};
+
 // Fine cells: one THREAD per cell, the 4^D children of a coarse cell on adjacent threads, so the
-// parent's key list and the keys themselves are warp-uniform (broadcast) loads.
+// parent's key list and the keys themselves are warp-uniform (broadcast) loads.  A thread assembles
+// its 16-byte record in registers and stores it to every rank's grid (one 128-bit store per peer,
+// posted over NVLink); the last block to finish raises this rank's flag on every peer.
 template <int D>
 __global__ void __launch_bounds__(256) keygrid_fine_kernel(const double* __restrict__ centers, int K,
-                                                           const GridHdr* __restrict__ hdr,
+                                                           GridHdr* __restrict__ hdr,
                                                            const unsigned short* __restrict__ coarse,
-                                                           unsigned short* __restrict__ fine,
-                                                           const int* stop) {
+                                                           const BuildOut out, int64_t parent0,
+                                                           int64_t n_cells, const int* stop) {
   if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
   constexpr int kChildren = D == 3 ? 64 : 256;
   const int G = hdr->G, Gc = G / 4;
-  const int64_t n_fine = ipow64(G, D);
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_fine) return;
-  const int64_t parent = t / kChildren;
-  int child = (int)(t % kChildren);
-  double lo[D], hi[D];
-  int64_t pr = parent, cell = 0, mul = 1;
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const int ck = 4 * (int)(pr % Gc) + (child & 3);
-    pr /= Gc;
-    child >>= 2;
-    const double eps = kBoxEps * hdr->cell[k];
-    lo[k] = hdr->origin[k] + (double)ck * hdr->cell[k] - eps;
-    hi[k] = hdr->origin[k] + (double)(ck + 1) * hdr->cell[k] + eps;
-    cell += (int64_t)ck * mul;
-    mul *= G;
-  }
-  const unsigned short* prec = coarse + parent * (kCoarseCap + 1);
-  const unsigned pc = prec[0];
-  const bool all = pc == kGridOverflow;
-  const int n_src = all ? K : (int)pc;
-  double u = INFINITY;
-  int piv = 0;
-  for (int j = 0; j < n_src; ++j) {
-    const int k = all ? j : (int)prec[1 + j];
-    double mn, mx;
-    box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-    if (mx < u) { u = mx; piv = k; }
-  }
-  const double thr = u * (1.0 + 1e-9) + 1e-300;
-  double cp[D];
-#pragma unroll
-  for (int k = 0; k < D; ++k) cp[k] = __ldg(centers + (int64_t)piv * D + k);
-  unsigned short* rec = fine + cell * (kGridCap + 1);
-  int cnt = 0;
-  for (int j = 0; j < n_src; ++j) {
-    const int k = all ? j : (int)prec[1 + j];
-    double mn, mx, sc;
-    box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-    const double bm = bisector_min<D>(centers + (int64_t)k * D, cp, lo, hi, sc);
-    if (mn <= thr && bm <= 1e-9 * sc) {
-      if (cnt < kGridCap) rec[1 + cnt] = (unsigned short)k;        // ascending key order
-      ++cnt;
-    }
-  }
-  rec[0] = (unsigned short)(cnt > kGridCap ? kGridOverflow : (unsigned)cnt);
-}
-
-// Query.  Every warp owns 32*kGPts consecutive points of a block tile: the points come in and the
-// residuals go out through a warp-private shared-memory stage so that global traffic is full 128-byte
-// lines (a 12-byte point per lane would touch every line three times).  Lloyd sums go to shared
-// memory as NATIVE 32-bit atomics on 16-bit chunks of the two fixed-point limbs (a 64-bit shared
-// atomicAdd is a compare-and-swap loop); a block folds its chunk counters into the global int64
-// accumulators every 2^16 points, before a counter can overflow.
-constexpr int kGThreads = 512;
-constexpr int kGWarps = kGThreads / 32;
-constexpr int kGPts = 2;
-constexpr int kGTile = kGThreads * kGPts;
-constexpr int kFlushTiles = 65536 / kGTile;
-
-template <int D>
-__device__ __forceinline__ void flush_acc32(unsigned* s_acc32, int K, unsigned long long* acc) {
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < K * (D + 1); idx += kGThreads) {
-    const int j = idx / (D + 1), k = idx % (D + 1);
-    const unsigned* a = s_acc32 + (size_t)j * (4 * D + 1);
-    const unsigned cnt = a[4 * D];
-    if (cnt == 0u) continue;
-    unsigned long long* g = acc + (size_t)j * (2 * D + 1);
-    if (k == D) {
-      atomicAdd(g + 2 * D, (unsigned long long)cnt);
-    } else {
-      const long long hi = (long long)a[4 * k] + ((long long)a[4 * k + 1] << 16) -
-                           (long long)cnt * 2147483648LL;          // remove the +2^31 bias
-      const unsigned long long lo = (unsigned long long)a[4 * k + 2] +
-                                    ((unsigned long long)a[4 * k + 3] << 16);
-      if (hi) atomicAdd(g + 2 * k, (unsigned long long)hi);
-      if (lo) atomicAdd(g + 2 * k + 1, lo);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < K * (4 * D + 1); i += kGThreads) s_acc32[i] = 0u;
-  __syncthreads();
-}
-
-template <typename T, int D, bool LLOYD>
-__global__ void __launch_bounds__(kGThreads, 2) assign_grid_kernel(const AssignParams P) {
-  if (P.stop != nullptr && *reinterpret_cast<const volatile int*>(P.stop) != 0) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [K float4 recs][K float norms (D==4)][warp stages][chunk accumulators (lloyd)]
-  float4* s_rec = reinterpret_cast<float4*>(smem_raw);
-  float* s_cn = reinterpret_cast<float*>(s_rec + P.K);
-  double* s_stage_all = reinterpret_cast<double*>(s_cn + (D == 4 ? ((P.K + 3) & ~3) : 0));
-  unsigned* s_acc32 = reinterpret_cast<unsigned*>(s_stage_all + kGWarps * kGPts * 32 * D);
-  __shared__ double s_red[2][kGWarps];
-  __shared__ float s_cmax[kGWarps];
-  const bool acc_in_smem = LLOYD && P.update && P.K <= kMaxSmemAccK;
-
-  const T* __restrict__ x = reinterpret_cast<const T*>(P.x);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t n_tiles = (P.N + kGTile - 1) / kGTile;
-  T* stage = reinterpret_cast<T*>(s_stage_all + warp * (kGPts * 32 * D));
-  float* rstage = reinterpret_cast<float*>(stage);
-
-  if (acc_in_smem) {
-    for (int i = threadIdx.x; i < P.K * (4 * D + 1); i += kGThreads) s_acc32[i] = 0u;
-  }
-  // stage the fp32 screening records of the whole dictionary + max ||c|| for the error bound
-  float cmax = 0.f;
-  for (int j = threadIdx.x; j < P.K; j += kGThreads) {
-    const double* c = P.centers + (int64_t)j * D;
-    double cn = 0.0;
-    float m2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (t < n_cells) {
+    const int64_t parent = parent0 + t / kChildren;
+    int child = (int)(t % kChildren);
+    double lo[D], hi[D];
+    int64_t pr = parent, cell = 0, mul = 1;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const double ck = __ldg(c + k);
-      cn += ck * ck;
-      m2[k] = (float)(-2.0 * ck);
+      const int ck = 4 * (int)(pr % Gc) + (child & 3);
+      pr /= Gc;
+      child >>= 2;
+      const double eps = kBoxEps * hdr->cell[k];
+      lo[k] = hdr->origin[k] + (double)ck * hdr->cell[k] - eps;
+      hi[k] = hdr->origin[k] + (double)(ck + 1) * hdr->cell[k] + eps;
+      cell += (int64_t)ck * mul;
+      mul *= G;
     }
-    if (D == 3) s_rec[j] = make_float4(m2[0], m2[1], m2[2], (float)cn);
-    else { s_rec[j] = make_float4(m2[0], m2[1], m2[2], m2[3]); s_cn[j] = (float)cn; }
-    cmax = fmaxf(cmax, (float)sqrt(cn) * 1.000001f);
-  }
-  cmax = warp_max(cmax);
-  if (lane == 0) s_cmax[warp] = cmax;
-  __syncthreads();
-#pragma unroll
-  for (int w = 0; w < kGWarps; ++w) cmax = fmaxf(cmax, s_cmax[w]);
-
-  // point -> cell in the arithmetic of the input type (see kBoxEps)
-  T g_org[D], g_inv[D];
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    if (sizeof(T) == 4) { g_org[k] = (T)P.ghdr->origin32[k]; g_inv[k] = (T)P.ghdr->inv_cell32[k]; }
-    else { g_org[k] = (T)P.ghdr->origin[k]; g_inv[k] = (T)P.ghdr->inv_cell[k]; }
-  }
-  const int G = P.ghdr->G;
-  const bool g_on = P.ghdr->enabled != 0;
-  const T Gt = (T)G;
-  const bool want_sq = LLOYD ? (P.inertia != nullptr) : (P.min_sqdist != nullptr);
-
-  int changed = 0, tiles_since_flush = 0;
-  double inertia = 0.0;
-
-  // Software pipeline over tiles: the rotations (and, for Lloyd, the previous labels) of the NEXT
-  // tile are requested before the current tile is processed, so their DRAM latency overlaps the
-  // record gather, the candidate screen and the stores of the current one (the kernel was bound by
-  // exposed load latency: x -> cell -> record -> old label were four serial round trips per tile).
-  T nx[kGPts * D];
-  int nlab[kGPts];
-  auto prefetch = [&](int64_t tile) {
-    const int64_t wb = tile * kGTile + (int64_t)warp * (32 * kGPts);
-    const int64_t rem = P.N - wb;
-    const int nv = rem <= 0 ? 0 : (rem < 32 * kGPts ? (int)rem : 32 * kGPts);
-#pragma unroll
-    for (int j = 0; j < kGPts * D; ++j) {
-      const int idx = j * 32 + lane;
-      nx[j] = idx < nv * D ? __ldcs(x + wb * D + idx) : (T)0;   // touched once: keep L1 for the keys
+    const unsigned short* prec = coarse + parent * (kCoarseCap + 1);
+    const unsigned pc = prec[0];
+    const bool all = pc == kGridOverflow;
+    const int n_src = all ? K : (int)pc;
+    double u = INFINITY;
+    int piv = 0;
+    for (int j = 0; j < n_src; ++j) {
+      const int k = all ? j : (int)prec[1 + j];
+      double mn, mx;
+      box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
+      if (mx < u) { u = mx; piv = k; }
     }
-    if (LLOYD) {
+    const double thr = u * (1.0 + 1e-9) + 1e-300;
+    double cp[D];
 #pragma unroll
-      for (int p = 0; p < kGPts; ++p) {
-        const int li = p * 32 + lane;
-        nlab[p] = li < nv ? __ldcs(P.labels32 + wb + li) : 0;
-      }
-    }
-  };
-  if ((int64_t)blockIdx.x < n_tiles) prefetch(blockIdx.x);
-
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t wbase = tile * kGTile + (int64_t)warp * (32 * kGPts);
-    const int64_t nrem = P.N - wbase;
-    const int nval = nrem <= 0 ? 0 : (nrem < 32 * kGPts ? (int)nrem : 32 * kGPts);
-    // this warp's points: prefetched registers -> shared stage (whole 128-byte lines came in)
-    int olab[kGPts];
-#pragma unroll
-    for (int j = 0; j < kGPts * D; ++j) stage[j * 32 + lane] = nx[j];
-#pragma unroll
-    for (int p = 0; p < kGPts; ++p) olab[p] = nlab[p];
-    __syncwarp();
-    if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
-    T xv[kGPts][D];          // the rotations in their input type; widened where exactness needs it
-    const uint4* recp[kGPts];
-    uint4 first[kGPts];
-    bool in_grid[kGPts], valid[kGPts];
-    // phase 1: points -> cells -> first 16 bytes of every record (all loads in flight together)
-#pragma unroll
-    for (int p = 0; p < kGPts; ++p) {
-      const int li = p * 32 + lane;
-      valid[p] = li < nval;
-      bool ok = g_on && valid[p];
-      int64_t cidx = 0, mul = 1;
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        xv[p][k] = valid[p] ? stage[li * D + k] : (T)0;
-        const T t = (xv[p][k] - g_org[k]) * g_inv[k];
-        ok = ok && (t >= (T)0) && (t < Gt);             // false for NaN as well
-        const int ck = ok ? (int)t : 0;                 // t >= 0: truncation == floor
-        cidx += (int64_t)ck * mul;
-        mul *= G;
-      }
-      in_grid[p] = ok;
-      recp[p] = reinterpret_cast<const uint4*>(P.gfine + (ok ? cidx : 0) * (kGridCap + 1));
-      first[p] = __ldg(recp[p]);
-    }
-    __syncwarp();                                       // stage is reused for the residuals
-    // phase 2: fp32 screen over the candidates, fp64 exact pass on near ties
-    int label[kGPts];
-    bool slow[kGPts];
-#pragma unroll
-    for (int p = 0; p < kGPts; ++p) {
-      label[p] = 0;
-      const unsigned cnt = first[p].x & 0xFFFFu;
-      slow[p] = valid[p] && (!in_grid[p] || cnt == kGridOverflow);
-      if (!valid[p] || slow[p]) continue;
-      float xf[D];
-      float n2 = 0.f;
-#pragma unroll
-      for (int k = 0; k < D; ++k) { xf[k] = (float)xv[p][k]; n2 += xf[k] * xf[k]; }
-      const float sN = sqrtf(n2) * 1.0000002f + cmax;
-      const float tau = P.err_coef * sN * sN;
-      float best = INFINITY, second = INFINITY;
-      int bidx = 0;
-      // Entries 1..7 sit in the 16 bytes already loaded: statically unrolled, two instructions turn
-      // a 16-bit id into the byte offset of its screening record (a generic shift of the 128-bit
-      // register group cost five per candidate).  Longer lists (3 % of the cells) continue from
-      // global memory.
-      unsigned boff = 0;                                 // byte offset (id * 16) of the best record
-      const unsigned fw[4] = {first[p].x, first[p].y, first[p].z, first[p].w};
-      const char* recs = reinterpret_cast<const char*>(s_rec);
-#pragma unroll
-      for (int e = 1; e <= 7; ++e) {
-        if ((unsigned)e > cnt) break;
-        const unsigned w = fw[e >> 1];
-        const unsigned off = (e & 1) ? ((w >> 12) & 0xFFFF0u) : ((w << 4) & 0xFFFF0u);
-        const float4 cr = *reinterpret_cast<const float4*>(recs + off);
-        const float cn = (D == 4) ? s_cn[off >> 4] : 0.f;
-        const float d = screen_dist<D>(xf, cr, cn);
-        const bool lt = d < best;
-        second = fminf(second, lt ? best : d);
-        boff = lt ? off : boff;
-        best = fminf(best, d);
-      }
-      if (cnt > 7u) {
-        const unsigned short* ids = reinterpret_cast<const unsigned short*>(recp[p]);
-        for (unsigned e = 8; e <= cnt; ++e) {
-          const unsigned off = (unsigned)__ldg(ids + e) << 4;
-          const float4 cr = *reinterpret_cast<const float4*>(recs + off);
-          const float cn = (D == 4) ? s_cn[off >> 4] : 0.f;
-          const float d = screen_dist<D>(xf, cr, cn);
-          const bool lt = d < best;
-          second = fminf(second, lt ? best : d);
-          boff = lt ? off : boff;
-          best = fminf(best, d);
-        }
-      }
-      bidx = (int)(boff >> 4);
-      if (!(second - best > tau) && cnt > 1u) {
-        // near tie: exact fp64 pass over the same candidates (ascending ids: lowest index wins)
-        double bd = INFINITY;
-        const unsigned short* ids = reinterpret_cast<const unsigned short*>(recp[p]);
-        for (unsigned e = 1; e <= cnt; ++e) {
-          const int id = (int)__ldg(ids + e);
-          const double* c = P.centers + (int64_t)id * D;
-          double sq = 0.0;
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            const double df = (double)xv[p][k] - __ldg(c + k);
-            sq += df * df;
-          }
-          if (sq < bd) { bd = sq; bidx = id; }
-        }
-      }
-      label[p] = bidx;
-    }
-    // slow path: points outside the grid / in overflowed cells, the whole warp scans the dictionary
-#pragma unroll
-    for (int p = 0; p < kGPts; ++p) {
-      unsigned m = __ballot_sync(BDP_FULL_MASK, slow[p]);
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        double xe[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) xe[k] = (double)__shfl_sync(BDP_FULL_MASK, xv[p][k], src);
-        double bd = INFINITY;
-        int bi = 0x7fffffff;
-        for (int j = lane; j < P.K; j += 32) {
-          const double* c = P.centers + (int64_t)j * D;
-          double sq = 0.0;
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            const double df = xe[k] - __ldg(c + k);
-            sq += df * df;
-          }
-          if (sq < bd) { bd = sq; bi = j; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double od = __shfl_xor_sync(BDP_FULL_MASK, bd, o);
-          const int oi = __shfl_xor_sync(BDP_FULL_MASK, bi, o);
-          if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-        if (bi == 0x7fffffff) bi = 0;                    // all distances NaN: argmin gives 0
-        if (lane == src) label[p] = bi;
-      }
-    }
-    // emit
-#pragma unroll
-    for (int p = 0; p < kGPts; ++p) {
-      if (!valid[p]) continue;
-      const int li = p * 32 + lane;
-      const int64_t i = wbase + li;
-      double diff[D], sq = 0.0;
-      if (!LLOYD || want_sq) {
-        const double* c = P.centers + (int64_t)label[p] * D;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-          diff[k] = (double)xv[p][k] - __ldg(c + k);
-          sq += diff[k] * diff[k];
-        }
-      }
-      if (LLOYD) {
-        changed += (olab[p] != label[p]);
-        __stcs(P.labels32 + i, label[p]);
-        inertia += sq;
-        if (P.update) {
-          if (acc_in_smem) {
-            unsigned* a = s_acc32 + (size_t)label[p] * (4 * D + 1);
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-              long long hi, lo;
-              to_limbs((double)xv[p][k], P.scale_hi, hi, lo);
-              const unsigned ub = (unsigned)(hi + 2147483648LL);      // hi in [-2^31, 2^31)
-              const unsigned ul = (unsigned)lo;
-              atomicAdd(a + 4 * k, ub & 0xFFFFu);
-              atomicAdd(a + 4 * k + 1, ub >> 16);
-              atomicAdd(a + 4 * k + 2, ul & 0xFFFFu);
-              atomicAdd(a + 4 * k + 3, ul >> 16);
+    for (int k = 0; k < D; ++k) cp[k] = __ldg(centers + (int64_t)piv * D + k);
+    unsigned long long w0 = 0ull, w1 = 0ull;       // halfwords h0..h3, h4..h7
+    unsigned short* srec = nullptr;               // this cell's side record in the LOCAL grid
+    bool overflow = false;
+    int cnt = 0;
+    for (int j = 0; j < n_src; ++j) {
+      const int k = all ? j : (int)prec[1 + j];
+      double mn, mx, sc;
+      box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
+      const double bm = bisector_min<D>(centers + (int64_t)k * D, cp, lo, hi, sc);
+      if (mn <= thr && bm <= 1e-9 * sc) {           // ascending key order
+        const int e = cnt + 1;                      // 1-based entry
+        if (e <= kFineInline) {
+          if (e < 4) w0 |= (unsigned long long)k << (16 * e);
+          else w1 |= (unsigned long long)k << (16 * (e - 4));
+        } else {
+          if (e == kFineInline + 1) {
+            // the 8th key: open a side record; key 7 moves there and its place takes the slot
+            const unsigned sl = atomicAdd(&hdr->side_next, 1u);
+            if (sl < out.side_per_rank) {
+              const unsigned slot = (unsigned)out.rank * out.side_per_rank + sl;
+              srec = out.side[out.rank] + (size_t)slot * kSideWidth;
+              srec[0] = (unsigned short)(w1 >> 48);
+              w1 = (w1 & 0x0000FFFFFFFFFFFFull) | ((unsigned long long)slot << 48);
+            } else {
+              overflow = true;
             }
-            atomicAdd(a + 4 * D, 1u);
-          } else {
-            unsigned long long* a = P.acc + (size_t)label[p] * (2 * D + 1);
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-              long long hi, lo;
-              to_limbs((double)xv[p][k], P.scale_hi, hi, lo);
-              atomicAdd(a + 2 * k, (unsigned long long)hi);
-              atomicAdd(a + 2 * k + 1, (unsigned long long)lo);
-            }
-            atomicAdd(a + 2 * D, 1ull);
           }
+          if (srec != nullptr && e <= kGridCap) srec[e - kFineInline] = (unsigned short)k;
         }
-      } else {
-        if (P.labels32) __stcs(P.labels32 + i, label[p]);
-        if (P.labels64) __stcs(reinterpret_cast<long long*>(P.labels64) + i, (long long)label[p]);
-        if (P.min_sqdist) __stcs(P.min_sqdist + i, sq);
-        if (P.residual) {
-#pragma unroll
-          for (int k = 0; k < D; ++k) rstage[li * D + k] = (float)diff[k];
-        }
+        ++cnt;
       }
     }
-    if (!LLOYD && P.residual) {
-      __syncwarp();
+    w0 |= (cnt > kGridCap || overflow) ? (unsigned long long)kGridOverflow : (unsigned long long)cnt;
+    const uint4 rec = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
 #pragma unroll
-      for (int j = 0; j < kGPts * D; ++j) {
-        const int idx = j * 32 + lane;
-        if (idx < nval * D) __stcs(P.residual + wbase * D + idx, rstage[idx]);
+    for (int r = 0; r < BDP_KMEANS_MAX_RANKS; ++r)
+      if (r < out.world) out.fine[r][cell] = rec;
+    if (srec != nullptr && out.world > 1) {
+      // the side record goes to the peers as it stands in the local grid (this thread wrote it)
+      const size_t off = (size_t)(srec - out.side[out.rank]);
+      const uint4* src = reinterpret_cast<const uint4*>(srec);
+      uint4 q[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) q[v] = __ldcv(src + v);
+      for (int r = 0; r < out.world; ++r) {
+        if (r == out.rank) continue;
+        uint4* dst = reinterpret_cast<uint4*>(out.side[r] + off);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dst[v] = q[v];
       }
-      __syncwarp();
-    }
-    if (acc_in_smem && ++tiles_since_flush == kFlushTiles) {
-      flush_acc32<D>(s_acc32, P.K, P.acc);
-      tiles_since_flush = 0;
     }
   }
-
-  if (LLOYD) {
-    if (acc_in_smem) flush_acc32<D>(s_acc32, P.K, P.acc);
-    changed = warp_sum(changed);
-    inertia = warp_sum(inertia);
-    if (lane == 0) { s_red[0][warp] = (double)changed; s_red[1][warp] = inertia; }
+  if (out.world > 1) {
+    // every store of this block is ordered before its ticket; the last block publishes the slab
+    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double ch = 0.0, in = 0.0;
-      for (int w = 0; w < kGWarps; ++w) { ch += s_red[0][w]; in += s_red[1][w]; }
-      if (ch != 0.0) atomicAdd(P.stats, (unsigned long long)ch);
-      if (P.inertia) atomicAdd(P.inertia, in);
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&hdr->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x < out.world) {
+      __threadfence_system();
+      st_release_sys(out.gflags[threadIdx.x] + out.rank, out.flag_value);
     }
   }
-}
-
-template <typename T, int D, bool LLOYD>
-int launch_assign_grid(const AssignParams& P, cudaStream_t st) {
-  const bool smem_acc = LLOYD && P.update && P.K <= kMaxSmemAccK;
-  size_t smem = (size_t)P.K * 16 + (D == 4 ? (size_t)((P.K + 3) & ~3) * 4 : 0);
-  smem += (size_t)kGWarps * kGPts * 32 * D * 8;
-  if (smem_acc) smem += (size_t)P.K * (4 * D + 1) * 4;
-  auto kern = assign_grid_kernel<T, D, LLOYD>;
-  if (smem > 48 * 1024) {
-    BDP_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  int per_sm = 0;
-  BDP_CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGThreads, smem));
-  if (per_sm < 1) per_sm = 1;
-  const int64_t n_tiles = ceil_div64(P.N, (int64_t)kGTile);
-  int64_t blocks = (int64_t)bdp_num_sms() * per_sm;
-  if (blocks > n_tiles) blocks = n_tiles;
-  if (blocks < 1) blocks = 1;
-  kern<<<(unsigned)blocks, kGThreads, smem, st>>>(P);
-  BDP_CUDA_CHECK_LAUNCH("assign_grid_kernel");
-  return BDP_OK;
 }
 
 template <bool LLOYD>
 int dispatch_assign_grid(AssignParams& P, int x_dtype, int d, cudaStream_t st) {
   P.err_coef = screen_err_coef(d);
-  if (x_dtype == BDP_F32) {
-    if (d == 3) return launch_assign_grid<float, 3, LLOYD>(P, st);
-    return launch_assign_grid<float, 4, LLOYD>(P, st);
-  }
-  if (d == 3) return launch_assign_grid<double, 3, LLOYD>(P, st);
-  return launch_assign_grid<double, 4, LLOYD>(P, st);
+  const int rc = bdpi_query_grid(P, x_dtype, d, LLOYD, st);      // the pruned query (query.cu)
+  if (rc != BDP_ERR_UNSUPPORTED) return rc;
+  return dispatch_assign<LLOYD>(P, x_dtype, d, st);              // e.g. both label widths at once
 }
 
 int keygrid_check(const void* grid, int64_t grid_bytes, int K, int d, const char* who) {
@@ -1082,19 +707,41 @@ int keygrid_check(const void* grid, int64_t grid_bytes, int K, int d, const char
   return BDP_OK;
 }
 
-// layout: [GridHdr][fine records][coarse records][super records]
+// layout: [GridHdr][fine records 16 B][side records 64 B][coarse records][super records]
 int64_t keygrid_super_cells(int G, int d) { return ipow64((G / 4 + 3) / 4, d); }
 
-void keygrid_pointers(const void* grid, int K, int d, const GridHdr** hdr,
-                      const unsigned short** coarse, const unsigned short** fine,
-                      const unsigned short** super = nullptr) {
-  const unsigned char* b = reinterpret_cast<const unsigned char*>(grid);
-  const int G = keygrid_G(K, d);
-  const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
-  *hdr = reinterpret_cast<const GridHdr*>(b);
-  *fine = reinterpret_cast<const unsigned short*>(b + sizeof(GridHdr));
-  *coarse = *fine + n_fine * (kGridCap + 1);
-  if (super) *super = *coarse + n_coarse * (kCoarseCap + 1);
+// side records of a grid: one per 8 fine cells (3 % of the cells have lists longer than 7 keys),
+// at most 65535 (the slot is a halfword of the cell record), divisible among up to 8 ranks
+int64_t keygrid_side_records(int64_t n_fine) {
+  int64_t n = n_fine / 8;
+  if (n < 1024) n = 1024;
+  if (n > 65528) n = 65528;
+  return n & ~(int64_t)7;
+}
+
+struct GridPtrs {
+  GridHdr* hdr;
+  uint4* fine;
+  unsigned short* side;
+  unsigned short* coarse;
+  unsigned short* super;
+  int G;
+  int64_t n_fine, n_coarse, n_side;
+};
+
+GridPtrs keygrid_pointers(const void* grid, int K, int d) {
+  unsigned char* b = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(grid));
+  GridPtrs g;
+  g.G = keygrid_G(K, d);
+  g.n_coarse = ipow64(g.G / 4, d);
+  g.n_fine = ipow64(g.G, d);
+  g.n_side = keygrid_side_records(g.n_fine);
+  g.hdr = reinterpret_cast<GridHdr*>(b);
+  g.fine = reinterpret_cast<uint4*>(b + sizeof(GridHdr));
+  g.side = reinterpret_cast<unsigned short*>(g.fine + g.n_fine);
+  g.coarse = g.side + g.n_side * kSideWidth;
+  g.super = g.coarse + g.n_coarse * (kCoarseCap + 1);
+  return g;
 }
 
 // ---- key-grid statistics of a query batch (diagnostics: benchmark / DESIGN numbers) ------------------
@@ -1103,7 +750,7 @@ void keygrid_pointers(const void* grid, int K, int d, const GridHdr** hdr,
 template <typename T, int D>
 __global__ void __launch_bounds__(256) keygrid_stats_kernel(const T* __restrict__ x, int64_t N,
                                                             const GridHdr* __restrict__ hdr,
-                                                            const unsigned short* __restrict__ fine,
+                                                            const uint4* __restrict__ fine,
                                                             unsigned long long* __restrict__ stats) {
   const int G = hdr->G;
   unsigned long long outside = 0, over = 0, len = 0, mx = 0, n = 0;
@@ -1122,7 +769,7 @@ __global__ void __launch_bounds__(256) keygrid_stats_kernel(const T* __restrict_
     }
     ++n;
     if (!ok) { ++outside; continue; }
-    const unsigned c = fine[cidx * (kGridCap + 1)];
+    const unsigned c = fine[cidx].x & 0xFFFFu;
     if (c == kGridOverflow) { ++over; continue; }
     len += c;
     mx = c > mx ? c : mx;
@@ -1311,6 +958,12 @@ __global__ void __launch_bounds__(128) euler_pose_kernel(const double* __restric
 
 }  // namespace
 
+float bdp_assign::screen_err_coef(int D) {
+  // |fl32(dist) - dist| <= (D + 2.1) * 2^-24 * (||x|| + ||c||)^2 (input rounding of x, -2c, ||c||^2
+  // plus one rounding per fma); the best/second GAP carries twice that.  x2 safety on top.
+  return (float)(2.0 * 2.0 * (D + 5) * 5.9604644775390625e-08);
+}
+
 extern "C" int bdp_assign_nearest(const void* x, int x_dtype, int64_t N, int d,
                                   const double* centers, int K, int32_t* labels32,
                                   int64_t* labels64, float* residual, double* min_sqdist,
@@ -1420,42 +1073,63 @@ extern "C" int64_t bdp_keygrid_bytes(int K, int d) {
   if ((d != 3 && d != 4) || K < 1 || K > kGridMaxK) return -1;
   const int G = keygrid_G(K, d);
   const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
-  return (int64_t)sizeof(GridHdr) + n_coarse * (kCoarseCap + 1) * 2 + n_fine * (kGridCap + 1) * 2 +
-         keygrid_super_cells(G, d) * (K + 1) * 2;
+  return (int64_t)sizeof(GridHdr) + n_fine * 16 + keygrid_side_records(n_fine) * kSideWidth * 2 +
+         n_coarse * (kCoarseCap + 1) * 2 + keygrid_super_cells(G, d) * (K + 1) * 2;
 }
 
+// Build for `centers`.  peers == NULL (or one rank): the whole grid, locally.  Several ranks: every
+// rank derives the same geometry, builds the hierarchy of ITS slab only (whole layers of coarse cells
+// along the last axis — the levels of a slab depend on nothing outside it) and stores its fine / side
+// records into every rank's grid; the query waits for all slabs (gflags).
 int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
-                       const int* stop, cudaStream_t st) {
+                       const int* stop, const bdpi_grid_peers* peers, cudaStream_t st) {
   BDP_REQUIRE(centers != nullptr, "keygrid_build: NULL centers");
   BDP_REQUIRE(d == 3 || d == 4, "keygrid_build: d must be 3 or 4 (got %d)", d);
   int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_build");
   if (rc != BDP_OK) return rc;
-  const GridHdr* hdr; const unsigned short *coarse, *fine, *super;
-  keygrid_pointers(grid, K, d, &hdr, &coarse, &fine, &super);
-  GridHdr* h = const_cast<GridHdr*>(hdr);
-  unsigned short* co = const_cast<unsigned short*>(coarse);
-  unsigned short* fi = const_cast<unsigned short*>(fine);
-  unsigned short* su = const_cast<unsigned short*>(super);
-  const int G = keygrid_G(K, d);
+  const GridPtrs g = keygrid_pointers(grid, K, d);
+  const int G = g.G, Gc = G / 4, Gs = (Gc + 3) / 4;
   const double r = pow((double)K, 1.0 / d);
   const double margin_frac = r > 2.0 ? 1.0 / r : 0.5;
-  const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
-  const unsigned n_super = (unsigned)keygrid_super_cells(G, d);
+  const int world = (peers && peers->world > 1) ? peers->world : 1;
+  const int rank = world > 1 ? peers->rank : 0;
+  BDP_REQUIRE(world <= BDP_KMEANS_MAX_RANKS && rank >= 0 && rank < world, "keygrid_build: rank %d of %d", rank, world);
+  // slab of this rank: coarse layers [zc0, zc1) along the last axis
+  const int zc0 = (int)((int64_t)rank * Gc / world), zc1 = (int)((int64_t)(rank + 1) * Gc / world);
+  BuildOut out = {};
+  out.world = world; out.rank = rank;
+  out.side_per_rank = (unsigned)(g.n_side / world);
+  out.flag_value = world > 1 ? peers->flag_value : 0ull;
+  for (int q = 0; q < world; ++q) {
+    const GridPtrs gq = keygrid_pointers(world > 1 ? peers->grid[q] : grid, K, d);
+    BDP_REQUIRE(world == 1 || peers->grid[q] != nullptr, "keygrid_build: grid of rank %d is NULL", q);
+    out.fine[q] = gq.fine; out.side[q] = gq.side;
+    out.gflags[q] = world > 1 ? peers->gflags[q] : nullptr;
+  }
   const int sms = bdp_num_sms();
+  const int64_t layer_c = ipow64(Gc, d - 1), layer_s = ipow64(Gs, d - 1);
+  const int64_t coarse0 = zc0 * layer_c, coarse1 = zc1 * layer_c;
+  const int zs0 = zc0 / 4, zs1 = zc1 > zc0 ? (zc1 - 1) / 4 + 1 : zs0;
+  const int64_t super0 = zc1 > zc0 ? zs0 * layer_s : 0;    // an empty slab still publishes the header
+  // every rank launches at least one super block: block 0 of the launch publishes the header
+  const unsigned n_super = (unsigned)((zs1 - zs0) * layer_s > 0 ? (zs1 - zs0) * layer_s : 1);
+  const int64_t n_coarse = coarse1 - coarse0;
+  const int64_t children = d == 3 ? 64 : 256;
+  const int64_t n_cells = n_coarse * children;
   auto blocks_for = [&](int64_t cells) {
     int64_t b = ceil_div64(cells, 8);                  // 8 warps per block, one cell per warp
     const int64_t cap = (int64_t)sms * 8;
     return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
   };
-  const unsigned fine_blocks = (unsigned)ceil_div64(n_fine, 256);
+  const unsigned fine_blocks = (unsigned)(n_cells > 0 ? ceil_div64(n_cells, 256) : 1);
   if (d == 3) {
-    keygrid_super_kernel<3><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, h, su, stop);
-    keygrid_coarse_kernel<3><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, su, co, stop);
-    keygrid_fine_kernel<3><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi, stop);
+    keygrid_super_kernel<3><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.super, (int)super0, stop);
+    keygrid_coarse_kernel<3><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, g.hdr, g.super, g.coarse, coarse0, coarse1, stop);
+    keygrid_fine_kernel<3><<<fine_blocks, 256, 0, st>>>(centers, K, g.hdr, g.coarse, out, coarse0, n_cells, stop);
   } else {
-    keygrid_super_kernel<4><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, h, su, stop);
-    keygrid_coarse_kernel<4><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, h, su, co, stop);
-    keygrid_fine_kernel<4><<<fine_blocks, 256, 0, st>>>(centers, K, h, co, fi, stop);
+    keygrid_super_kernel<4><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.super, (int)super0, stop);
+    keygrid_coarse_kernel<4><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, g.hdr, g.super, g.coarse, coarse0, coarse1, stop);
+    keygrid_fine_kernel<4><<<fine_blocks, 256, 0, st>>>(centers, K, g.hdr, g.coarse, out, coarse0, n_cells, stop);
   }
   BDP_CUDA_CHECK_LAUNCH("keygrid kernels");
   return BDP_OK;
@@ -1463,7 +1137,7 @@ int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t 
 
 extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
                                  void* stream) {
-  return bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr,
+  return bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr, nullptr,
                             reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1475,8 +1149,9 @@ extern "C" int bdp_keygrid_stats(const void* x, int x_dtype, int64_t N, int d, i
   int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_stats");
   if (rc != BDP_OK) return rc;
   if (N == 0) return BDP_OK;
-  const GridHdr* hdr; const unsigned short *coarse, *fine;
-  keygrid_pointers(grid, K, d, &hdr, &coarse, &fine);
+  const GridPtrs g = keygrid_pointers(grid, K, d);
+  const GridHdr* hdr = g.hdr;
+  const uint4* fine = g.fine;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned long long* s = reinterpret_cast<unsigned long long*>(stats);
   const unsigned blocks = (unsigned)(ceil_div64(N, 256) < 1184 ? ceil_div64(N, 256) : 1184);
@@ -1505,15 +1180,16 @@ extern "C" int bdp_assign_nearest_grid(const void* x, int x_dtype, int64_t N, in
   AssignParams P = {};
   P.x = x; P.N = N; P.centers = centers; P.K = K;
   P.labels32 = labels32; P.labels64 = labels64; P.residual = residual; P.min_sqdist = min_sqdist;
-  const unsigned short* coarse;
-  keygrid_pointers(grid, K, d, &P.ghdr, &coarse, &P.gfine);
+  const GridPtrs g = keygrid_pointers(grid, K, d);
+  P.ghdr = g.hdr; P.gfine = g.fine; P.gside = g.side;
   return dispatch_assign_grid<false>(P, x_dtype, d, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int bdpi_lloyd_step_grid(const double* x, int64_t N, int d, const double* centers, int K,
                          const void* grid, int64_t grid_bytes, int32_t* labels, int64_t* acc,
                          int fix_hi_bits, int64_t* stats, double* inertia, int update,
-                         const int* stop, cudaStream_t st) {
+                         const int* stop, const unsigned long long* gflags, int gworld,
+                         unsigned long long gflag_value, cudaStream_t st) {
   BDP_REQUIRE(N >= 0 && N < (1ll << 30), "kmeans_lloyd_step_grid: N out of range");
   if (N == 0) return BDP_OK;
   BDP_REQUIRE(x && centers && labels && stats, "kmeans_lloyd_step_grid: NULL buffer");
@@ -1529,8 +1205,9 @@ int bdpi_lloyd_step_grid(const double* x, int64_t N, int d, const double* center
   P.scale_hi = ldexp(1.0, fix_hi_bits);
   P.stats = reinterpret_cast<unsigned long long*>(stats);
   P.inertia = inertia; P.update = update; P.stop = stop;
-  const unsigned short* coarse;
-  keygrid_pointers(grid, K, d, &P.ghdr, &coarse, &P.gfine);
+  P.gflags = gflags; P.gworld = gworld; P.gflag_value = gflag_value;
+  const GridPtrs g = keygrid_pointers(grid, K, d);
+  P.ghdr = g.hdr; P.gfine = g.fine; P.gside = g.side;
   return dispatch_assign_grid<true>(P, BDP_F64, d, st);
 }
 
@@ -1540,7 +1217,8 @@ extern "C" int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, con
                                           int64_t* stats, double* inertia, int update,
                                           void* stream) {
   return bdpi_lloyd_step_grid(x, N, d, centers, K, grid, grid_bytes, labels, acc, fix_hi_bits, stats,
-                              inertia, update, nullptr, reinterpret_cast<cudaStream_t>(stream));
+                              inertia, update, nullptr, nullptr, 0, 0ull,
+                              reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bdp_euler_to_pose(const double* euler_deg, int64_t N, double* aa, double* quat,

@@ -19,18 +19,22 @@
 // loop into no-ops through a device flag.
 #include <stddef.h>
 
-#include "common.cuh"
+#include "assign_common.cuh"
 
 // internal entry points of assign.cu (same shared object, not part of the C ABI)
 int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
-                       const int* stop, cudaStream_t st);
+                       const int* stop, const bdpi_grid_peers* peers, cudaStream_t st);
 int bdpi_lloyd_step_grid(const double* x, int64_t N, int d, const double* centers, int K,
                          const void* grid, int64_t grid_bytes, int32_t* labels, int64_t* acc,
                          int fix_hi_bits, int64_t* stats, double* inertia, int update,
-                         const int* stop, cudaStream_t st);
+                         const int* stop, const unsigned long long* gflags, int gworld,
+                         unsigned long long gflag_value, cudaStream_t st);
 int bdpi_lloyd_step(const double* x, int64_t N, int d, const double* centers, int K,
                     int32_t* labels, int64_t* acc, int fix_hi_bits, int64_t* stats, double* inertia,
                     int update, const int* stop, cudaStream_t st);
+
+using bdp_assign::ld_acquire_sys;
+using bdp_assign::st_release_sys;
 
 namespace {
 
@@ -39,7 +43,7 @@ constexpr int kXfThreads = 128;
 constexpr int kMaxBlocks = 64;
 constexpr int kMaxK = 8192;
 
-// Control block of a fit (device memory, zero-initialised by the caller).  The first 48 bytes are the
+// Control block of a fit (device memory, zero-initialised by the caller).  The first 40 bytes are the
 // public part (struct bdp_kmeans_status in include/bdpose.h).
 struct KmCtl {
   int state;               // BDP_KMEANS_RUNNING / _STRICT / _TOL / _NEEDS_HOST
@@ -59,7 +63,7 @@ struct KmCtl {
 static_assert(offsetof(KmCtl, ticket) == 40, "public part of KmCtl");
 
 struct XfinParams {
-  unsigned long long* xchg[kMaxWorld];   // exchange buffer of every rank: [acc0 A][acc1 A][flags 8]
+  unsigned long long* xchg[kMaxWorld];   // exchange buffer of every rank: [acc0 A][acc1 A][flags 8][gflags 8]
   const unsigned long long* mc;          // multicast mapping of the exchange buffer, or NULL
   int world, rank;
   int K;
@@ -78,14 +82,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // in-switch sum over every rank's copy of one accumulator word (NVLS)
 __device__ __forceinline__ unsigned long long multimem_add_u64(const unsigned long long* p) {
@@ -288,7 +284,7 @@ extern "C" int64_t bdp_kmeans_ctl_bytes(void) { return (int64_t)sizeof(KmCtl); }
 
 extern "C" int64_t bdp_kmeans_xchg_bytes(int K, int d) {
   if ((d != 3 && d != 4) || K < 1 || K > kMaxK) return -1;
-  return (int64_t)(2 * ((int64_t)K * (2 * d + 1) + 2) + kMaxWorld) * 8;
+  return (int64_t)(2 * ((int64_t)K * (2 * d + 1) + 2) + 2 * kMaxWorld) * 8;
 }
 
 extern "C" int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_multicast, int world,
@@ -317,10 +313,10 @@ extern "C" int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_
 
 // n_iters Lloyd iterations as one launch sequence: [key-grid build, E+M step, exchange+finalise] x n.
 extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers2, int K, void* grid,
-                              int64_t grid_bytes, int32_t* labels, void* const* xchg,
-                              const void* xchg_multicast, int world, int rank, int fix_hi_bits,
-                              int64_t iter0, int n_iters, int check, double tol_abs, void* ctl,
-                              void* stream) {
+                              int64_t grid_bytes, void* const* grid_peers, int32_t* labels,
+                              void* const* xchg, const void* xchg_multicast, int world, int rank,
+                              int fix_hi_bits, int64_t iter0, int n_iters, int check, double tol_abs,
+                              void* ctl, void* stream) {
   int rc = check_common(K, d, world, rank, "kmeans_run");
   if (rc != BDP_OK) return rc;
   BDP_REQUIRE(centers2 && labels && xchg && ctl, "kmeans_run: NULL buffer");
@@ -329,24 +325,39 @@ extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int A = K * (2 * d + 1) + 2;
   const int* stop = reinterpret_cast<const int*>(ctl);          // KmCtl::state
+  // sharded key-grid build: every rank builds one slab and stores it into every rank's grid
+  const bool shard = grid != nullptr && grid_peers != nullptr && world > 1;
+  bdpi_grid_peers gp = {};
+  if (shard) {
+    gp.world = world; gp.rank = rank;
+    for (int r = 0; r < world; ++r) {
+      BDP_REQUIRE(grid_peers[r] && xchg[r], "kmeans_run: peer buffers of rank %d are NULL", r);
+      gp.grid[r] = grid_peers[r];
+      gp.gflags[r] = reinterpret_cast<unsigned long long*>(xchg[r]) + 2 * (size_t)A + kMaxWorld;
+    }
+  }
   for (int it = 0; it < n_iters; ++it) {
     const int64_t gi = iter0 + it;
     const int cur = (int)(gi & 1);
     double* c_cur = centers2 + (size_t)cur * K * d;
     double* c_new = centers2 + (size_t)(cur ^ 1) * K * d;
     int64_t* acc = reinterpret_cast<int64_t*>(xchg[rank]) + (size_t)cur * A;
-    if (N > 0) {
-      if (grid) {
-        rc = bdpi_keygrid_build(c_cur, K, d, grid, grid_bytes, stop, st);
+    if (grid) {
+      // (a rank without rows still builds its slab: the peers' queries read it)
+      gp.flag_value = (unsigned long long)(gi + 1);
+      if (N > 0 || shard) {
+        rc = bdpi_keygrid_build(c_cur, K, d, grid, grid_bytes, stop, shard ? &gp : nullptr, st);
         if (rc != BDP_OK) return rc;
-        rc = bdpi_lloyd_step_grid(x, N, d, c_cur, K, grid, grid_bytes, labels, acc, fix_hi_bits,
-                                  acc + A - 2, nullptr, 1, stop, st);
-      } else {
-        rc = bdpi_lloyd_step(x, N, d, c_cur, K, labels, acc, fix_hi_bits, acc + A - 2, nullptr, 1,
-                             stop, st);
       }
-      if (rc != BDP_OK) return rc;
+      if (N > 0)
+        rc = bdpi_lloyd_step_grid(x, N, d, c_cur, K, grid, grid_bytes, labels, acc, fix_hi_bits,
+                                  acc + A - 2, nullptr, 1, stop, shard ? gp.gflags[rank] : nullptr,
+                                  world, gp.flag_value, st);
+    } else if (N > 0) {
+      rc = bdpi_lloyd_step(x, N, d, c_cur, K, labels, acc, fix_hi_bits, acc + A - 2, nullptr, 1,
+                           stop, st);
     }
+    if (rc != BDP_OK) return rc;
     rc = bdp_kmeans_exchange_finalize(xchg, xchg_multicast, world, rank, K, d, fix_hi_bits, cur,
                                       gi + 1, check, tol_abs, c_cur, c_new, ctl, stream);
     if (rc != BDP_OK) return rc;
@@ -459,10 +470,10 @@ extern "C" int bdp_kmeans_iteration(const double* x, int64_t N, int d, const dou
   BDP_CUDA_CALL(cudaMemsetAsync(acc_stats, 0, (n_acc + 2) * sizeof(int64_t), st));
   int rc;
   if (grid) {
-    rc = bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr, st);
+    rc = bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr, nullptr, st);
     if (rc != BDP_OK) return rc;
     rc = bdpi_lloyd_step_grid(x, N, d, centers, K, grid, grid_bytes, labels, acc_stats, fix_hi_bits,
-                              acc_stats + n_acc, inertia, update, nullptr, st);
+                              acc_stats + n_acc, inertia, update, nullptr, nullptr, 0, 0ull, st);
   } else {
     rc = bdpi_lloyd_step(x, N, d, centers, K, labels, acc_stats, fix_hi_bits, acc_stats + n_acc,
                          inertia, update, nullptr, st);
