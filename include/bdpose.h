@@ -129,6 +129,49 @@ int bdp_expected_pose_loss(const float* logits, int64_t B, int64_t K, int64_t ld
                            const float* target, int pose_mode, float* rows, float* grad_logits,
                            float* grad_delta, void* stream);
 
+/*
+ * Test-time pose composition of the scripts' testing() loops, per prediction:
+ * bin = argmax_k score[k] (first maximum, np.argmax), then
+ *   BDP_COMPOSE_ADD            out = dict[bin] + residual        learnGeodesicBDModel.py:217-219
+ *   BDP_COMPOSE_ADD_NORMALIZE  y = dict[bin] + residual, out = y / max(||y||, 1e-10)
+ *                                                                learnGeodesicBDModel_quaternion.py:217-218
+ *   BDP_COMPOSE_RIEMANNIAN     out = get_y(R_key[bin] . get_R(residual))   (dict = [K,9] key rotations)
+ *                                                                learnRiemannianBDModel.py:247
+ * score [N, ld_score] fp32 (K valid columns), residual [N, ndim] fp32, dict [K, ndim] (or [K,9]) fp64
+ * -> out [N, ndim] fp64 (numpy's float64 + float32 result type), bin_out [N] int64 (NULL: skip).
+ */
+enum { BDP_COMPOSE_ADD = 0, BDP_COMPOSE_ADD_NORMALIZE = 1, BDP_COMPOSE_RIEMANNIAN = 2 };
+int bdp_compose_prediction(const float* score, int64_t N, int K, int64_t ld_score,
+                           const float* residual, int ndim, const double* dict, int mode, double* out,
+                           int64_t* bin_out, void* stream);
+
+/* out[0] = min_{i != j} ||keys_i - keys_j||^2, keys [K, d] fp64 — helperFunctions.get_gamma
+ * (helperFunctions.py:51-58) is 1 / (2 * that). */
+int bdp_min_key_gap(const double* keys, int K, int d, double* out, void* stream);
+
+/*
+ * One optimizer step of helperFunctions.mySGD (helperFunctions.py:62-120; the snapshot-ensemble SGD
+ * of the evaluate* scripts) over MANY tensors in one launch.  table_dev: device array of n_tensors
+ * rows; per tensor  d = g (+ weight_decay * p);  with momentum: buf = d on the first step, else
+ * momentum * buf + (1 - dampening) * d;  d = d + momentum * buf (nesterov) or buf;  p -= step_size * d.
+ * step_size is the cyclical learning rate of the row's own step counter (computed by the caller).
+ * The gradient tensors are read only (the reference adds the weight decay into .grad in place).
+ */
+typedef struct bdp_sgd_tensor {
+  float* p;        /* parameter, updated in place */
+  const float* g;  /* gradient */
+  float* buf;      /* momentum buffer (may be NULL when momentum == 0) */
+  int64_t n;
+  float step_size;
+  int32_t first;   /* 1: the momentum buffer is created by this step */
+} bdp_sgd_tensor;
+int bdp_sgd_step(const bdp_sgd_tensor* table_dev, int n_tensors, int64_t max_numel, float weight_decay,
+                 float momentum, float dampening, int nesterov, void* stream);
+
+/* buf[i] *= *scale_dev, i < n; returns at once (no memory traffic) when *scale_dev == 1 — the upstream
+ * scalar of a loss whose gradient the forward launch already wrote (buf 16-byte aligned). */
+int bdp_scale_inplace(float* buf, int64_t n, const float* scale_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (c) nearest-dictionary-key assignment + residual, and the k-means Lloyd step.
  *   kmeans.predict + residual        binDeltaGenerators.py:27-30, 78-82 (quaternion keys: 67)

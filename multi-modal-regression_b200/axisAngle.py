@@ -8,7 +8,7 @@ the error metrics and the geodesic loss — runs in the CUDA library.
 import numpy as np
 from torch import nn
 
-from helperFunctions_compat import eps
+from helperFunctions import eps
 from bdpose import ops, metrics
 from bdpose import _lib as L
 

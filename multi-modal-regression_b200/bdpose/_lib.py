@@ -37,6 +37,10 @@ SIGNATURES = {
     "bdp_geodesic_error_deg": (_int, [_p, _p, _int, _int, _i64, _p, _p]),
     "bdp_error_stats_workspace_bytes": (_i64, [_i64, _int]),
     "bdp_error_stats": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p, _p, _i64, _p]),
+    "bdp_compose_prediction": (_int, [_p, _i64, _int, _i64, _p, _int, _p, _int, _p, _p, _p]),
+    "bdp_min_key_gap": (_int, [_p, _int, _int, _p, _p]),
+    "bdp_sgd_step": (_int, [_p, _int, _i64, _f32, _f32, _f32, _int, _p]),
+    "bdp_scale_inplace": (_int, [_p, _i64, _p, _p]),
     "bdp_assign_nearest": (_int, [_p, _int, _i64, _int, _p, _int, _p, _p, _p, _p, _p]),
     "bdp_assign_quatdot": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p]),
     "bdp_assign_soft": (_int, [_p, _int, _i64, _int, _p, _int, _f64, _p, _p, _p]),
@@ -77,6 +81,14 @@ SIGNATURES = {
 }
 
 HEAD_MAX_GROUPS = 4
+COMPOSE_ADD, COMPOSE_ADD_NORMALIZE, COMPOSE_RIEMANNIAN = range(3)
+
+
+class SgdTensor(C.Structure):
+    """struct bdp_sgd_tensor (include/bdpose.h)"""
+    _fields_ = [("p", _p), ("g", _p), ("buf", _p), ("n", C.c_int64), ("step_size", C.c_float),
+                ("first", C.c_int32)]
+
 KMEANS_MAX_RANKS = 8
 KMEANS_RUNNING, KMEANS_STRICT, KMEANS_TOL, KMEANS_NEEDS_HOST = range(4)
 

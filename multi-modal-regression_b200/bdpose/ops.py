@@ -101,6 +101,17 @@ def bd_loss_raw(logits, bin_true, pred, target, keys, pose_mode, use_keys, want_
                 row_pose=row_pose)
 
 
+def _scale_inplace(buf, g):
+    """buf *= g (0-dim tensor on the device) without a host read of g."""
+    if not (buf.is_contiguous() and buf.data_ptr() % 16 == 0):
+        return buf * g
+    g = g.detach().to(torch.float32).reshape(1)
+    with torch.cuda.device(buf.device):
+        st = L.lib().bdp_scale_inplace(L.ptr(buf), buf.numel(), L.ptr(g), L.stream_ptr())
+    L.check(st, "bdp_scale_inplace")
+    return buf
+
+
 class _BDLoss(torch.autograd.Function):
     """(Lc, Lr) = fused(logits, pred); the backward only scales the gradients the forward launch
     already wrote (saved per call, so two forwards before one backward are fine —
@@ -113,6 +124,7 @@ class _BDLoss(torch.autograd.Function):
                         want_grad=any(need))
         ctx.save_for_backward(r["grad_logits"], r["grad_pred"])
         ctx.shapes = (None if logits is None else logits.shape, None if pred is None else pred.shape)
+        ctx.scaled = False
         ctx.mark_non_differentiable(r["argmax"]) if r["argmax"] is not None else None
         lc, lr = r["loss"][0], r["loss"][1]
         if r["argmax"] is None:
@@ -125,7 +137,14 @@ class _BDLoss(torch.autograd.Function):
         s_logits, s_pred = ctx.shapes
         gl = gp = None
         if g_logits is not None and ctx.needs_input_grad[0]:
-            gl = (g_logits * g_lc).reshape(s_logits)
+            # The forward launch already wrote d Lc / d logits; the upstream scalar (1 for
+            # `Lc + w * Lr`) is applied in place by a kernel that returns without touching memory
+            # when it is 1 — no second pass over [B, K].
+            if ctx.scaled:
+                raise RuntimeError("bd_loss: backward through the same graph twice (the saved "
+                                   "gradient was scaled in place); re-run the forward")
+            ctx.scaled = True
+            gl = _scale_inplace(g_logits, g_lc).reshape(s_logits)
         if g_pred is not None and ctx.needs_input_grad[1]:
             gp = (g_pred * g_lr).reshape(s_pred)
         return gl, gp, None, None, None, None, None
@@ -500,3 +519,47 @@ def convert_axis_angle(aa, want_rot=True, want_quat=True):
         st = L.lib().bdp_convert_axis_angle(L.ptr(aa), N, L.ptr(rot), L.ptr(quat), L.stream_ptr())
     L.check(st, "bdp_convert_axis_angle")
     return rot, quat
+
+
+# ------------------------------------------------------------------------------------------------
+# (d3) test-time pose composition, (f2) get_gamma
+# ------------------------------------------------------------------------------------------------
+def compose_prediction(score, residual, dictionary, mode="add"):
+    """ypred of the scripts' testing() loops on the device: bin = argmax(score), then
+    mode "add": dict[bin] + res (learnGeodesicBDModel.py:217-219); "normalize": that, divided by
+    max(norm, 1e-10) (learnGeodesicBDModel_quaternion.py:217-218); "riemannian": dictionary = key
+    rotations [K,3,3], get_y(R_key[bin] . get_R(res)) (learnRiemannianBDModel.py:247).
+    Returns (ypred [N, ndim] fp64, bin [N] int64)."""
+    _need_cuda(score, residual, dictionary)
+    modes = {"add": L.COMPOSE_ADD, "normalize": L.COMPOSE_ADD_NORMALIZE, "riemannian": L.COMPOSE_RIEMANNIAN}
+    if mode not in modes:
+        raise NameError("Unknown composition mode passed")
+    score = score.float()
+    if score.dim() != 2 or score.stride(1) != 1:
+        score = score.contiguous()
+    N, K = score.shape
+    residual = residual.float().reshape(N, -1).contiguous()
+    nd = residual.shape[1]
+    dictionary = dictionary.double().reshape(K, -1).contiguous()
+    want = 9 if mode == "riemannian" else nd
+    if dictionary.shape[1] != want:
+        raise ValueError("compose_prediction: dictionary has %d columns, expected %d" % (dictionary.shape[1], want))
+    out = torch.empty((N, nd), dtype=torch.float64, device=score.device)
+    bins = torch.empty(N, dtype=torch.int64, device=score.device)
+    with torch.cuda.device(score.device):
+        st = L.lib().bdp_compose_prediction(L.ptr(score), N, K, score.stride(0), L.ptr(residual), nd,
+                                            L.ptr(dictionary), modes[mode], L.ptr(out), L.ptr(bins),
+                                            L.stream_ptr())
+    L.check(st, "bdp_compose_prediction")
+    return out, bins
+
+
+def min_key_gap(keys):
+    """min_{i != j} ||k_i - k_j||^2 of a dictionary [K, d] (0-dim fp64 tensor on the device)."""
+    _need_cuda(keys)
+    keys = keys.double().contiguous()
+    out = torch.empty(1, dtype=torch.float64, device=keys.device)
+    with torch.cuda.device(keys.device):
+        st = L.lib().bdp_min_key_gap(L.ptr(keys), keys.shape[0], keys.shape[1], L.ptr(out), L.stream_ptr())
+    L.check(st, "bdp_min_key_gap")
+    return out[0]

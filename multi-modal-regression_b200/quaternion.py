@@ -6,7 +6,7 @@ import torch
 from torch import nn
 import torch.nn.functional as F
 
-from helperFunctions_compat import eps
+from helperFunctions import eps
 from bdpose import ops, metrics
 from bdpose import _lib as L
 

@@ -394,3 +394,78 @@ class OneDeltaPerBinHeads(nn.Module):
         _, pose_label = torch.max(y1, dim=1, keepdim=True)
         pl = torch.zeros(pose_label.size(0), self.num_clusters).scatter_(1, pose_label, 1.0).unsqueeze(2)
         return [y1, torch.squeeze(torch.bmm(y2.permute(1, 2, 0), pl), 2)]
+
+
+# --------------------------------------------------------------------------------------------------
+# round 2: loss_m2, get_gamma, test-time compositions, mySGD, get_accuracy, detection-metric helpers
+# --------------------------------------------------------------------------------------------------
+def loss_m2(score, res, bin_true, res_true, alpha):
+    """binDeltaLosses.py:280-297: CE + alpha * MSE(residual, res_true[b, argmax score_b, :]) — the
+    one-hot bmm over ytrue[1].permute(0, 2, 1) picks the row of the predicted bin."""
+    l1 = F.cross_entropy(score, bin_true)
+    ind = torch.argmax(score, dim=1)
+    yres = res_true[torch.arange(score.shape[0]), ind]
+    return l1 + alpha * F.mse_loss(res, yres)
+
+
+def get_gamma(kmeans_dict):
+    """helperFunctions.py:51-58"""
+    c = np.asarray(kmeans_dict, dtype=np.float64)
+    D = ((c[:, None, :] - c[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(D, np.inf)
+    return 1.0 / (2.0 * D.min())
+
+
+def compose_add(score, res, dictionary):
+    """learnGeodesicBDModel.py:217-219"""
+    return np.asarray(dictionary)[np.argmax(score, axis=1), :] + res
+
+
+def compose_normalize(score, res, dictionary):
+    """learnGeodesicBDModel_quaternion.py:217-218"""
+    y = compose_add(score, res, dictionary)
+    return y / np.maximum(np.linalg.norm(y, 2, 1, True), 1e-10)
+
+
+def compose_riemannian(score, res, rot_dict):
+    """learnRiemannianBDModel.py:247"""
+    b = np.argmax(score, axis=1)
+    return np.stack([get_y(np.dot(rot_dict[b[j]], get_R(res[j]))) for j in range(b.shape[0])])
+
+
+def cyclic_step_size(step, c, alpha1, alpha2):
+    """helperFunctions.py:111-116"""
+    t = (np.fmod(step - 1, c) + 1) / c
+    if t <= 0.5:
+        return (1 - 2 * t) * alpha1 + 2 * t * alpha2
+    return 2 * (1 - t) * alpha2 + (2 * t - 1) * alpha1
+
+
+def my_sgd(params, grad_fn, n_steps, c, alpha1, alpha2, momentum=0.0, dampening=0.0, weight_decay=0.0,
+           nesterov=False):
+    """helperFunctions.mySGD (62-120) on numpy arrays: params list, grad_fn(params) -> grads list.
+    Returns the flattened parameters after every step."""
+    params = [np.array(p, dtype=np.float32) for p in params]
+    bufs = [None] * len(params)
+    traj = []
+    for step in range(1, n_steps + 1):
+        grads = grad_fn(params)
+        lr = np.float32(cyclic_step_size(step, c, alpha1, alpha2))
+        for i, (p, g) in enumerate(zip(params, grads)):
+            d_p = np.array(g, dtype=np.float32)
+            if weight_decay != 0:
+                d_p = d_p + np.float32(weight_decay) * p
+            if momentum != 0:
+                if bufs[i] is None:
+                    bufs[i] = d_p.copy()
+                else:
+                    bufs[i] = np.float32(momentum) * bufs[i] + np.float32(1 - dampening) * d_p
+                d_p = d_p + np.float32(momentum) * bufs[i] if nesterov else bufs[i]
+            params[i] = p - lr * d_p
+        traj.append(np.concatenate([p.ravel() for p in params]))
+    return np.stack(traj)
+
+
+def get_accuracy(ytrue, ypred, num_classes):
+    """helperFunctions.py:123-130"""
+    return float(np.mean([np.sum((ytrue == i) * (ypred == i)) / np.sum(ytrue == i) for i in range(num_classes)]))

@@ -21,7 +21,7 @@ LEFT_TO_REFERENCE = {
     "objectnetHelperFunctions": set(),
     "binDeltaGenerators": set(),
     "binDeltaModels": set(), "binDeltaLosses": set(), "poseModels": set(),
-    "axisAngle": set(), "quaternion": set(), "featureModels": set(),
+    "axisAngle": set(), "quaternion": set(), "featureModels": set(), "helperFunctions": set(),
 }
 
 

@@ -172,3 +172,30 @@ def test_per_bin_delta_heads_oracle_vs_reference(golden):
     assert torch.allclose(e2, torch.from_numpy(g["eval_y2"]), rtol=1e-5, atol=1e-6)
     assert torch.allclose(p2, torch.from_numpy(g["prob_y2"]), rtol=1e-5, atol=1e-6)
     assert torch.allclose(p1, torch.from_numpy(g["prob_y1"]), rtol=1e-5, atol=1e-6)
+
+
+def test_round2_misc(golden):
+    """loss_m2, get_gamma, the testing() compositions, mySGD and get_accuracy of the reference
+    (tests/golden/make_golden.py misc)."""
+    g = golden("misc_r2")
+    s = torch.from_numpy(g["m2_score"]).requires_grad_(True)
+    r = torch.from_numpy(g["m2_res"]).requires_grad_(True)
+    loss = O.loss_m2(s, r, torch.from_numpy(g["m2_bins"]), torch.from_numpy(g["m2_res_true"]), float(g["m2_alpha"]))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["m2_loss"], rtol=1e-6)
+    np.testing.assert_allclose(s.grad.numpy(), g["m2_g_score"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(r.grad.numpy(), g["m2_g_res"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(O.get_gamma(g["gamma_centers"]), g["gamma"], rtol=1e-12)
+    np.testing.assert_array_equal(O.compose_add(g["t_score"], g["t_res"], g["t_dict"]), g["t_add"])
+    np.testing.assert_array_equal(O.compose_normalize(g["t_score"], g["t_res4"], g["t_qdict"]), g["t_quat"])
+    np.testing.assert_allclose(O.compose_riemannian(g["t_score"], g["t_res"], g["t_rotdict"]), g["t_riem"],
+                               rtol=0, atol=1e-6)      # the script evaluates get_R on float32 residuals
+    t1, t2 = g["sgd_t1"], g["sgd_t2"]
+
+    def grads(p):
+        return [2 * (p[0] - t1), 4 * (p[1] - t2) ** 3]
+    for name, kw in (("plain", {}), ("mom", dict(momentum=0.9, weight_decay=1e-2)),
+                     ("nest", dict(momentum=0.8, nesterov=True))):
+        traj = O.my_sgd([g["sgd_p1"], g["sgd_p2"]], grads, 7, 4, 1e-1, 1e-3, **kw)
+        np.testing.assert_allclose(traj, g["sgd_traj_" + name], rtol=2e-5, atol=1e-6)
+    assert O.get_accuracy(g["acc_true"], g["acc_pred"], 5) == float(g["acc"])
