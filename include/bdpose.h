@@ -332,6 +332,14 @@ int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
  *     scan), runs the E+M step on this rank's rows into acc[i & 1] and calls the exchange step, which
  *     writes centers2[(i & 1) ^ 1].  Once the status leaves BDP_KMEANS_RUNNING the remaining launches
  *     do nothing; status.iter_done tells which centres buffer is current.
+ *     incremental != 0 (needs the key grid): the accumulators PERSIST across iterations — the
+ *     exchange step carries acc[parity] over to acc[parity ^ 1] instead of zeroing it and the E+M
+ *     kernel only moves the rotations whose label changed (out of the old cluster, into the new one).
+ *     The sums are integers, so this equals a recomputation bit for bit; after the first iterations
+ *     few labels change and the M-step costs next to nothing.  `labels` must then be the labels the
+ *     accumulators were built from (-1 and zeroed accumulators at the start of a fit).
+ *     em_events (NULL: none): 2 * n_iters caller-owned cudaEvent_t handles recorded right before and
+ *     after the E+M kernel of every iteration (benchmark instrumentation).
  *     grid_peers (NULL: every rank builds the whole grid itself) = this process's addresses of
  *     every rank's key-grid buffer, allocated like the exchange buffers: the build is then SHARDED —
  *     a rank builds the cells of one slab of the grid and stores them into every rank's buffer over
@@ -353,12 +361,14 @@ int64_t bdp_kmeans_ctl_bytes(void);
 int64_t bdp_kmeans_xchg_bytes(int K, int d);
 int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_multicast, int world, int rank,
                                  int K, int d, int fix_hi_bits, int parity, int64_t flag_value,
-                                 int check, double tol_abs, const double* centers_old,
-                                 double* centers_new, void* ctl, void* stream);
+                                 int check, int incremental, double tol_abs,
+                                 const double* centers_old, double* centers_new, void* ctl,
+                                 void* stream);
 int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers2, int K, void* grid,
                    int64_t grid_bytes, void* const* grid_peers, int32_t* labels, void* const* xchg,
                    const void* xchg_multicast, int world, int rank, int fix_hi_bits, int64_t iter0,
-                   int n_iters, int check, double tol_abs, void* ctl, void* stream);
+                   int n_iters, int check, int incremental, double tol_abs, void* ctl,
+                   void* const* em_events, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (a) category-conditioned bin-delta heads.

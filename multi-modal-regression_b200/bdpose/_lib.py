@@ -59,10 +59,10 @@ SIGNATURES = {
     "bdp_kmeans_finalize": (_int, [_p, _int, _int, _int, _p, _p, _p, _p, _p]),
     "bdp_kmeans_ctl_bytes": (_i64, []),
     "bdp_kmeans_xchg_bytes": (_i64, [_int, _int]),
-    "bdp_kmeans_exchange_finalize": (_int, [_p, _p, _int, _int, _int, _int, _int, _int, _i64, _int, _f64,
-                                            _p, _p, _p, _p]),
+    "bdp_kmeans_exchange_finalize": (_int, [_p, _p, _int, _int, _int, _int, _int, _int, _i64, _int, _int,
+                                            _f64, _p, _p, _p, _p]),
     "bdp_kmeans_run": (_int, [_p, _i64, _int, _p, _int, _p, _i64, _p, _p, _p, _p, _int, _int, _int, _i64,
-                              _int, _int, _f64, _p, _p]),
+                              _int, _int, _int, _f64, _p, _p, _p]),
     "bdp_gemm_tf32": (_int, [_p, _int, _i64, _i64, _p, _int, _i64, _i64, _p, _int, _i64, _i64, _i64,
                              _i64, _i64, _int, _int, _i64, _int, _p]),
     "bdp_gemm_tf32_splits": (_int, [_i64, _int]),

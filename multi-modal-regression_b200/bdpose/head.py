@@ -200,6 +200,12 @@ class HeadStack:
             raise RuntimeError("bdpose heads run on CUDA only (parameters are on %s); call .cuda()" % dev)
         if len(self.groups) > L.HEAD_MAX_GROUPS or len({len(g) for g in self.groups}) != 1:
             raise RuntimeError("head stack: 1..%d fc3 groups with the same number of heads each" % L.HEAD_MAX_GROUPS)
+        for m in heads:
+            for bn in (m.bn1, m.bn2):
+                if bn.eps != BN_EPS or bn.momentum != BN_MOMENTUM or not bn.affine or not bn.track_running_stats:
+                    raise RuntimeError("bdpose heads implement nn.BatchNorm1d with the defaults the reference "
+                                       "uses (eps=1e-5, momentum=0.1, affine, running stats); got eps=%r "
+                                       "momentum=%r" % (bn.eps, bn.momentum))
         buf = {}
         with torch.no_grad():
             for key, sub, name in _SLOTS:
@@ -289,7 +295,7 @@ class HeadStack:
             # ONE flat allocation: the data-parallel all-reduce is a single collective over it
             shapes = {k: self._stacked_tensor(k).shape for k in self._keys()}
             sizes = {k: (int(torch.Size(v).numel()) + 3) // 4 * 4 for k, v in shapes.items()}
-            self.gflat = torch.empty(sum(sizes.values()), dtype=torch.float32,
+            self.gflat = torch.zeros(sum(sizes.values()), dtype=torch.float32,
                                      device=self.buf["w1"].device)
             self.grad, off = {}, 0
             for k in self._keys():
@@ -818,12 +824,20 @@ def allreduce_stack_grads(stack, group=None, average=True):
             if average:
                 flat.div_(ws)
         return
-    works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True)
-             for _, g in sorted(stack.grad.items())]
+    # The Parameters' .grad are NOT views of the stacked buffers (foreign gradients were present and
+    # accumulate() added into separate tensors, or the stack was re-published): reduce the gradients
+    # the Parameters actually hold.
+    plists = getattr(stack, "plists", None) or {}
+    grads = [p.grad for plist in plists.values() for p in plist if p.grad is not None]
+    if getattr(stack, "stacked", None):
+        grads = [p.grad for p in stack.stacked.values() if p.grad is not None]
+    if not grads:
+        raise RuntimeError("allreduce_stack_grads: the stack's parameters hold no gradients")
+    works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in grads]
     for w in works:
         w.wait()
     if average:
-        for g in stack.grad.values():
+        for g in grads:
             g.div_(ws)
 
 

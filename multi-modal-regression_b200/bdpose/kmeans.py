@@ -291,6 +291,10 @@ class LloydLoop:
         self._tmp_shift = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._tmp_empty = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.n_iter, self.strict, self.stopped = 0, False, False
+        # incremental M-step (exact: integer sums): on whenever the loop runs through bdp_kmeans_run
+        # with the key grid; the NCCL fallback all-reduces its accumulator in place and recomputes
+        self.incremental = self.grid is not None and self.mode != "nccl" and \
+            os.environ.get("BDPOSE_KMEANS_INCREMENTAL", "1") != "0"
 
     def reset(self, centers):
         """Start over from `centers` (same data): accumulators, flags, labels and status cleared."""
@@ -309,17 +313,23 @@ class LloydLoop:
         raw = bytes(self.ctl[:40].cpu().numpy())
         return L.KMeansStatus.from_buffer_copy(raw)
 
-    def launch(self, i0, n, check):
-        """Queue iterations i0 .. i0+n-1 on the current stream (no host synchronisation)."""
+    def launch(self, i0, n, check, em_events=None):
+        """Queue iterations i0 .. i0+n-1 on the current stream (no host synchronisation).
+        em_events: 2n recorded-once torch.cuda.Event(enable_timing=True) objects that will bracket
+        the E+M kernel of every iteration (benchmark instrumentation)."""
+        import ctypes as C
         lib = L.lib()
         g = self.grid
+        ev = None
+        if em_events is not None:
+            ev = (C.c_void_p * len(em_events))(*[e.cuda_event for e in em_events])
         with torch.cuda.device(self.dev):
             st = lib.bdp_kmeans_run(self.x.data_ptr(), self.N, self.d, self.c2.data_ptr(), self.K,
                                     None if g is None else g.buf.data_ptr(), 0 if g is None else g.nbytes,
                                     self.grid_ptrs, self.labels.data_ptr(), self.ptrs, self.ex.mc,
                                     self.world, self.rank,
-                                    self.hb, i0, n, 1 if check else 0, self.tol_abs,
-                                    self.ctl.data_ptr(), L.stream_ptr())
+                                    self.hb, i0, n, 1 if check else 0, 1 if self.incremental else 0,
+                                    self.tol_abs, self.ctl.data_ptr(), ev, L.stream_ptr())
         L.check(st, "bdp_kmeans_run")
 
     def _launch_nccl(self, i0, check):
@@ -345,7 +355,7 @@ class LloydLoop:
                 L.check(st, "bdp_kmeans_lloyd_step")
             dist.all_reduce(acc, group=self.group)
             st = lib.bdp_kmeans_exchange_finalize(
-                self.ptrs, None, 1, 0, self.K, self.d, self.hb, cur, i0 + 1, 1 if check else 0,
+                self.ptrs, None, 1, 0, self.K, self.d, self.hb, cur, i0 + 1, 1 if check else 0, 0,
                 self.tol_abs, c2[cur].data_ptr(), c2[cur ^ 1].data_ptr(), self.ctl.data_ptr(),
                 L.stream_ptr())
         L.check(st, "bdp_kmeans_exchange_finalize")
@@ -358,8 +368,12 @@ class LloydLoop:
         g = int(st.iter_done) - 1
         p = g & 1
         acc = ex.acc(p)
-        if ex.world > 1 and ex.mode != "nccl":
-            dist.all_reduce(acc, group=self.group)
+        if ex.mode != "nccl":
+            # this rank's sums persist (incremental M-step) and the peers may still read them: the
+            # relocation works on a copy of the GLOBAL sums
+            acc = acc.clone()
+            if ex.world > 1:
+                dist.all_reduce(acc, group=self.group)
         view = _AccView(acc[:ex.A - 2], self.labels)
         _relocate_empty(self.x, self.c2[p], view, self.hb, self.group)
         finalize(view, self.c2[p], self.c2[p ^ 1], self.hb, shift2=self._tmp_shift,

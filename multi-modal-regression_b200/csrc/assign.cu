@@ -1189,7 +1189,7 @@ int bdpi_lloyd_step_grid(const double* x, int64_t N, int d, const double* center
                          const void* grid, int64_t grid_bytes, int32_t* labels, int64_t* acc,
                          int fix_hi_bits, int64_t* stats, double* inertia, int update,
                          const int* stop, const unsigned long long* gflags, int gworld,
-                         unsigned long long gflag_value, cudaStream_t st) {
+                         unsigned long long gflag_value, int incremental, cudaStream_t st) {
   BDP_REQUIRE(N >= 0 && N < (1ll << 30), "kmeans_lloyd_step_grid: N out of range");
   if (N == 0) return BDP_OK;
   BDP_REQUIRE(x && centers && labels && stats, "kmeans_lloyd_step_grid: NULL buffer");
@@ -1206,6 +1206,7 @@ int bdpi_lloyd_step_grid(const double* x, int64_t N, int d, const double* center
   P.stats = reinterpret_cast<unsigned long long*>(stats);
   P.inertia = inertia; P.update = update; P.stop = stop;
   P.gflags = gflags; P.gworld = gworld; P.gflag_value = gflag_value;
+  P.incremental = incremental;
   const GridPtrs g = keygrid_pointers(grid, K, d);
   P.ghdr = g.hdr; P.gfine = g.fine; P.gside = g.side;
   return dispatch_assign_grid<true>(P, BDP_F64, d, st);
@@ -1217,7 +1218,7 @@ extern "C" int bdp_kmeans_lloyd_step_grid(const double* x, int64_t N, int d, con
                                           int64_t* stats, double* inertia, int update,
                                           void* stream) {
   return bdpi_lloyd_step_grid(x, N, d, centers, K, grid, grid_bytes, labels, acc, fix_hi_bits, stats,
-                              inertia, update, nullptr, nullptr, 0, 0ull,
+                              inertia, update, nullptr, nullptr, 0, 0ull, 0,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -44,6 +44,8 @@ struct AssignParams {
   unsigned long long* stats;
   double* inertia;
   int update;
+  int incremental;         // Lloyd: acc holds the sums of the PREVIOUS labels; only rotations whose
+                           // label changed move (subtracted from the old cluster, added to the new)
   float err_coef;          // 2^-24 * 2(D+5) * safety
   // key grid (candidate pruning); NULL for the brute-force kernel
   const struct GridHdr* ghdr;

@@ -28,7 +28,7 @@ int bdpi_lloyd_step_grid(const double* x, int64_t N, int d, const double* center
                          const void* grid, int64_t grid_bytes, int32_t* labels, int64_t* acc,
                          int fix_hi_bits, int64_t* stats, double* inertia, int update,
                          const int* stop, const unsigned long long* gflags, int gworld,
-                         unsigned long long gflag_value, cudaStream_t st);
+                         unsigned long long gflag_value, int incremental, cudaStream_t st);
 int bdpi_lloyd_step(const double* x, int64_t N, int d, const double* centers, int K,
                     int32_t* labels, int64_t* acc, int fix_hi_bits, int64_t* stats, double* inertia,
                     int update, const int* stop, cudaStream_t st);
@@ -70,6 +70,7 @@ struct XfinParams {
   int A;                                 // K*(2d+1) + 2 accumulator words per buffer
   int parity;
   int check;                             // apply scikit-learn's stopping rules
+  int incremental;                       // the accumulators persist: carry them over instead of zeroing
   unsigned long long flag_value;         // global iteration index + 1
   double inv_scale_lo;
   double tol_abs;
@@ -193,11 +194,15 @@ __global__ void __launch_bounds__(kXfThreads) kmeans_xfin_kernel(const XfinParam
     }
     ctl->p_cnt[blockIdx.x] = bc; ctl->p_idx[blockIdx.x] = bi; ctl->p_empty[blockIdx.x] = ne;
   }
-  // 4. zero the OTHER parity buffer for the next iteration's E+M kernel: every peer has raised its
-  //    flag for this iteration, i.e. finished reading that buffer in its previous exchange kernel
+  // 4. prepare the OTHER parity buffer for the next iteration's E+M kernel (every peer has raised its
+  //    flag for this iteration, i.e. finished reading that buffer in its previous exchange kernel):
+  //    zero it, or — incremental M-step — carry this rank's sums over (the next E+M kernel only moves
+  //    the rotations whose label changes); the {changed, unused} counters always restart at 0
   {
+    const unsigned long long* cur = local + (size_t)P.parity * P.A;
     unsigned long long* nxt = local + (size_t)(P.parity ^ 1) * P.A;
-    for (int i = blockIdx.x * kXfThreads + tid; i < P.A; i += gridDim.x * kXfThreads) nxt[i] = 0ull;
+    for (int i = blockIdx.x * kXfThreads + tid; i < P.A; i += gridDim.x * kXfThreads)
+      nxt[i] = (P.incremental && i < P.A - 2) ? cur[i] : 0ull;
   }
   // 5. the last block to arrive closes the iteration
   __threadfence();
@@ -289,9 +294,9 @@ extern "C" int64_t bdp_kmeans_xchg_bytes(int K, int d) {
 
 extern "C" int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_multicast, int world,
                                             int rank, int K, int d, int fix_hi_bits, int parity,
-                                            int64_t flag_value, int check, double tol_abs,
-                                            const double* centers_old, double* centers_new,
-                                            void* ctl, void* stream) {
+                                            int64_t flag_value, int check, int incremental,
+                                            double tol_abs, const double* centers_old,
+                                            double* centers_new, void* ctl, void* stream) {
   int rc = check_common(K, d, world, rank, "kmeans_exchange_finalize");
   if (rc != BDP_OK) return rc;
   BDP_REQUIRE(xchg && centers_old && centers_new && ctl, "kmeans_exchange_finalize: NULL buffer");
@@ -303,7 +308,8 @@ extern "C" int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_
   }
   P.mc = reinterpret_cast<const unsigned long long*>(xchg_multicast);
   P.world = world; P.rank = rank; P.K = K; P.A = K * (2 * d + 1) + 2;
-  P.parity = parity & 1; P.check = check; P.flag_value = (unsigned long long)flag_value;
+  P.parity = parity & 1; P.check = check; P.incremental = incremental;
+  P.flag_value = (unsigned long long)flag_value;
   P.inv_scale_lo = ldexp(1.0, -(fix_hi_bits + 32));
   P.tol_abs = tol_abs; P.c_old = centers_old; P.c_new = centers_new;
   P.ctl = reinterpret_cast<KmCtl*>(ctl);
@@ -315,8 +321,8 @@ extern "C" int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_
 extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers2, int K, void* grid,
                               int64_t grid_bytes, void* const* grid_peers, int32_t* labels,
                               void* const* xchg, const void* xchg_multicast, int world, int rank,
-                              int fix_hi_bits, int64_t iter0, int n_iters, int check, double tol_abs,
-                              void* ctl, void* stream) {
+                              int fix_hi_bits, int64_t iter0, int n_iters, int check, int incremental,
+                              double tol_abs, void* ctl, void* const* em_events, void* stream) {
   int rc = check_common(K, d, world, rank, "kmeans_run");
   if (rc != BDP_OK) return rc;
   BDP_REQUIRE(centers2 && labels && xchg && ctl, "kmeans_run: NULL buffer");
@@ -349,17 +355,21 @@ extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers
         rc = bdpi_keygrid_build(c_cur, K, d, grid, grid_bytes, stop, shard ? &gp : nullptr, st);
         if (rc != BDP_OK) return rc;
       }
-      if (N > 0)
+      if (N > 0) {
+        if (em_events) BDP_CUDA_CALL(cudaEventRecord(reinterpret_cast<cudaEvent_t>(em_events[2 * it]), st));
         rc = bdpi_lloyd_step_grid(x, N, d, c_cur, K, grid, grid_bytes, labels, acc, fix_hi_bits,
                                   acc + A - 2, nullptr, 1, stop, shard ? gp.gflags[rank] : nullptr,
-                                  world, gp.flag_value, st);
+                                  world, gp.flag_value, incremental, st);
+        if (em_events) BDP_CUDA_CALL(cudaEventRecord(reinterpret_cast<cudaEvent_t>(em_events[2 * it + 1]), st));
+      }
     } else if (N > 0) {
+      BDP_REQUIRE(!incremental, "kmeans_run: the incremental M-step needs the key grid");
       rc = bdpi_lloyd_step(x, N, d, c_cur, K, labels, acc, fix_hi_bits, acc + A - 2, nullptr, 1,
                            stop, st);
     }
     if (rc != BDP_OK) return rc;
     rc = bdp_kmeans_exchange_finalize(xchg, xchg_multicast, world, rank, K, d, fix_hi_bits, cur,
-                                      gi + 1, check, tol_abs, c_cur, c_new, ctl, stream);
+                                      gi + 1, check, incremental, tol_abs, c_cur, c_new, ctl, stream);
     if (rc != BDP_OK) return rc;
   }
   return BDP_OK;
@@ -473,7 +483,7 @@ extern "C" int bdp_kmeans_iteration(const double* x, int64_t N, int d, const dou
     rc = bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr, nullptr, st);
     if (rc != BDP_OK) return rc;
     rc = bdpi_lloyd_step_grid(x, N, d, centers, K, grid, grid_bytes, labels, acc_stats, fix_hi_bits,
-                              acc_stats + n_acc, inertia, update, nullptr, nullptr, 0, 0ull, st);
+                              acc_stats + n_acc, inertia, update, nullptr, nullptr, 0, 0ull, 0, st);
   } else {
     rc = bdpi_lloyd_step(x, N, d, centers, K, labels, acc_stats, fix_hi_bits, acc_stats + n_acc,
                          inertia, update, nullptr, st);

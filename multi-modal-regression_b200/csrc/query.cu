@@ -19,6 +19,8 @@
 // The arithmetic that decides a label is unchanged (fp32 screen of the cell's candidate keys with a
 // rigorous error bound, fp64 exact pass on near ties, ascending key order, warp-cooperative scan for
 // points outside the grid), so labels and residuals are bit-identical to the brute-force kernel.
+#include <stdlib.h>
+
 #include "assign_common.cuh"
 
 using namespace bdp_assign;
@@ -117,6 +119,48 @@ __device__ __forceinline__ void flush_acc(unsigned* s_acc32, int K, unsigned lon
   __syncthreads();
   for (int i = threadIdx.x; i < K * (4 * D + 1); i += kQThreads) s_acc32[i] = 0u;
   __syncthreads();
+}
+
+// M-step contribution of ONE rotation (kept out of line: after the first iterations few rotations
+// move, and the hot loop keeps its registers): subtract it from cluster `from` (>= 0: incremental
+// mode, global 64-bit atomics — rare) and add it to cluster `to` (shared 32-bit chunk counters, or
+// global atomics for dictionaries too large for shared memory).
+template <int D>
+__device__ __noinline__ void lloyd_move(const double* x, int to, int from, double scale_hi,
+                                        unsigned* s_acc32, unsigned long long* acc) {
+  long long hi[D], lw[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) to_limbs(x[k], scale_hi, hi[k], lw[k]);
+  if (from >= 0) {
+    unsigned long long* a = acc + (size_t)from * (2 * D + 1);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      atomicAdd(a + 2 * k, (unsigned long long)(-hi[k]));
+      atomicAdd(a + 2 * k + 1, (unsigned long long)(-lw[k]));
+    }
+    atomicAdd(a + 2 * D, ~0ull);                            // count - 1
+  }
+  if (s_acc32 != nullptr) {
+    unsigned* a = s_acc32 + (size_t)to * (4 * D + 1);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const unsigned ub = (unsigned)(hi[k] + 2147483648LL);  // hi in [-2^31, 2^31)
+      const unsigned ul = (unsigned)lw[k];
+      atomicAdd(a + 4 * k, ub & 0xFFFFu);
+      atomicAdd(a + 4 * k + 1, ub >> 16);
+      atomicAdd(a + 4 * k + 2, ul & 0xFFFFu);
+      atomicAdd(a + 4 * k + 3, ul >> 16);
+    }
+    atomicAdd(a + 4 * D, 1u);
+  } else {
+    unsigned long long* a = acc + (size_t)to * (2 * D + 1);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      atomicAdd(a + 2 * k, (unsigned long long)hi[k]);
+      atomicAdd(a + 2 * k + 1, (unsigned long long)lw[k]);
+    }
+    atomicAdd(a + 2 * D, 1ull);
+  }
 }
 
 // LAB64: assign mode writes int64 labels (else int32); Lloyd labels are int32
@@ -427,34 +471,18 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
         }
         if (LLOYD) {
           if (valid[p]) {
-            changed += (olab[p] != label[p]);
+            const bool moved = olab[p] != label[p];
+            changed += moved;
             inertia += sq;
-            if (P.update) {
-              if (acc_in_smem) {
-                unsigned* a = s_acc32 + (size_t)label[p] * (4 * D + 1);
+            // incremental M-step: the integer sums are exact, so "remove from the old cluster, add
+            // to the new one" for the rotations that moved equals a recomputation bit for bit —
+            // and after the first iterations most rotations stay where they are
+            if (P.update && (moved || !P.incremental)) {
+              double xm[D];
 #pragma unroll
-                for (int k = 0; k < D; ++k) {
-                  long long hi, lw;
-                  to_limbs((double)xv[p * D + k], P.scale_hi, hi, lw);
-                  const unsigned ub = (unsigned)(hi + 2147483648LL);      // hi in [-2^31, 2^31)
-                  const unsigned ul = (unsigned)lw;
-                  atomicAdd(a + 4 * k, ub & 0xFFFFu);
-                  atomicAdd(a + 4 * k + 1, ub >> 16);
-                  atomicAdd(a + 4 * k + 2, ul & 0xFFFFu);
-                  atomicAdd(a + 4 * k + 3, ul >> 16);
-                }
-                atomicAdd(a + 4 * D, 1u);
-              } else {
-                unsigned long long* a = P.acc + (size_t)label[p] * (2 * D + 1);
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                  long long hi, lw;
-                  to_limbs((double)xv[p * D + k], P.scale_hi, hi, lw);
-                  atomicAdd(a + 2 * k, (unsigned long long)hi);
-                  atomicAdd(a + 2 * k + 1, (unsigned long long)lw);
-                }
-                atomicAdd(a + 2 * D, 1ull);
-              }
+              for (int k = 0; k < D; ++k) xm[k] = (double)xv[p * D + k];
+              lloyd_move<D>(xm, label[p], (P.incremental && moved) ? olab[p] : -1, P.scale_hi,
+                            acc_in_smem ? s_acc32 : nullptr, P.acc);
             }
           }
         } else {
@@ -549,9 +577,8 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
 
 // Threads per CTA (one CTA per SM): the assign form fits 64 registers and runs 32 warps per SM; the
 // Lloyd form (fixed-point limbs + 13 shared atomics per rotation) needs ~120 and runs 16.
-template <typename T, int D, bool LLOYD, bool LAB64>
-int launch_query(const AssignParams& P, cudaStream_t st) {
-  constexpr int kQThreads = LLOYD ? 512 : 1024;
+template <typename T, int D, bool LLOYD, bool LAB64, int kQThreads>
+int launch_query_nt(const AssignParams& P, cudaStream_t st) {
   constexpr int kQWarps = kQThreads / 32;
   using G_ = Geo<T, D>;
   QueryCfg C = {};
@@ -589,6 +616,17 @@ int launch_query(const AssignParams& P, cudaStream_t st) {
   kern<<<(unsigned)blocks, kQThreads, smem, st>>>(P, C);
   BDP_CUDA_CHECK_LAUNCH("query_kernel");
   return BDP_OK;
+}
+
+// 32 warps per SM when everything fits (64 registers, a 2-3 stage ring per warp), else 16
+template <typename T, int D, bool LLOYD, bool LAB64>
+int launch_query(const AssignParams& P, cudaStream_t st) {
+  static const int forced = [] { const char* e = getenv("BDPOSE_QUERY_THREADS"); return e ? atoi(e) : 0; }();
+  if (forced != 512) {
+    const int rc = launch_query_nt<T, D, LLOYD, LAB64, 1024>(P, st);
+    if (rc != BDP_ERR_UNSUPPORTED) return rc;
+  }
+  return launch_query_nt<T, D, LLOYD, LAB64, 512>(P, st);
 }
 
 }  // namespace
