@@ -832,7 +832,9 @@ def allreduce_stack_grads(stack, group=None, average=True):
     if getattr(stack, "stacked", None):
         grads = [p.grad for p in stack.stacked.values() if p.grad is not None]
     if not grads:
-        raise RuntimeError("allreduce_stack_grads: the stack's parameters hold no gradients")
+        if plists:
+            raise RuntimeError("allreduce_stack_grads: the stack's parameters hold no gradients")
+        grads = [g for _, g in sorted(stack.grad.items())]     # a bare stack of gradient buffers
     works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in grads]
     for w in works:
         w.wait()

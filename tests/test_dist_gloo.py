@@ -97,6 +97,19 @@ def _grad_worker(rank, world, store, out):
     mean = sum(range(1, world + 1)) / world
     for k, v in base.items():
         assert torch.allclose(stack.grad[k], v * mean, rtol=1e-6, atol=1e-7), k
+    # Parameters whose .grad are NOT views of the stacked buffers (foreign gradients were present
+    # when backward ran): the gradients the Parameters hold are the ones reduced
+    stack2 = head.HeadStack.__new__(head.HeadStack)
+    ps = [torch.nn.Parameter(torch.zeros(3, 2)) for _ in range(3)]
+    for i, p_ in enumerate(ps):
+        p_.grad = torch.full((3, 2), float((rank + 1) * (i + 1)))
+    stack2.grad = {"w1": torch.zeros(3, 3, 2)}              # stale stacked buffer: must stay untouched
+    stack2.gflat, stack2.stacked = None, None
+    stack2.plists = {"w1": ps}
+    head.allreduce_stack_grads(stack2, group=None)
+    for i, p_ in enumerate(ps):
+        assert torch.allclose(p_.grad, torch.full((3, 2), mean * (i + 1))), i
+    assert float(stack2.grad["w1"].abs().max()) == 0.0
     torch.save({"ok": True}, os.path.join(out, "g_%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
