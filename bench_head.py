@@ -28,6 +28,57 @@ def _time(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
+def _head_context(dev, m, C, K, hbm, ours):
+    """The same Pascal head + loss step (B = 32) through the ORACLE's stock torch modules — on this GPU
+    (torch eager: cuBLAS / ATen kernels, the bar SURVEY §2 names) and on the host cores (the
+    reference's CPU path) — next to ours.  Benchmark-only use of the oracle."""
+    import os
+    import time
+    import bdpose_oracle as O
+    B = 32
+    torch.manual_seed(0)
+    ref = O.OneBinDeltaHeads(C, K, 2048, 1000, 500, 3)
+    x = torch.randn(B, 2048)
+    lab = torch.randint(0, C, (B, 1))
+    bins = torch.randint(0, K, (B,))
+    tgt = torch.randn(B, 3)
+    keys = torch.randn(K, 3)
+
+    def step(mod, dev_):
+        for p in mod.parameters():
+            p.grad = None
+        xx = x.to(dev_).requires_grad_(True)
+        oh = torch.zeros(B, C, device=dev_).scatter_(1, lab.to(dev_), 1.0)
+        y1, y2 = mod(xx, mix=oh)
+        lc, lr = O.bin_delta_terms(y1, y2, bins.to(dev_), tgt.to(dev_), keys.to(dev_), "aa")
+        (lc + lr).backward()
+    # CPU: the reference's path on the host cores (bounded: 1 warm-up + 3 steps)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref.train()
+    step(ref, "cpu")
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step(ref, "cpu")
+    cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+    # stock torch eager on this GPU
+    gref = ref.to(dev)
+    ms_eager = _time(lambda: step(gref, dev), 20, 10)
+    n_params = sum(p.numel() for p in ref.parameters())
+    by = 3 * n_params * 4
+    return {"torch_eager_gpu": {"ms_fwd_bwd": ms_eager, "samples_per_s_fwd_bwd": B / (ms_eager * 1e-3),
+                                "note": "oracle OneBinDeltaHeads (stock nn.Linear / BatchNorm1d) + torch loss "
+                                        "ops on the same B200, fp32"},
+            "cpu_baseline": {"value": B / (cpu_ms * 1e-3), "unit": "samples/s", "ms_fwd_bwd": cpu_ms,
+                             "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": "3 steps of the oracle head + loss (B=32, C=12, K=200) on the host cores"},
+            "roofline": {"bound": "hbm", "achieved": by / (ours["ms_fwd_bwd"] * 1e-3) / 1e9, "peak": hbm,
+                         "unit": "GB/s", "frac": by / (ours["ms_fwd_bwd"] * 1e-3) / 1e9 / hbm,
+                         "algorithmic_bytes_per_step": by,
+                         "note": "drop-in eager step through the reference-named modules: weights streamed "
+                                 "for fprop, dgrad (reads) and wgrad (write), 3 x %d MB" % (n_params * 4 // 1_000_000)},
+            "speedup_vs_torch_eager_gpu": ms_eager / ours["ms_fwd_bwd"]}
+
+
 def bench(dev, peaks):
     """BASELINE configs 1 and 4: head + fused loss, forward+backward, samples/s."""
     import binDeltaLosses  # noqa: F401  (the fused loss mirrors)
@@ -69,6 +120,9 @@ def bench(dev, peaks):
                 "fwd_hbm_frac": wbytes / (ms_f * 1e-3) / 1e9 / hbm,
                 "fwd_bwd_hbm_frac": 3 * wbytes / (ms * 1e-3) / 1e9 / hbm,
                 "weight_bytes": wbytes}
+    # ---- the bars this leg is measured against ("stock PyTorch eager ops on the same B200"
+    #      and the reference's CPU path), config 1: B = 32, fp32 -------------------------------------------
+    out["pascal_head_B32_context"] = _head_context(dev, m, C, K, hbm, out["pascal_head_B32_fp32"])
     # opt-in fast path: 10 stacked Parameters instead of 336 per-module ones
     sp = m.stacked_head_parameters()
     for B in (32, 96):
