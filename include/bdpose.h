@@ -168,6 +168,19 @@ typedef struct bdp_sgd_tensor {
 int bdp_sgd_step(const bdp_sgd_tensor* table_dev, int n_tensors, int64_t max_numel, float weight_decay,
                  float momentum, float dampening, int nesterov, void* stream);
 
+/*
+ * Column statistics of the k-means preprocessing (scikit-learn KMeans.fit: X -= X.mean(0);
+ * tol = mean(var(X)) * tol — sklearn/cluster/_kmeans.py), in fixed point so that they do not depend on
+ * the order of summation or on how the rows are split over GPUs.  x [N, d] fp64; `out` is ADDED to /
+ * max-ed into (zero it first; all-reduce it across ranks afterwards):
+ *   mode 0  out[0] = max |x|                         (uint64 bit pattern of the double, atomic max)
+ *   mode 1  out[0..d) += sum floor(x * scale), out[d..2d) += sum trunc(frac(x * scale) * 2^32)  (int64)
+ *   mode 2  y = x - mean[col]; out[0] = max (x - mean)^2, out[1] = max |x - mean|   (bit patterns)
+ *   mode 3  out[0..d) += sum llrint(x^2 * scale)     (x already centred; int64)
+ */
+int bdp_fit_stats(const double* x, int64_t N, int d, int mode, const double* mean, double scale,
+                  double* y, void* out, void* stream);
+
 /* buf[i] *= *scale_dev, i < n; returns at once (no memory traffic) when *scale_dev == 1 — the upstream
  * scalar of a loss whose gradient the forward launch already wrote (buf 16-byte aligned). */
 int bdp_scale_inplace(float* buf, int64_t n, const float* scale_dev, void* stream);

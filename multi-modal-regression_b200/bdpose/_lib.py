@@ -41,6 +41,7 @@ SIGNATURES = {
     "bdp_min_key_gap": (_int, [_p, _int, _int, _p, _p]),
     "bdp_sgd_step": (_int, [_p, _int, _i64, _f32, _f32, _f32, _int, _p]),
     "bdp_scale_inplace": (_int, [_p, _i64, _p, _p]),
+    "bdp_fit_stats": (_int, [_p, _i64, _int, _int, _p, _f64, _p, _p, _p]),
     "bdp_assign_nearest": (_int, [_p, _int, _i64, _int, _p, _int, _p, _p, _p, _p, _p]),
     "bdp_assign_quatdot": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p]),
     "bdp_assign_soft": (_int, [_p, _int, _i64, _int, _p, _int, _f64, _p, _p, _p]),

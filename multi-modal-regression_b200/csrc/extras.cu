@@ -217,3 +217,98 @@ extern "C" int bdp_scale_inplace(float* buf, int64_t n, const float* scale_dev, 
   BDP_CUDA_CHECK_LAUNCH("scale_kernel");
   return BDP_OK;
 }
+
+// ---- fit preprocessing (scikit-learn KMeans.fit: X -= X.mean(0); tol = mean(var(X)) * tol) -------------
+// Column statistics in fixed point, so that the mean / variance — and with them the centred data and
+// every label — do not depend on how the rows are split over blocks or GPUs.
+namespace {
+
+// mode 0: stats[0] = max |x| (as the bit pattern of a non-negative double, atomicMax)
+// mode 1: limbs[2][d] += two-limb fixed-point column sums of x * 2^hi_bits
+// mode 2: y = x - mean (written), stats[0] = max (x-mean)^2, stats[1] = max |x - mean|
+// mode 3: q[d] += round((x)^2 * 2^sh) column sums (x already centred)
+template <int MODE>
+__global__ void __launch_bounds__(256) fit_stats_kernel(const double* __restrict__ x, int64_t N, int d,
+                                                        const double* __restrict__ mean, double scale,
+                                                        double* __restrict__ y,
+                                                        unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long s_a[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t total = N * d;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // every thread keeps its column fixed: the stride is a multiple of d
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double m0 = 0.0, m1 = 0.0;
+  long long a_hi = 0, a_lo = 0;
+  const int col = (int)(i0 % d);
+  const double mu = (MODE == 2) ? mean[col] : 0.0;
+  for (int64_t i = i0; i < total; i += stride) {
+    const double v = x[i];
+    if (MODE == 0) {
+      m0 = fmax(m0, fabs(v));
+    } else if (MODE == 1) {
+      const double xs = v * scale;
+      const double f = floor(xs);
+      a_hi += (long long)f;
+      a_lo += (long long)((xs - f) * 4294967296.0);
+    } else if (MODE == 2) {
+      const double c = v - mu;
+      y[i] = c;
+      m0 = fmax(m0, c * c);
+      m1 = fmax(m1, fabs(c));
+    } else {
+      a_hi += llrint(v * v * scale);
+    }
+  }
+  if (MODE == 0 || MODE == 2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m0 = fmax(m0, __shfl_xor_sync(BDP_FULL_MASK, m0, o));
+      m1 = fmax(m1, __shfl_xor_sync(BDP_FULL_MASK, m1, o));
+    }
+    if (lane == 0) {
+      atomicMax(out + 0, (unsigned long long)__double_as_longlong(m0));
+      if (MODE == 2) atomicMax(out + 1, (unsigned long long)__double_as_longlong(m1));
+    }
+  } else {
+    // per-column sums: lanes of a warp hold different columns (lane % d pattern differs per warp), so
+    // reduce through shared memory by column
+    if (threadIdx.x < 64) s_a[threadIdx.x >> 3][threadIdx.x & 7] = 0ull;
+    __syncthreads();
+    atomicAdd(&s_a[0][col], (unsigned long long)a_hi);
+    if (MODE == 1) atomicAdd(&s_a[1][col], (unsigned long long)a_lo);
+    __syncthreads();
+    if (threadIdx.x < d) {
+      atomicAdd(out + threadIdx.x, s_a[0][threadIdx.x]);
+      if (MODE == 1) atomicAdd(out + d + threadIdx.x, s_a[1][threadIdx.x]);
+    }
+    (void)warp;
+  }
+}
+
+}  // namespace
+
+extern "C" int bdp_fit_stats(const double* x, int64_t N, int d, int mode, const double* mean,
+                             double scale, double* y, void* out, void* stream) {
+  BDP_REQUIRE(N >= 0 && d >= 1 && d <= 8, "fit_stats: N %lld, d %d", (long long)N, d);
+  if (N == 0) return BDP_OK;
+  BDP_REQUIRE(x && out, "fit_stats: NULL buffer");
+  BDP_REQUIRE(mode >= 0 && mode <= 3, "fit_stats: mode %d", mode);
+  BDP_REQUIRE(mode != 2 || (mean && y), "fit_stats: mode 2 needs mean and y");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // grid stride = blocks * 256 must be a multiple of d so that a thread stays in one column
+  int64_t blocks = (int64_t)bdp_num_sms() * 8;
+  blocks -= blocks % d;
+  const int64_t need = ceil_div64(N * d, 256);
+  if (blocks > need) blocks = need - need % d;
+  if (blocks < d) blocks = d;
+  unsigned long long* o = reinterpret_cast<unsigned long long*>(out);
+  switch (mode) {
+    case 0: fit_stats_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(x, N, d, mean, scale, y, o); break;
+    case 1: fit_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, N, d, mean, scale, y, o); break;
+    case 2: fit_stats_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, N, d, mean, scale, y, o); break;
+    default: fit_stats_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, N, d, mean, scale, y, o); break;
+  }
+  BDP_CUDA_CHECK_LAUNCH("fit_stats_kernel");
+  return BDP_OK;
+}

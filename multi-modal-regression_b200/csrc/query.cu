@@ -19,8 +19,6 @@
 // The arithmetic that decides a label is unchanged (fp32 screen of the cell's candidate keys with a
 // rigorous error bound, fp64 exact pass on near ties, ascending key order, warp-cooperative scan for
 // points outside the grid), so labels and residuals are bit-identical to the brute-force kernel.
-#include <stdlib.h>
-
 #include "assign_common.cuh"
 
 using namespace bdp_assign;
@@ -70,14 +68,6 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // generic-proxy shared writes -> visible to the async proxy (the bulk store that follows)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void unpack16(const uint4& q, float* d) {
-  d[0] = __uint_as_float(q.x); d[1] = __uint_as_float(q.y); d[2] = __uint_as_float(q.z); d[3] = __uint_as_float(q.w);
-}
-__device__ __forceinline__ void unpack16(const uint4& q, double* d) {
-  d[0] = __hiloint2double((int)q.y, (int)q.x); d[1] = __hiloint2double((int)q.w, (int)q.z);
-}
-__device__ __forceinline__ void unpack8(const uint2& q, float* d) { d[0] = __uint_as_float(q.x); d[1] = __uint_as_float(q.y); }
-__device__ __forceinline__ void unpack8(const uint2& q, double* d) { d[0] = __hiloint2double((int)q.y, (int)q.x); }
 __host__ __device__ constexpr size_t a16(size_t b) { return (b + 15) & ~(size_t)15; }
 
 struct QueryCfg {
@@ -169,7 +159,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
   constexpr int kQWarps = kQThreads / 32;
   if (P.stop != nullptr && *reinterpret_cast<const volatile int*>(P.stop) != 0) return;
   using G_ = Geo<T, D>;
-  constexpr int PTS = G_::PTS, WPTS = G_::WPTS, XB = G_::XB, XV = G_::XV, RB = G_::RB, RV = G_::RV;
+  constexpr int PTS = G_::PTS, WPTS = G_::WPTS, XB = G_::XB, RB = G_::RB, RV = G_::RV;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_full[kQWarps][kMaxStages];
   __shared__ double s_red[2][kQWarps];
@@ -234,11 +224,11 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
 
   // point -> cell: t = x * inv + (-origin * inv), one FMA per coordinate in the input type (the
   // rounding is covered by kBoxEps, see assign_common.cuh)
-  T g_inv[D], g_off[D];
+  float g_inv[D], g_off[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
-    g_inv[k] = (T)P.ghdr->inv_cell[k];
-    g_off[k] = (T)(-P.ghdr->origin[k] * P.ghdr->inv_cell[k]);
+    g_inv[k] = (float)P.ghdr->inv_cell[k];
+    g_off[k] = (float)(-P.ghdr->origin[k] * P.ghdr->inv_cell[k]);
   }
   const int G = P.ghdr->G;
   const bool g_on = P.ghdr->enabled != 0;
@@ -297,33 +287,21 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
         }
         __syncwarp();
       }
-      // this lane's PTS consecutive rotations (and previous labels)
-      T xv[PTS * D];
-      if ((PTS * D * (int)sizeof(T)) % 16 == 0) {
-        const uint4* src = reinterpret_cast<const uint4*>(xs) + lane * XV;
-#pragma unroll
-        for (int v = 0; v < XV; ++v) unpack16(src[v], xv + v * (16 / (int)sizeof(T)));
-      } else {                                              // fp32, d = 3: 24 bytes per lane
-        const uint2* src = reinterpret_cast<const uint2*>(xs) + lane * (PTS * D * (int)sizeof(T) / 8);
-#pragma unroll
-        for (int v = 0; v < PTS * D * (int)sizeof(T) / 8; ++v) {
-          const uint2 q = src[v];
-          unpack8(q, xv + v * (8 / (int)sizeof(T)));
-        }
-      }
+      // The stage stays valid for the whole tile (its reload is issued at the end): registers only
+      // hold the fp32 copies of the lane's PTS consecutive rotations; the few places that need the
+      // original values (exact re-check, residual, M-step of a moved rotation) read the stage again.
+      const T* xst = reinterpret_cast<const T*>(xs) + lane * (PTS * D);
       int olab[PTS];
       if (LLOYD) {                                          // Lloyd data is fp64: PTS == 2
         const int2 o = *(reinterpret_cast<const int2*>(ls) + lane);
         olab[0] = o.x; olab[PTS - 1] = o.y;
       }
-      __syncwarp();                                         // the stage is free again
-      if (tma) {
-        if (lane == 0 && it + nst < m_tma) issue(it + nst, s);
-        if (++stage == nst) { stage = 0; phase ^= 1u; }
-      }
 
-      // phase 1: cells and the first 16 bytes of every record (all loads in flight together)
+      // phase 1: cells and the 16-byte record of every rotation (all loads in flight together).  The
+      // point -> cell map runs in fp32 for fp64 rotations too (the fp32 copy is needed for the screen
+      // anyway; its rounding moves the cell coordinate by < 1e-5 cells, covered by kBoxEps)
       uint4 first[PTS];
+      float xf[PTS * D];
       bool valid[PTS], slow[PTS];
 #pragma unroll
       for (int p = 0; p < PTS; ++p) {
@@ -332,11 +310,12 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
         unsigned cidx = 0, mul = 1;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          const T t = xv[p * D + k] * g_inv[k] + g_off[k];
+          xf[p * D + k] = (float)xst[p * D + k];
+          const float t = fmaf(xf[p * D + k], g_inv[k], g_off[k]);
           // floor + one unsigned compare: negative, too large and infinite coordinates fail it; a NaN
           // converts to 0 and flows through the candidates of a valid cell — every comparison with
           // it is false, which ends at label 0 exactly like the scan (argmin of an all-NaN row)
-          const int ck = sizeof(T) == 4 ? __float2int_rd((float)t) : __double2int_rd((double)t);
+          const int ck = __float2int_rd(t);
           ok = ok && ((unsigned)ck < (unsigned)G);
           cidx += (unsigned)ck * mul;
           mul *= (unsigned)G;
@@ -352,17 +331,17 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
         const unsigned cnt = first[p].x & 0xFFFFu;
         if (valid[p] && cnt == kGridOverflow) slow[p] = true;
         if (!valid[p] || slow[p]) continue;
-        float xf[D];
+        const float* xfp = xf + p * D;
         float n2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < D; ++k) { xf[k] = (float)xv[p * D + k]; n2 = fmaf(xf[k], xf[k], n2); }
+        for (int k = 0; k < D; ++k) n2 = fmaf(xfp[k], xfp[k], n2);
         float best = INFINITY, second = INFINITY;
         unsigned boff = 0;                                 // byte offset (id * 16) of the best record
         const unsigned fw[4] = {first[p].x, first[p].y, first[p].z, first[p].w};
         auto screen = [&](unsigned off) {                  // off = key id * 16 (byte offset of its record)
           const float4 cr = *reinterpret_cast<const float4*>(recs + off);
           const float cn = (D == 4) ? s_cn[off >> 4] : 0.f;
-          const float d = screen_dist<D>(xf, cr, cn);
+          const float d = screen_dist<D>(xfp, cr, cn);
           const bool lt = d < best;
           second = fminf(second, lt ? best : d);
           boff = lt ? off : boff;
@@ -407,7 +386,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
             double sq = 0.0;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-              const double df = (double)xv[p * D + k] - __ldg(c + k);
+              const double df = (double)xst[p * D + k] - __ldg(c + k);
               sq += df * df;
             }
             if (sq < bd) { bd = sq; bidx = id; }
@@ -423,8 +402,9 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
           const int src = __ffs(m) - 1;
           m &= m - 1;
           double xe[D];
+          const T* xsrc = reinterpret_cast<const T*>(xs) + (src * PTS + p) * D;
 #pragma unroll
-          for (int k = 0; k < D; ++k) xe[k] = (double)__shfl_sync(BDP_FULL_MASK, xv[p * D + k], src);
+          for (int k = 0; k < D; ++k) xe[k] = (double)xsrc[k];
           double bd = INFINITY;
           int bi = 0x7fffffff;
           for (int j = lane; j < K; j += 32) {
@@ -460,11 +440,11 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
         if (!LLOYD || want_sq) {
           if (C.cd_smem) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) diff[k] = (double)xv[p * D + k] - s_cd[label[p] * D + k];
+            for (int k = 0; k < D; ++k) diff[k] = (double)xst[p * D + k] - s_cd[label[p] * D + k];
           } else {
             const double* c = P.centers + (int64_t)label[p] * D;
 #pragma unroll
-            for (int k = 0; k < D; ++k) diff[k] = (double)xv[p * D + k] - __ldg(c + k);
+            for (int k = 0; k < D; ++k) diff[k] = (double)xst[p * D + k] - __ldg(c + k);
           }
 #pragma unroll
           for (int k = 0; k < D; ++k) sq += diff[k] * diff[k];
@@ -480,7 +460,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
             if (P.update && (moved || !P.incremental)) {
               double xm[D];
 #pragma unroll
-              for (int k = 0; k < D; ++k) xm[k] = (double)xv[p * D + k];
+              for (int k = 0; k < D; ++k) xm[k] = (double)xst[p * D + k];
               lloyd_move<D>(xm, label[p], (P.incremental && moved) ? olab[p] : -1, P.scale_hi,
                             acc_in_smem ? s_acc32 : nullptr, P.acc);
             }
@@ -552,6 +532,11 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
         __syncwarp();
       }
       ++done_tiles;
+      __syncwarp();                                         // every lane is done with the stage
+      if (tma) {
+        if (lane == 0 && it + nst < m_tma) issue(it + nst, s);
+        if (++stage == nst) { stage = 0; phase ^= 1u; }
+      }
     }
     if (acc_in_smem && ++since_flush == flush_every) {
       flush_acc<D, kQThreads>(s_acc32, K, P.acc);
@@ -618,15 +603,12 @@ int launch_query_nt(const AssignParams& P, cudaStream_t st) {
   return BDP_OK;
 }
 
-// 32 warps per SM when everything fits (64 registers, a 2-3 stage ring per warp), else 16
+// One CTA of 1024 threads per SM (64 registers: 32 warps hide the scattered L2 record loads).  A
+// 512-thread / 128-register build of the same kernel was slower (170 vs 137 us for 10 M rotations) and
+// is not kept; dictionaries too large for this form's shared memory take the brute-force scan.
 template <typename T, int D, bool LLOYD, bool LAB64>
 int launch_query(const AssignParams& P, cudaStream_t st) {
-  static const int forced = [] { const char* e = getenv("BDPOSE_QUERY_THREADS"); return e ? atoi(e) : 0; }();
-  if (forced != 512) {
-    const int rc = launch_query_nt<T, D, LLOYD, LAB64, 1024>(P, st);
-    if (rc != BDP_ERR_UNSUPPORTED) return rc;
-  }
-  return launch_query_nt<T, D, LLOYD, LAB64, 512>(P, st);
+  return launch_query_nt<T, D, LLOYD, LAB64, 1024>(P, st);
 }
 
 }  // namespace

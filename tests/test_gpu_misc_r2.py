@@ -37,7 +37,7 @@ def test_get_gamma_and_accuracy_golden(cuda, golden):
 
 def test_compose_prediction_golden(cuda, golden):
     """dict[argmax] (+) residual in the three forms of the scripts' testing() loops: outputs equal
-    the numpy lines of the scripts (1e-6 absolute for the Riemannian form, whose script evaluates
+    the numpy lines of the scripts (5e-6 absolute for the Riemannian form, whose script evaluates
     get_R on float32 residuals), bins bit-exact incl. the planted argmax tie."""
     from bdpose import ops
     g = golden("misc_r2")
@@ -51,7 +51,9 @@ def test_compose_prediction_golden(cuda, golden):
     np.testing.assert_allclose(y.cpu().numpy(), g["t_quat"], rtol=0, atol=1e-15)
     y, _ = ops.compose_prediction(sc, torch.from_numpy(g["t_res"]).to(cuda),
                                   torch.from_numpy(g["t_rotdict"]).to(cuda), mode="riemannian")
-    np.testing.assert_allclose(y.cpu().numpy(), g["t_riem"], rtol=0, atol=1e-6)
+    # (the script line runs get_R on float32 residuals: its own rounding is ~1e-7 relative, amplified
+    # near theta = pi by the log map — 5e-6 absolute against it, 1e-12 against the fp64 restatement)
+    np.testing.assert_allclose(y.cpu().numpy(), g["t_riem"], rtol=0, atol=5e-6)
     # the fp64 oracle restatement (same arithmetic precision as the kernel) to 1e-12
     np.testing.assert_allclose(y.cpu().numpy(), O.compose_riemannian(g["t_score"], g["t_res"].astype(np.float64),
                                                                      g["t_rotdict"]), rtol=0, atol=1e-12)

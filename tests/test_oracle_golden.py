@@ -189,7 +189,7 @@ def test_round2_misc(golden):
     np.testing.assert_array_equal(O.compose_add(g["t_score"], g["t_res"], g["t_dict"]), g["t_add"])
     np.testing.assert_array_equal(O.compose_normalize(g["t_score"], g["t_res4"], g["t_qdict"]), g["t_quat"])
     np.testing.assert_allclose(O.compose_riemannian(g["t_score"], g["t_res"], g["t_rotdict"]), g["t_riem"],
-                               rtol=0, atol=1e-6)      # the script evaluates get_R on float32 residuals
+                               rtol=0, atol=5e-6)      # the script evaluates get_R on float32 residuals
     t1, t2 = g["sgd_t1"], g["sgd_t2"]
 
     def grads(p):
