@@ -455,15 +455,21 @@ def main():
     # ---- dominant kernel: the E+M kernel of every iteration of the SAME fit, bracketed by CUDA events
     #      on its stream inside bdp_kmeans_run (the first iteration accumulates every rotation, the later
     #      ones only move the rotations whose label changed) --------------------------------------------
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4 * steps)]
     for e in evs:
         e.record()                                       # creates the underlying cudaEvent_t
     loop.reset(fs.centers)
     torch.cuda.synchronize()
     loop.launch(0, steps, False, em_events=evs)
     torch.cuda.synchronize()
-    em_ms = [evs[2 * i].elapsed_time(evs[2 * i + 1]) for i in range(steps)]
+    em_ms = [evs[4 * i + 1].elapsed_time(evs[4 * i + 2]) for i in range(steps)]
     kernel_ms = sum(em_ms) / steps
+    anatomy = {"grid_build_ms": sum(evs[4 * i].elapsed_time(evs[4 * i + 1]) for i in range(steps)) / steps,
+               "e_m_kernel_ms": kernel_ms,
+               "exchange_finalise_ms": sum(evs[4 * i + 2].elapsed_time(evs[4 * i + 3]) for i in range(steps)) / steps,
+               "note": "mean per iteration on this rank, CUDA events inside bdp_kmeans_run; with several ranks "
+                       "the E+M kernel first waits for every rank's grid slab and the exchange kernel for "
+                       "every rank's sums, so rank skew shows up there"}
     grid.rebuild(fs.centers)
     build_ms = timed(lambda: grid.rebuild(), max(steps, 10), 3)
     achieved = n_local * BYTES_PER_ROT_ITER / (kernel_ms * 1e-3) / 1e9
@@ -572,6 +578,7 @@ def main():
                                  "the E+M kernels of the timed fit's iterations (CUDA events inside the loop); "
                                  "an iteration also runs the 3 key-grid build launches (sharded over the ranks) "
                                  "and the exchange+finalise kernel"},
+            "iteration_anatomy": anatomy,
             "parity": parity,
             "cpu_baseline": cpu,
             "extras": ex,

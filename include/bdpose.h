@@ -351,8 +351,9 @@ int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
  *     The sums are integers, so this equals a recomputation bit for bit; after the first iterations
  *     few labels change and the M-step costs next to nothing.  `labels` must then be the labels the
  *     accumulators were built from (-1 and zeroed accumulators at the start of a fit).
- *     em_events (NULL: none): 2 * n_iters caller-owned cudaEvent_t handles recorded right before and
- *     after the E+M kernel of every iteration (benchmark instrumentation).
+ *     em_events (NULL: none): 4 * n_iters caller-owned cudaEvent_t handles (benchmark
+ *     instrumentation; needs the key grid), recorded per iteration before the grid build, before the E+M
+ *     kernel, after it, and after the exchange+finalise kernel.
  *     grid_peers (NULL: every rank builds the whole grid itself) = this process's addresses of
  *     every rank's key-grid buffer, allocated like the exchange buffers: the build is then SHARDED —
  *     a rank builds the cells of one slab of the grid and stores them into every rank's buffer over

@@ -315,8 +315,9 @@ class LloydLoop:
 
     def launch(self, i0, n, check, em_events=None):
         """Queue iterations i0 .. i0+n-1 on the current stream (no host synchronisation).
-        em_events: 2n recorded-once torch.cuda.Event(enable_timing=True) objects that will bracket
-        the E+M kernel of every iteration (benchmark instrumentation)."""
+        em_events: 4n recorded-once torch.cuda.Event(enable_timing=True) objects, recorded per
+        iteration before the grid build, before / after the E+M kernel and after the exchange kernel
+        (benchmark instrumentation)."""
         import ctypes as C
         lib = L.lib()
         g = self.grid

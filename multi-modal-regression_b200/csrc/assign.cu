@@ -400,52 +400,6 @@ __device__ __forceinline__ double bisector_min(const double* __restrict__ ck, co
   return f + (nk - np);
 }
 
-// One warp filters a key list against one box.  src == nullptr: the whole dictionary.
-template <int D>
-__device__ __forceinline__ void filter_box(const double* __restrict__ centers, int K,
-                                           const unsigned short* __restrict__ src, int n_src,
-                                           const double lo[D], const double hi[D],
-                                           unsigned short* __restrict__ rec, int cap, int lane) {
-  double u = INFINITY;
-  int piv = 0;
-  for (int j = lane; j < n_src; j += 32) {
-    const int k = src ? (int)src[j] : j;
-    double mn, mx;
-    box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-    if (mx < u) { u = mx; piv = k; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ou = __shfl_xor_sync(BDP_FULL_MASK, u, o);
-    const int op = __shfl_xor_sync(BDP_FULL_MASK, piv, o);
-    if (ou < u || (ou == u && op < piv)) { u = ou; piv = op; }
-  }
-  const double thr = u * (1.0 + 1e-9) + 1e-300;
-  double cp[D];
-#pragma unroll
-  for (int k = 0; k < D; ++k) cp[k] = __ldg(centers + (int64_t)piv * D + k);
-  int cnt = 0;
-  for (int j0 = 0; j0 < n_src; j0 += 32) {
-    const int j = j0 + lane;
-    bool keep = false;
-    int k = 0;
-    if (j < n_src) {
-      k = src ? (int)src[j] : j;
-      double mn, mx, sc;
-      box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-      const double bm = bisector_min<D>(centers + (int64_t)k * D, cp, lo, hi, sc);
-      keep = mn <= thr && bm <= 1e-9 * sc;
-    }
-    const unsigned m = __ballot_sync(BDP_FULL_MASK, keep);
-    if (keep) {
-      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-      if (pos < cap) rec[1 + pos] = (unsigned short)k;      // ascending key order
-    }
-    cnt += __popc(m);
-  }
-  if (lane == 0) rec[0] = (unsigned short)(cnt > cap ? kGridOverflow : (unsigned)cnt);
-}
-
 // A block of 8 warps filters the WHOLE dictionary against one box; the warps take contiguous key
 // ranges so the compacted list stays in ascending key order.  rec has room for K ids.
 template <int D>
@@ -508,63 +462,101 @@ __device__ __forceinline__ void filter_box_block(const double* __restrict__ cent
   __syncthreads();
 }
 
-// Super cells (4 coarse = 16 fine cells per side): one block per cell over the whole dictionary.
-// Every block derives the grid geometry itself (K*D loads); block 0 publishes it.
+// The coarse filter of the fused build, in fp32: keys of the WHOLE dictionary that can be nearest to
+// some point of the box [lo, hi], ascending, into rec[0] = count, rec[1..] = ids, with their fp32
+// coordinates next to them in s_cf (both shared memory; at most `cap` keys are stored, the count is
+// the true one).  Same two tests as box_bounds / bisector_min, on a box widened by 1e-6 and with
+// thresholds relaxed by far more than the fp32 rounding — a list may only grow.
 template <int D>
-__global__ void __launch_bounds__(256) keygrid_super_kernel(const double* __restrict__ centers, int K,
-                                                            int G, double margin_frac,
-                                                            GridHdr* __restrict__ hdr,
-                                                            unsigned short* __restrict__ super,
-                                                            int super0, const int* stop) {
-  if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
-  __shared__ GridHdr s_hdr;
-  compute_header<D>(centers, K, G, margin_frac, &s_hdr);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { s_hdr.side_next = 0u; s_hdr.ticket = 0u; *hdr = s_hdr; }
-  const int Gs = (G / 4 + 3) / 4;
-  double lo[D], hi[D];
-  const int cell = super0 + blockIdx.x;             // this rank's slab of super cells
-  int r = cell;
+__device__ __forceinline__ void coarse_filter_f32(const float4* __restrict__ cf32, int K,
+                                                  const float lo[D], const float hi[D],
+                                                  unsigned short* __restrict__ rec,
+                                                  float4* __restrict__ s_cf, int cap) {
+  __shared__ float s_u[8];
+  __shared__ int s_p[8], s_c[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (((K + 7) / 8) + 31) & ~31;          // contiguous key range per warp (<= 512)
+  const int b0 = min(K, warp * per), b1 = min(K, b0 + per);
+  float u = INFINITY;
+  int piv = 0x7fffffff;
+  for (int k = b0 + lane; k < b1; k += 32) {
+    const float4 c4 = __ldg(cf32 + k);
+    const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+    float mx = 0.f;
 #pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const int ck = r % Gs;
-    r /= Gs;
-    const double eps = kBoxEps * s_hdr.cell[k];
-    lo[k] = s_hdr.origin[k] + (double)(16 * ck) * s_hdr.cell[k] - eps;
-    hi[k] = s_hdr.origin[k] + (double)min(16 * ck + 16, G) * s_hdr.cell[k] + eps;
-  }
-  filter_box_block<D>(centers, K, lo, hi, super + (int64_t)cell * (K + 1));
-}
-
-// Coarse cells (4 fine cells per side): one warp filters its super cell's list against one cell.
-template <int D>
-__global__ void __launch_bounds__(256) keygrid_coarse_kernel(const double* __restrict__ centers,
-                                                             int K, const GridHdr* __restrict__ hdr,
-                                                             const unsigned short* __restrict__ super,
-                                                             unsigned short* __restrict__ coarse,
-                                                             int64_t cell0, int64_t cell1,
-                                                             const int* stop) {
-  if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
-  const int lane = threadIdx.x & 31;
-  const int Gc = hdr->G / 4, Gs = (Gc + 3) / 4;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t cell = cell0 + warp0; cell < cell1; cell += n_warps) {
-    double lo[D], hi[D];
-    int64_t r = cell, parent = 0, pm = 1;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      const int ck = (int)(r % Gc);
-      r /= Gc;
-      const double eps = kBoxEps * hdr->cell[k];
-      lo[k] = hdr->origin[k] + (double)(4 * ck) * hdr->cell[k] - eps;
-      hi[k] = hdr->origin[k] + (double)(4 * ck + 4) * hdr->cell[k] + eps;
-      parent += (int64_t)(ck / 4) * pm;
-      pm *= Gs;
+    for (int q = 0; q < D; ++q) {
+      const float far = fmaxf(fabsf(c[q] - lo[q]), fabsf(hi[q] - c[q]));
+      mx = fmaf(far, far, mx);
     }
-    const unsigned short* prec = super + parent * (K + 1);
-    filter_box<D>(centers, K, prec + 1, (int)prec[0], lo, hi, coarse + cell * (kCoarseCap + 1),
-                  kCoarseCap, lane);
+    if (mx < u) { u = mx; piv = k; }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ou = __shfl_xor_sync(BDP_FULL_MASK, u, o);
+    const int op = __shfl_xor_sync(BDP_FULL_MASK, piv, o);
+    if (ou < u || (ou == u && op < piv)) { u = ou; piv = op; }
+  }
+  if (lane == 0) { s_u[warp] = u; s_p[warp] = piv; }
+  __syncthreads();
+  u = s_u[0]; piv = s_p[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w)
+    if (s_u[w] < u || (s_u[w] == u && s_p[w] < piv)) { u = s_u[w]; piv = s_p[w]; }
+  if (piv == 0x7fffffff) piv = 0;
+  const float thr = u * (1.f + 1e-4f) + 1e-5f;
+  const float4 p4 = __ldg(cf32 + piv);
+  const float cp[4] = {p4.x, p4.y, p4.z, p4.w};
+  float np = 0.f;
+#pragma unroll
+  for (int q = 0; q < D; ++q) np = fmaf(cp[q], cp[q], np);
+  // keep flags of this warp's range, one ballot per 32 keys (at most 16 chunks)
+  unsigned masks[16];
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    masks[i] = 0u;
+    const int k0 = b0 + 32 * i;
+    if (k0 < b1) {                                       // warp-uniform
+      const int k = k0 + lane;
+      bool keep = false;
+      if (k < b1) {
+        const float4 c4 = __ldg(cf32 + k);
+        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+        float mn = 0.f, f = 0.f, nk = 0.f;
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+          const float near = fmaxf(fmaxf(lo[q] - c[q], c[q] - hi[q]), 0.f);
+          mn = fmaf(near, near, mn);
+          const float dlt = c[q] - cp[q];
+          f = fmaf(-2.f * dlt, dlt > 0.f ? hi[q] : lo[q], f);
+          nk = fmaf(c[q], c[q], nk);
+        }
+        keep = mn <= thr && f + (nk - np) <= 1e-3f * (1.f + nk + np);
+      }
+      masks[i] = __ballot_sync(BDP_FULL_MASK, keep);
+      cnt += __popc(masks[i]);
+    }
+  }
+  if (lane == 0) s_c[warp] = cnt;
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { off += w < warp ? s_c[w] : 0; total += s_c[w]; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const unsigned m = masks[i];
+    if (m & (1u << lane)) {
+      const int pos = off + __popc(m & ((1u << lane) - 1u));
+      if (pos < cap) {
+        const int k = b0 + 32 * i + lane;
+        rec[1 + pos] = (unsigned short)k;
+        s_cf[pos] = __ldg(cf32 + k);
+      }
+    }
+    off += __popc(m);
+  }
+  if (threadIdx.x == 0) rec[0] = (unsigned short)(total > 0xFFFF ? 0xFFFF : total);
+  __syncthreads();
 }
 
 // Where a build writes its cells: the fine / side arrays of every rank of a multi-GPU fit (peer
@@ -578,85 +570,169 @@ struct BuildOut {
   unsigned long long flag_value;
 };
 
-// Fine cells: one THREAD per cell, the 4^D children of a coarse cell on adjacent threads, so the
-// parent's key list and the keys themselves are warp-uniform (broadcast) loads.  A thread assembles
-// its 16-byte record in registers and stores it to every rank's grid (one 128-bit store per peer,
-// posted over NVLink); the last block to finish raises this rank's flag on every peer.
+// Grid geometry + reset of the build counters: one block.
 template <int D>
-__global__ void __launch_bounds__(256) keygrid_fine_kernel(const double* __restrict__ centers, int K,
-                                                           GridHdr* __restrict__ hdr,
-                                                           const unsigned short* __restrict__ coarse,
-                                                           const BuildOut out, int64_t parent0,
-                                                           int64_t n_cells, const int* stop) {
+__global__ void __launch_bounds__(256) keygrid_header_kernel(const double* __restrict__ centers, int K,
+                                                             int G, double margin_frac,
+                                                             GridHdr* __restrict__ hdr,
+                                                             float4* __restrict__ cf32, const int* stop) {
   if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
+  __shared__ GridHdr s_hdr;
+  compute_header<D>(centers, K, G, margin_frac, &s_hdr);
+  if (threadIdx.x == 0) { s_hdr.side_next = 0u; s_hdr.ticket = 0u; *hdr = s_hdr; }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {   // fp32 copy of the keys for the box tests
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < D; ++q) c[q] = (float)centers[(int64_t)k * D + q];
+    cf32[k] = make_float4(c[0], c[1], c[2], c[3]);
+  }
+}
+
+// One BLOCK per coarse cell (4^D fine cells).  Phase (a): all 256 threads filter the whole dictionary
+// against the coarse box into an ascending shared-memory list (the keys that can be nearest somewhere
+// in the coarse cell).  Phase (b): the fine children filter that list against their own boxes — four
+// lanes per child for d = 3 (64 children), one for d = 4 (256 children) — and one lane per child
+// assembles the 16-byte record (+ side record) and stores it to every rank's grid (posted 128-bit
+// stores over NVLink).  The last block to finish raises this rank's flag on every peer.  No level of
+// the hierarchy leaves the block, so a rank that builds 1/8 of the cells pays 1/8 of the time.
+// The box tests run in fp32 with relaxed thresholds (a candidate list has to CONTAIN every key that
+// can be nearest; a few extra keys only cost query time — the query itself is exact).
+constexpr int kCoarseListCap = 1024;
+template <int D>
+__global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restrict__ cf32, int K,
+                                                           GridHdr* __restrict__ hdr, const BuildOut out,
+                                                           int64_t coarse0, int active, const int* stop) {
+  if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
+  if (!active) {                                       // a rank with an empty slab only publishes its flag
+    if (out.world > 1 && threadIdx.x < out.world) {
+      __threadfence_system();
+      st_release_sys(out.gflags[threadIdx.x] + out.rank, out.flag_value);
+    }
+    return;
+  }
   constexpr int kChildren = D == 3 ? 64 : 256;
+  constexpr int kSubs = 256 / kChildren;               // lanes per child
+  extern __shared__ __align__(16) unsigned char s_build[];
+  const int cap = K < kCoarseListCap ? K : kCoarseListCap;
+  float4* s_cf = reinterpret_cast<float4*>(s_build);                                // [cap] fp32 keys of the list
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_cf + cap);           // [1 + cap]: count, ids
+  unsigned short* s_ids = s_list + ((cap + 1 + 7) & ~7);                            // [kChildren][32]
   const int G = hdr->G, Gc = G / 4;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n_cells) {
-    const int64_t parent = parent0 + t / kChildren;
-    int child = (int)(t % kChildren);
-    double lo[D], hi[D];
-    int64_t pr = parent, cell = 0, mul = 1;
+  const int lane = threadIdx.x & 31;
+  const int64_t parent = coarse0 + blockIdx.x;
+  float org[D], cel[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) { org[k] = (float)hdr->origin[k]; cel[k] = (float)hdr->cell[k]; }
+  // boxes in fp32, widened by kBoxEps of a cell (query rounding) + 1e-5 of a cell (their own rounding)
+  constexpr float kEps = (float)kBoxEps + 1e-5f;
+  // (a) coarse box -> s_list, s_cf
+  {
+    float lo[D], hi[D];
+    int64_t pr = parent;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const int ck = 4 * (int)(pr % Gc) + (child & 3);
+      const int ck = (int)(pr % Gc);
       pr /= Gc;
-      child >>= 2;
-      const double eps = kBoxEps * hdr->cell[k];
-      lo[k] = hdr->origin[k] + (double)ck * hdr->cell[k] - eps;
-      hi[k] = hdr->origin[k] + (double)(ck + 1) * hdr->cell[k] + eps;
-      cell += (int64_t)ck * mul;
-      mul *= G;
+      lo[k] = fmaf((float)(4 * ck) - kEps, cel[k], org[k]) - 1e-6f * fabsf(org[k]);
+      hi[k] = fmaf((float)(4 * ck + 4) + kEps, cel[k], org[k]) + 1e-6f * fabsf(org[k]);
     }
-    const unsigned short* prec = coarse + parent * (kCoarseCap + 1);
-    const unsigned pc = prec[0];
-    const bool all = pc == kGridOverflow;
-    const int n_src = all ? K : (int)pc;
-    double u = INFINITY;
-    int piv = 0;
-    for (int j = 0; j < n_src; ++j) {
-      const int k = all ? j : (int)prec[1 + j];
-      double mn, mx;
-      box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-      if (mx < u) { u = mx; piv = k; }
-    }
-    const double thr = u * (1.0 + 1e-9) + 1e-300;
-    double cp[D];
+    coarse_filter_f32<D>(cf32, K, lo, hi, s_list, s_cf, cap);   // ends with __syncthreads()
+  }
+  const int n_all = (int)s_list[0];
+  const bool too_long = n_all > cap;                   // never seen; the children then take the scan
+  const int n_src = too_long ? 0 : n_all;
+  // (b) fine children
+  const int child = threadIdx.x / kSubs, sub = threadIdx.x % kSubs;
+  float lo[D], hi[D];
+  int64_t pr = parent, cell = 0, mul = 1;
+  int ch = child;
 #pragma unroll
-    for (int k = 0; k < D; ++k) cp[k] = __ldg(centers + (int64_t)piv * D + k);
-    unsigned long long w0 = 0ull, w1 = 0ull;       // halfwords h0..h3, h4..h7
-    unsigned short* srec = nullptr;               // this cell's side record in the LOCAL grid
-    bool overflow = false;
-    int cnt = 0;
-    for (int j = 0; j < n_src; ++j) {
-      const int k = all ? j : (int)prec[1 + j];
-      double mn, mx, sc;
-      box_bounds<D>(centers + (int64_t)k * D, lo, hi, mn, mx);
-      const double bm = bisector_min<D>(centers + (int64_t)k * D, cp, lo, hi, sc);
-      if (mn <= thr && bm <= 1e-9 * sc) {           // ascending key order
-        const int e = cnt + 1;                      // 1-based entry
-        if (e <= kFineInline) {
-          if (e < 4) w0 |= (unsigned long long)k << (16 * e);
-          else w1 |= (unsigned long long)k << (16 * (e - 4));
-        } else {
-          if (e == kFineInline + 1) {
-            // the 8th key: open a side record; key 7 moves there and its place takes the slot
-            const unsigned sl = atomicAdd(&hdr->side_next, 1u);
-            if (sl < out.side_per_rank) {
-              const unsigned slot = (unsigned)out.rank * out.side_per_rank + sl;
-              srec = out.side[out.rank] + (size_t)slot * kSideWidth;
-              srec[0] = (unsigned short)(w1 >> 48);
-              w1 = (w1 & 0x0000FFFFFFFFFFFFull) | ((unsigned long long)slot << 48);
-            } else {
-              overflow = true;
-            }
-          }
-          if (srec != nullptr && e <= kGridCap) srec[e - kFineInline] = (unsigned short)k;
-        }
-        ++cnt;
+  for (int k = 0; k < D; ++k) {
+    const int ck = 4 * (int)(pr % Gc) + (ch & 3);
+    pr /= Gc;
+    ch >>= 2;
+    lo[k] = fmaf((float)ck - kEps, cel[k], org[k]) - 1e-6f * fabsf(org[k]);
+    hi[k] = fmaf((float)(ck + 1) + kEps, cel[k], org[k]) + 1e-6f * fabsf(org[k]);
+    cell += (int64_t)ck * mul;
+    mul *= G;
+  }
+  float u = INFINITY;
+  int pj = 0x7fffffff;                                  // pivot: position in the list
+  for (int j = sub; j < n_src; j += kSubs) {
+    const float4 c4 = s_cf[j];
+    const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+    float mx = 0.f;
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      const float far = fmaxf(fabsf(c[q] - lo[q]), fabsf(hi[q] - c[q]));
+      mx = fmaf(far, far, mx);
+    }
+    if (mx < u) { u = mx; pj = j; }
+  }
+#pragma unroll
+  for (int o = kSubs / 2; o > 0; o >>= 1) {
+    const float ou = __shfl_xor_sync(BDP_FULL_MASK, u, o);
+    const int op = __shfl_xor_sync(BDP_FULL_MASK, pj, o);
+    if (ou < u || (ou == u && op < pj)) { u = ou; pj = op; }
+  }
+  if (pj == 0x7fffffff) pj = 0;
+  const float thr = u * (1.f + 1e-5f) + 1e-5f;
+  const float4 p4 = n_src > 0 ? s_cf[pj] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float cp[4] = {p4.x, p4.y, p4.z, p4.w};
+  float np = 0.f;
+#pragma unroll
+  for (int q = 0; q < D; ++q) np = fmaf(cp[q], cp[q], np);
+  unsigned short* ids = s_ids + child * kSideWidth;
+  int cnt = 0;
+  for (int j0 = 0; j0 < n_src; j0 += kSubs) {           // block-uniform trip count: ballots are safe
+    const int j = j0 + sub;
+    bool keep = false;
+    if (j < n_src) {
+      const float4 c4 = s_cf[j];
+      const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+      float mn = 0.f, f = 0.f, nk = 0.f;
+#pragma unroll
+      for (int q = 0; q < D; ++q) {
+        const float near = fmaxf(fmaxf(lo[q] - c[q], c[q] - hi[q]), 0.f);
+        mn = fmaf(near, near, mn);
+        const float dlt = c[q] - cp[q];
+        f = fmaf(-2.f * dlt, dlt > 0.f ? hi[q] : lo[q], f);
+        nk = fmaf(c[q], c[q], nk);
+      }
+      // fp32 rounding of f is < 2e-5 here (|c| < 4, keys within ~2 of the cell): 2e-5 (1 + nk + np)
+      keep = mn <= thr && f + (nk - np) <= 2e-5f * (1.f + nk + np);
+    }
+    const unsigned m = __ballot_sync(BDP_FULL_MASK, keep);
+    const unsigned gm = (m >> (lane & ~(kSubs - 1))) & ((1u << kSubs) - 1u);   // this child's lanes
+    const int pos = cnt + __popc(gm & ((1u << sub) - 1u));
+    if (keep && pos < kSideWidth - 1) ids[pos] = s_list[1 + j];                // ascending key order
+    cnt += __popc(gm);
+  }
+  __syncwarp();
+  if (sub == 0) {
+    unsigned long long w0 = 0ull, w1 = 0ull;            // halfwords h0..h3, h4..h7
+    const unsigned short* srec = nullptr;               // this cell's side record in the LOCAL grid
+    bool overflow = cnt > kGridCap || too_long;
+    const int n_inline = cnt <= kFineInline ? cnt : kFineInline - 1;
+    for (int e = 1; e <= n_inline && !overflow; ++e) {
+      const unsigned long long id = ids[e - 1];
+      if (e < 4) w0 |= id << (16 * e);
+      else w1 |= id << (16 * (e - 4));
+    }
+    if (!overflow && cnt > kFineInline) {
+      // long list: keys 1..6 inline, h7 = slot of a side record with keys 7..cnt
+      const unsigned sl = atomicAdd(&hdr->side_next, 1u);
+      if (sl < out.side_per_rank) {
+        const unsigned slot = (unsigned)out.rank * out.side_per_rank + sl;
+        unsigned short* dst = out.side[out.rank] + (size_t)slot * kSideWidth;
+        for (int e = kFineInline; e <= cnt; ++e) dst[e - kFineInline] = ids[e - 1];
+        w1 |= (unsigned long long)slot << 48;
+        srec = dst;
+      } else {
+        overflow = true;
       }
     }
-    w0 |= (cnt > kGridCap || overflow) ? (unsigned long long)kGridOverflow : (unsigned long long)cnt;
+    w0 = (w0 & ~0xFFFFull) | (overflow ? (unsigned long long)kGridOverflow : (unsigned long long)cnt);
     const uint4 rec = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
 #pragma unroll
     for (int r = 0; r < BDP_KMEANS_MAX_RANKS; ++r)
@@ -707,9 +783,7 @@ int keygrid_check(const void* grid, int64_t grid_bytes, int K, int d, const char
   return BDP_OK;
 }
 
-// layout: [GridHdr][fine records 16 B][side records 64 B][coarse records][super records]
-int64_t keygrid_super_cells(int G, int d) { return ipow64((G / 4 + 3) / 4, d); }
-
+// layout: [GridHdr][fine records 16 B][side records 64 B][fp32 copy of the keys, float4 x kGridMaxK]
 // side records of a grid: one per 8 fine cells (3 % of the cells have lists longer than 7 keys),
 // at most 65535 (the slot is a halfword of the cell record), divisible among up to 8 ranks
 int64_t keygrid_side_records(int64_t n_fine) {
@@ -723,8 +797,7 @@ struct GridPtrs {
   GridHdr* hdr;
   uint4* fine;
   unsigned short* side;
-  unsigned short* coarse;
-  unsigned short* super;
+  float4* cf32;
   int G;
   int64_t n_fine, n_coarse, n_side;
 };
@@ -739,8 +812,7 @@ GridPtrs keygrid_pointers(const void* grid, int K, int d) {
   g.hdr = reinterpret_cast<GridHdr*>(b);
   g.fine = reinterpret_cast<uint4*>(b + sizeof(GridHdr));
   g.side = reinterpret_cast<unsigned short*>(g.fine + g.n_fine);
-  g.coarse = g.side + g.n_side * kSideWidth;
-  g.super = g.coarse + g.n_coarse * (kCoarseCap + 1);
+  g.cf32 = reinterpret_cast<float4*>(g.side + g.n_side * kSideWidth);
   return g;
 }
 
@@ -1072,15 +1144,15 @@ extern "C" int bdp_convert_axis_angle(const double* aa, int64_t N, double* rotma
 extern "C" int64_t bdp_keygrid_bytes(int K, int d) {
   if ((d != 3 && d != 4) || K < 1 || K > kGridMaxK) return -1;
   const int G = keygrid_G(K, d);
-  const int64_t n_coarse = ipow64(G / 4, d), n_fine = ipow64(G, d);
+  const int64_t n_fine = ipow64(G, d);
   return (int64_t)sizeof(GridHdr) + n_fine * 16 + keygrid_side_records(n_fine) * kSideWidth * 2 +
-         n_coarse * (kCoarseCap + 1) * 2 + keygrid_super_cells(G, d) * (K + 1) * 2;
+         (int64_t)kGridMaxK * 16;
 }
 
 // Build for `centers`.  peers == NULL (or one rank): the whole grid, locally.  Several ranks: every
-// rank derives the same geometry, builds the hierarchy of ITS slab only (whole layers of coarse cells
-// along the last axis — the levels of a slab depend on nothing outside it) and stores its fine / side
-// records into every rank's grid; the query waits for all slabs (gflags).
+// rank derives the same grid geometry, builds the coarse cells of ITS slab only (whole layers along
+// the last axis) and stores their fine / side records into every rank's grid; the query waits for all
+// slabs (gflags).
 int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
                        const int* stop, const bdpi_grid_peers* peers, cudaStream_t st) {
   BDP_REQUIRE(centers != nullptr, "keygrid_build: NULL centers");
@@ -1088,7 +1160,7 @@ int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t 
   int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_build");
   if (rc != BDP_OK) return rc;
   const GridPtrs g = keygrid_pointers(grid, K, d);
-  const int G = g.G, Gc = G / 4, Gs = (Gc + 3) / 4;
+  const int G = g.G, Gc = G / 4;
   const double r = pow((double)K, 1.0 / d);
   const double margin_frac = r > 2.0 ? 1.0 / r : 0.5;
   const int world = (peers && peers->world > 1) ? peers->world : 1;
@@ -1101,35 +1173,26 @@ int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t 
   out.side_per_rank = (unsigned)(g.n_side / world);
   out.flag_value = world > 1 ? peers->flag_value : 0ull;
   for (int q = 0; q < world; ++q) {
+    BDP_REQUIRE(world == 1 || (peers->grid[q] != nullptr && peers->gflags[q] != nullptr),
+                "keygrid_build: buffers of rank %d are NULL", q);
     const GridPtrs gq = keygrid_pointers(world > 1 ? peers->grid[q] : grid, K, d);
-    BDP_REQUIRE(world == 1 || peers->grid[q] != nullptr, "keygrid_build: grid of rank %d is NULL", q);
     out.fine[q] = gq.fine; out.side[q] = gq.side;
     out.gflags[q] = world > 1 ? peers->gflags[q] : nullptr;
   }
-  const int sms = bdp_num_sms();
-  const int64_t layer_c = ipow64(Gc, d - 1), layer_s = ipow64(Gs, d - 1);
-  const int64_t coarse0 = zc0 * layer_c, coarse1 = zc1 * layer_c;
-  const int zs0 = zc0 / 4, zs1 = zc1 > zc0 ? (zc1 - 1) / 4 + 1 : zs0;
-  const int64_t super0 = zc1 > zc0 ? zs0 * layer_s : 0;    // an empty slab still publishes the header
-  // every rank launches at least one super block: block 0 of the launch publishes the header
-  const unsigned n_super = (unsigned)((zs1 - zs0) * layer_s > 0 ? (zs1 - zs0) * layer_s : 1);
-  const int64_t n_coarse = coarse1 - coarse0;
-  const int64_t children = d == 3 ? 64 : 256;
-  const int64_t n_cells = n_coarse * children;
-  auto blocks_for = [&](int64_t cells) {
-    int64_t b = ceil_div64(cells, 8);                  // 8 warps per block, one cell per warp
-    const int64_t cap = (int64_t)sms * 8;
-    return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
-  };
-  const unsigned fine_blocks = (unsigned)(n_cells > 0 ? ceil_div64(n_cells, 256) : 1);
+  const int64_t layer_c = ipow64(Gc, d - 1);
+  const int64_t coarse0 = zc0 * layer_c, n_coarse = (zc1 - zc0) * layer_c;
+  const int cap = K < kCoarseListCap ? K : kCoarseListCap;
+  const size_t smem = (size_t)cap * 16 + (size_t)(((cap + 1 + 7) & ~7) + (d == 3 ? 64 : 256) * kSideWidth) * 2;
+  const unsigned blocks = (unsigned)(n_coarse > 0 ? n_coarse : 1);
+  const int active = n_coarse > 0 ? 1 : 0;
   if (d == 3) {
-    keygrid_super_kernel<3><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.super, (int)super0, stop);
-    keygrid_coarse_kernel<3><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, g.hdr, g.super, g.coarse, coarse0, coarse1, stop);
-    keygrid_fine_kernel<3><<<fine_blocks, 256, 0, st>>>(centers, K, g.hdr, g.coarse, out, coarse0, n_cells, stop);
+    keygrid_header_kernel<3><<<1, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.cf32, stop);
+    if (active || world > 1)
+      keygrid_cell_kernel<3><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, active, stop);
   } else {
-    keygrid_super_kernel<4><<<n_super, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.super, (int)super0, stop);
-    keygrid_coarse_kernel<4><<<blocks_for(n_coarse), 256, 0, st>>>(centers, K, g.hdr, g.super, g.coarse, coarse0, coarse1, stop);
-    keygrid_fine_kernel<4><<<fine_blocks, 256, 0, st>>>(centers, K, g.hdr, g.coarse, out, coarse0, n_cells, stop);
+    keygrid_header_kernel<4><<<1, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.cf32, stop);
+    if (active || world > 1)
+      keygrid_cell_kernel<4><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, active, stop);
   }
   BDP_CUDA_CHECK_LAUNCH("keygrid kernels");
   return BDP_OK;

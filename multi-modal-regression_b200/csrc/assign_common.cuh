@@ -67,7 +67,6 @@ struct AssignParams {
 constexpr int kFineInline = 7;
 constexpr int kSideWidth = 32;               // halfwords per side record
 constexpr int kGridCap = 31;                 // ids per fine record  (u16 count + 31 u16 ids = 64 B)
-constexpr int kCoarseCap = 255;              // ids per coarse record (512 B)
 constexpr int kGridMaxK = 4096;              // fp32 screening records of the whole dictionary in smem
 constexpr unsigned kGridOverflow = 0xFFFFu;
 // Cell boxes are grown by this fraction of a cell on every side before the bounds are taken, which

@@ -117,10 +117,12 @@ __device__ __forceinline__ double limbs_to_double(long long hi, long long lo, do
 __device__ __forceinline__ unsigned long long xsum(const XfinParams& P, int w) {
   const size_t off = (size_t)P.parity * P.A + w;
   if (P.mc != nullptr) return multimem_add_u64(P.mc + off);
+  unsigned long long v[kMaxWorld];
+#pragma unroll
+  for (int r = 0; r < kMaxWorld; ++r) v[r] = r < P.world ? ld_relaxed_sys(P.xchg[r] + off) : 0ull;
   unsigned long long s = 0ull;
 #pragma unroll
-  for (int r = 0; r < kMaxWorld; ++r)
-    if (r < P.world) s += ld_relaxed_sys(P.xchg[r] + off);
+  for (int r = 0; r < kMaxWorld; ++r) s += v[r];
   return s;
 }
 
@@ -155,9 +157,31 @@ __global__ void __launch_bounds__(kXfThreads) kmeans_xfin_kernel(const XfinParam
   long long cnt = -1;
   int empty = 0;
   if (j < P.K) {
+    // all loads of the cluster's words from all ranks are issued before the first one is consumed:
+    // a dependent add after every load would serialise 8 x (2d+1) NVLink round trips (~2 us each)
     unsigned long long a[W];
+    if (P.mc != nullptr) {
 #pragma unroll
-    for (int w = 0; w < W; ++w) a[w] = xsum(P, j * W + w);
+      for (int w = 0; w < W; ++w) a[w] = multimem_add_u64(P.mc + (size_t)P.parity * P.A + j * W + w);
+    } else {
+      unsigned long long v[kMaxWorld][W];
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r) {
+        if (r < P.world) {
+#pragma unroll
+          for (int w = 0; w < W; ++w) v[r][w] = ld_relaxed_sys(P.xchg[r] + (size_t)P.parity * P.A + j * W + w);
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < W; ++w) a[w] = 0ull;
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r) {
+        if (r < P.world) {
+#pragma unroll
+          for (int w = 0; w < W; ++w) a[w] += v[r][w];
+        }
+      }
+    }
     cnt = (long long)a[2 * D];
     ctl->cnt[j] = cnt;
     double sh = 0.0;
@@ -348,6 +372,11 @@ extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers
     double* c_cur = centers2 + (size_t)cur * K * d;
     double* c_new = centers2 + (size_t)(cur ^ 1) * K * d;
     int64_t* acc = reinterpret_cast<int64_t*>(xchg[rank]) + (size_t)cur * A;
+    auto mark = [&](int k) -> int {                 // benchmark instrumentation: 4 events per iteration
+      if (em_events) BDP_CUDA_CALL(cudaEventRecord(reinterpret_cast<cudaEvent_t>(em_events[4 * it + k]), st));
+      return BDP_OK;
+    };
+    if ((rc = mark(0)) != BDP_OK) return rc;
     if (grid) {
       // (a rank without rows still builds its slab: the peers' queries read it)
       gp.flag_value = (unsigned long long)(gi + 1);
@@ -355,13 +384,13 @@ extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers
         rc = bdpi_keygrid_build(c_cur, K, d, grid, grid_bytes, stop, shard ? &gp : nullptr, st);
         if (rc != BDP_OK) return rc;
       }
+      if ((rc = mark(1)) != BDP_OK) return rc;
       if (N > 0) {
-        if (em_events) BDP_CUDA_CALL(cudaEventRecord(reinterpret_cast<cudaEvent_t>(em_events[2 * it]), st));
         rc = bdpi_lloyd_step_grid(x, N, d, c_cur, K, grid, grid_bytes, labels, acc, fix_hi_bits,
                                   acc + A - 2, nullptr, 1, stop, shard ? gp.gflags[rank] : nullptr,
                                   world, gp.flag_value, incremental, st);
-        if (em_events) BDP_CUDA_CALL(cudaEventRecord(reinterpret_cast<cudaEvent_t>(em_events[2 * it + 1]), st));
       }
+      if (rc == BDP_OK) rc = mark(2);
     } else if (N > 0) {
       BDP_REQUIRE(!incremental, "kmeans_run: the incremental M-step needs the key grid");
       rc = bdpi_lloyd_step(x, N, d, c_cur, K, labels, acc, fix_hi_bits, acc + A - 2, nullptr, 1,
@@ -371,6 +400,7 @@ extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers
     rc = bdp_kmeans_exchange_finalize(xchg, xchg_multicast, world, rank, K, d, fix_hi_bits, cur,
                                       gi + 1, check, incremental, tol_abs, c_cur, c_new, ctl, stream);
     if (rc != BDP_OK) return rc;
+    if ((rc = mark(3)) != BDP_OK) return rc;
   }
   return BDP_OK;
 }

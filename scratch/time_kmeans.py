@@ -17,7 +17,7 @@ grid = ops.KeyGrid(fs.centers)
 loop = kmeans.LloydLoop(fs.x, fs.centers, labels, fs.hb, grid, kmeans.LOCAL, fs.tol_abs)
 steps = 20
 for rep in range(2):
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4 * steps)]
     for e in evs:
         e.record()
     loop.reset(fs.centers)
@@ -27,7 +27,9 @@ for rep in range(2):
     loop.launch(0, steps, False, em_events=evs)
     e1.record()
     torch.cuda.synchronize()
-em = [evs[2 * i].elapsed_time(evs[2 * i + 1]) * 1e3 for i in range(steps)]
+em = [evs[4 * i + 1].elapsed_time(evs[4 * i + 2]) * 1e3 for i in range(steps)]
+print('  build us', ' '.join('%.0f' % (evs[4*i].elapsed_time(evs[4*i+1])*1e3) for i in range(steps)))
+print('  xfin  us', ' '.join('%.0f' % (evs[4*i+2].elapsed_time(evs[4*i+3])*1e3) for i in range(steps)))
 print("n=%d incremental=%s: loop %.1f us/iter; E+M kernel us per iteration: %s" % (
     n, loop.incremental, e0.elapsed_time(e1) * 1e3 / steps, " ".join("%.0f" % v for v in em)))
 print("  E+M mean %.1f us -> %.0f GB/s (28 B/rot)" % (sum(em) / steps, n * 28 / (sum(em) / steps) / 1e3))

@@ -80,10 +80,17 @@ def test_sharded_kmeans_equals_single_gpu():
     print("exchange modes:", modes)
     assert modes["nccl"] == "nccl"
     assert modes["converge"] in ("p2p", "nccl"), modes      # nccl only where symmetric memory is absent
+    bad = []
     for case in CASES:
         one = _fit(kmeans, X, 0, X.shape[0], case)
-        for p in parts:
-            assert p[case]["n_iter"] == one["n_iter"], case
-            assert torch.equal(p[case]["centers"], one["centers"].cpu()), case
-            assert p[case]["inertia"] == pytest.approx(one["inertia"], rel=1e-12), case
-        assert torch.equal(torch.cat([p[case]["labels"] for p in parts]), one["labels"].cpu()), case
+        for r, p in enumerate(parts):
+            if p[case]["n_iter"] != one["n_iter"]:
+                bad.append("%s: rank %d ran %d iterations, single GPU %d" % (case, r, p[case]["n_iter"], one["n_iter"]))
+            elif not torch.equal(p[case]["centers"], one["centers"].cpu()):
+                bad.append("%s: centres of rank %d differ (max %.3e)" % (
+                    case, r, float((p[case]["centers"] - one["centers"].cpu()).abs().max())))
+            elif p[case]["inertia"] != pytest.approx(one["inertia"], rel=1e-12):
+                bad.append("%s: inertia of rank %d" % (case, r))
+        if not torch.equal(torch.cat([p[case]["labels"] for p in parts]), one["labels"].cpu()):
+            bad.append("%s: labels differ" % case)
+    assert not bad, bad

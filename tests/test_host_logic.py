@@ -12,10 +12,9 @@ import torch
 def test_keygrid_sizes_and_errors():
     from bdpose import _lib
     lib = _lib.lib()
-    # 64^3 fine records of 16 B + 64^3 / 8 side records of 64 B + 16^3 coarse records of 512 B +
-    # 64 super records + header
+    # header + 64^3 fine records of 16 B + 64^3 / 8 side records of 64 B + fp32 copy of up to 4096 keys
     b = lib.bdp_keygrid_bytes(1000, 3)
-    assert b == 160 + 64 ** 3 * 16 + (64 ** 3 // 8) * 64 + 16 ** 3 * 512 + 4 ** 3 * 1001 * 2
+    assert b == 160 + 64 ** 3 * 16 + (64 ** 3 // 8) * 64 + 4096 * 16
     assert lib.bdp_keygrid_bytes(16, 3) < lib.bdp_keygrid_bytes(200, 3) < b
     assert lib.bdp_keygrid_bytes(200, 4) > 0
     assert lib.bdp_keygrid_bytes(5000, 3) == -1 and lib.bdp_keygrid_bytes(100, 5) == -1
