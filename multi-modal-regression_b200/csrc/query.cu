@@ -86,20 +86,27 @@ template <typename T, int D> struct Geo {
   static constexpr int RV = PTS * D * 4 / 8;                    // 64-bit words of residuals per lane
 };
 
+// Shared chunk accumulators of a block, per cluster: 4 x D counters of 16-bit chunks of the two
+// fixed-point limbs (hi biased by 2^31), the number of operations (to remove the bias) and the SIGNED
+// net member count (a rotation that leaves a cluster is added as the negated two-limb number).
+template <int D> struct AccLayout { static constexpr int W = 4 * D + 2; };
+
 template <int D, int kQThreads>
 __device__ __forceinline__ void flush_acc(unsigned* s_acc32, int K, unsigned long long* acc) {
+  constexpr int W = AccLayout<D>::W;
   __syncthreads();
   for (int idx = threadIdx.x; idx < K * (D + 1); idx += kQThreads) {
     const int j = idx / (D + 1), k = idx % (D + 1);
-    const unsigned* a = s_acc32 + (size_t)j * (4 * D + 1);
-    const unsigned cnt = a[4 * D];
-    if (cnt == 0u) continue;
+    const unsigned* a = s_acc32 + (size_t)j * W;
+    const unsigned nb = a[4 * D];
+    if (nb == 0u) continue;
     unsigned long long* g = acc + (size_t)j * (2 * D + 1);
     if (k == D) {
-      atomicAdd(g + 2 * D, (unsigned long long)cnt);
+      const long long members = (long long)(int)a[4 * D + 1];
+      if (members) atomicAdd(g + 2 * D, (unsigned long long)members);
     } else {
       const long long hi = (long long)a[4 * k] + ((long long)a[4 * k + 1] << 16) -
-                           (long long)cnt * 2147483648LL;          // remove the +2^31 bias
+                           (long long)nb * 2147483648LL;           // remove the +2^31 bias
       const unsigned long long lo = (unsigned long long)a[4 * k + 2] +
                                     ((unsigned long long)a[4 * k + 3] << 16);
       if (hi) atomicAdd(g + 2 * k, (unsigned long long)hi);
@@ -107,42 +114,59 @@ __device__ __forceinline__ void flush_acc(unsigned* s_acc32, int K, unsigned lon
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * (4 * D + 1); i += kQThreads) s_acc32[i] = 0u;
+  for (int i = threadIdx.x; i < K * W; i += kQThreads) s_acc32[i] = 0u;
   __syncthreads();
 }
 
 // M-step contribution of ONE rotation (kept out of line: after the first iterations few rotations
-// move, and the hot loop keeps its registers): subtract it from cluster `from` (>= 0: incremental
-// mode, global 64-bit atomics — rare) and add it to cluster `to` (shared 32-bit chunk counters, or
-// global atomics for dictionaries too large for shared memory).
+// move, and the hot loop keeps its registers): take it out of cluster `from` (>= 0: incremental mode)
+// and add it to cluster `to` — shared 32-bit chunk counters, or global 64-bit atomics for dictionaries
+// too large for shared memory.  Leaving a cluster = adding the NEGATED two-limb number
+// (-(hi 2^32 + lo) = (-hi - [lo != 0]) 2^32 + (2^32 - lo) mod 2^32), so one code path serves both.
+template <int D>
+__device__ __forceinline__ void acc_one(long long hi, unsigned lo, unsigned member, int k,
+                                        unsigned* a) {
+  const unsigned ub = (unsigned)(hi + 2147483648LL);      // |hi| < 2^30 by the choice of the scale
+  atomicAdd(a + 4 * k, ub & 0xFFFFu);
+  atomicAdd(a + 4 * k + 1, ub >> 16);
+  atomicAdd(a + 4 * k + 2, lo & 0xFFFFu);
+  atomicAdd(a + 4 * k + 3, lo >> 16);
+  (void)member;
+}
+
 template <int D>
 __device__ __noinline__ void lloyd_move(const double* x, int to, int from, double scale_hi,
                                         unsigned* s_acc32, unsigned long long* acc) {
+  constexpr int W = AccLayout<D>::W;
   long long hi[D], lw[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) to_limbs(x[k], scale_hi, hi[k], lw[k]);
-  if (from >= 0) {
-    unsigned long long* a = acc + (size_t)from * (2 * D + 1);
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      atomicAdd(a + 2 * k, (unsigned long long)(-hi[k]));
-      atomicAdd(a + 2 * k + 1, (unsigned long long)(-lw[k]));
-    }
-    atomicAdd(a + 2 * D, ~0ull);                            // count - 1
-  }
   if (s_acc32 != nullptr) {
-    unsigned* a = s_acc32 + (size_t)to * (4 * D + 1);
+    unsigned* a = s_acc32 + (size_t)to * W;
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-      const unsigned ub = (unsigned)(hi[k] + 2147483648LL);  // hi in [-2^31, 2^31)
-      const unsigned ul = (unsigned)lw[k];
-      atomicAdd(a + 4 * k, ub & 0xFFFFu);
-      atomicAdd(a + 4 * k + 1, ub >> 16);
-      atomicAdd(a + 4 * k + 2, ul & 0xFFFFu);
-      atomicAdd(a + 4 * k + 3, ul >> 16);
-    }
+    for (int k = 0; k < D; ++k) acc_one<D>(hi[k], (unsigned)lw[k], 1u, k, a);
     atomicAdd(a + 4 * D, 1u);
+    atomicAdd(a + 4 * D + 1, 1u);
+    if (from >= 0) {
+      unsigned* b = s_acc32 + (size_t)from * W;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const unsigned lo = (unsigned)lw[k];
+        acc_one<D>(-hi[k] - (lo != 0u ? 1 : 0), 0u - lo, 0u, k, b);
+      }
+      atomicAdd(b + 4 * D, 1u);
+      atomicAdd(b + 4 * D + 1, 0xFFFFFFFFu);             // member count - 1
+    }
   } else {
+    if (from >= 0) {
+      unsigned long long* a = acc + (size_t)from * (2 * D + 1);
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        atomicAdd(a + 2 * k, (unsigned long long)(-hi[k]));
+        atomicAdd(a + 2 * k + 1, (unsigned long long)(-lw[k]));
+      }
+      atomicAdd(a + 2 * D, ~0ull);                        // count - 1
+    }
     unsigned long long* a = acc + (size_t)to * (2 * D + 1);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -173,7 +197,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
   float* s_cn = reinterpret_cast<float*>(sp); sp += (D == 4 ? a16((size_t)K * 4) : 0);
   double* s_cd = reinterpret_cast<double*>(sp); sp += C.cd_smem ? a16((size_t)K * D * 8) : 0;
   unsigned* s_acc32 = reinterpret_cast<unsigned*>(sp);
-  sp += (LLOYD && C.acc_smem) ? a16((size_t)K * (4 * D + 1) * 4) : 0;
+  sp += (LLOYD && C.acc_smem) ? a16((size_t)K * (4 * D + 2) * 4) : 0;
   constexpr int LB_IN = LLOYD ? WPTS * 4 : 0;                           // previous labels in
   constexpr int LB_OUT = WPTS * ((!LLOYD && LAB64) ? 8 : 4);            // labels out
   constexpr int RB_OUT = LLOYD ? 0 : RB;
@@ -186,7 +210,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
 
   const bool acc_in_smem = LLOYD && P.update && C.acc_smem;
   if (LLOYD && C.acc_smem) {
-    for (int i = threadIdx.x; i < K * (4 * D + 1); i += kQThreads) s_acc32[i] = 0u;
+    for (int i = threadIdx.x; i < K * (4 * D + 2); i += kQThreads) s_acc32[i] = 0u;
   }
   // stage the fp32 screening records (+ fp64 keys) of the whole dictionary, max ||c||^2 for the bound
   float cmax2 = 0.f;
@@ -573,7 +597,7 @@ int launch_query_nt(const AssignParams& P, cudaStream_t st) {
   const size_t lim = 227 * 1024 - 2048;                     // static shared memory + margin
   const size_t rec = (size_t)K * 16 + (D == 4 ? a16((size_t)K * 4) : 0);
   const size_t cd = a16((size_t)K * D * 8);
-  const size_t acc = a16((size_t)K * (4 * D + 1) * 4);
+  const size_t acc = a16((size_t)K * (4 * D + 2) * 4);
   const int lb_in = LLOYD ? G_::WPTS * 4 : 0;
   const int lb_out = G_::WPTS * ((!LLOYD && LAB64) ? 8 : 4);
   const int rb_out = LLOYD ? 0 : G_::RB;
