@@ -48,6 +48,12 @@ WORKLOAD = ("configs[2]: k-means pose-dictionary learning, 10M random rotations 
             "explicit init = first K rotations, fixed Lloyd iterations, strong scaling")
 
 
+def bench_config(steps):
+    """The workload both arms (this one and --impl reference) run: identical on both lines."""
+    return {"workload": WORKLOAD, "n_rotations_total": N_ROT, "K": K_DICT, "x_dtype": "f64",
+            "init": "first K rotations (explicit)", "iterations_timed": steps}
+
+
 def synth_rotations(n, seed, device, dtype=torch.float32):
     """Uniform rotations on SO(3) as axis-angle [n,3]."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -218,7 +224,7 @@ def run_reference(args, rank, world):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_rotations_total": N_ROT, "K": K_DICT, "x_dtype": "f64"},
+            "config": bench_config(args.steps),
             "cpu_baseline": {"value": rate, "unit": "rotation-iterations/s", "cores": cores,
                              "kind": "reference", "sample": sample},
             "e2e": {"value": rate, "unit": "rotation-iterations/s", "h2d_bytes_per_step": 0,
@@ -501,6 +507,7 @@ def main():
     def e2e_fit():
         km = kmeans.KMeans(n_clusters=K_DICT, init=init_np, n_init=1, max_iter=steps, fixed_iters=steps,
                            group=grp, device=dev)
+        km.copy_labels = False           # labels_ stays in the pinned host buffer the D2H copy filled
         km.fit(x_host)
         return km
     e2e_fit()
@@ -548,14 +555,15 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 (f32 screen of the candidate keys, f64 exact re-check; int64 fixed-point sums)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_rotations_total": N_ROT, "K": K_DICT, "x_dtype": "f64",
-                       "n_rotations_per_gpu": n_local,
-                       "l2": "shard per GPU = %d MB fp64 + %d MB labels; > 126 MB L2 at 1-2 GPUs, L2-resident "
-                             "across iterations at 4-8 GPUs as in any real fit (no flush in the timed loop; "
-                             "ms_per_step_l2_flushed re-times the iterations one by one with a 256 MB write "
-                             "in between)" % (n_local * 24 // 1_000_000, n_local * 4 // 1_000_000),
-                       "algorithm": "key grid (candidate pruning) rebuilt every iteration; exact int64 "
-                                    "fixed-point cluster sums; exchange " + parity["exchange"]},
+            "config": bench_config(steps),
+            "notes": {"n_rotations_per_gpu": n_local,
+                      "l2": "shard per GPU = %d MB fp64 + %d MB labels; > 126 MB L2 at 1-2 GPUs, L2-resident "
+                            "across iterations at 4-8 GPUs as in any real fit (no flush in the timed loop; "
+                            "ms_per_step_l2_flushed re-times the iterations one by one with a 256 MB write "
+                            "in between)" % (n_local * 24 // 1_000_000, n_local * 4 // 1_000_000),
+                      "algorithm": "key grid (candidate pruning) rebuilt every iteration, sharded over the "
+                                   "ranks; exact int64 fixed-point cluster sums, incremental M-step; "
+                                   "exchange " + parity["exchange"]},
             "ms_per_step_l2_flushed": ms_step_flushed,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "rotation-iterations/s", "ms_per_fit": float(ms_e2e),

@@ -424,11 +424,20 @@ class _AccView:
         self.shift2 = self.n_empty = None
 
 
+def _fit_stats(x, mode, out, mean=None, scale=1.0, y=None):
+    N, d = x.shape
+    with torch.cuda.device(x.device):
+        st = L.lib().bdp_fit_stats(x.data_ptr(), N, d, mode, L.ptr(mean), float(scale), L.ptr(y),
+                                   out.data_ptr(), L.stream_ptr())
+    L.check(st, "bdp_fit_stats")
+
+
 class FitSetup:
     """What scikit-learn's `fit` does before the first Lloyd iteration, for this rank's shard:
     global mean / variance (X -= X.mean(0); tol = mean(var(X)) * tol) summed in fixed point — integer
-    sums do not depend on how the rows are split over ranks, so the centred data, and with them every
-    label and centre, are bit-identical for any world size."""
+    sums do not depend on how the rows are split over blocks or ranks, so the centred data, and with
+    them every label and centre, are bit-identical for any world size.  Four passes over the shard
+    (bdp_fit_stats: max |x|, two-limb column sums, centring + maxima, variance sums)."""
 
     def __init__(self, x, init, group=None, tol=1e-4, center=True):
         import torch.distributed as dist
@@ -442,32 +451,62 @@ class FitSetup:
                 dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=group)
             return t
         MAXOP = dist.ReduceOp.MAX if distributed else None
+        use_kernels = x.is_cuda and 1 <= d <= 8
+
+        def absmax(t):
+            if use_kernels:
+                o = torch.zeros(2, dtype=torch.int64, device=dev)     # bit pattern of a double >= 0
+                _fit_stats(t, 0, o)
+                return o[:1]
+            return (t.abs().max().reshape(1) if t.numel() else t.new_zeros(1)).view(torch.int64)
         n_tot = allreduce(torch.tensor([N], dtype=torch.int64, device=dev)).double()
-        amax = float(allreduce(x.abs().max().reshape(1) if N else x.new_zeros(1), op=MAXOP))
+        # (non-negative doubles order like their bit patterns: the MAX all-reduce runs on int64)
+        amax = float(allreduce(absmax(x), op=MAXOP).view(torch.float64))
         hb0 = _fix_hi_bits(amax)
-        xs = x * float(2.0 ** hb0)
-        fl = torch.floor(xs)
-        limbs = torch.stack([fl.to(torch.int64).sum(0),
-                             torch.trunc((xs - fl) * 4294967296.0).to(torch.int64).sum(0)])
-        del xs, fl
+        if use_kernels:
+            limbs = torch.zeros(2 * d, dtype=torch.int64, device=dev)
+            _fit_stats(x, 1, limbs, scale=2.0 ** hb0)
+            limbs = limbs.view(2, d)
+        else:
+            xs = x * float(2.0 ** hb0)
+            fl = torch.floor(xs)
+            limbs = torch.stack([fl.to(torch.int64).sum(0),
+                                 torch.trunc((xs - fl) * 4294967296.0).to(torch.int64).sum(0)])
+            del xs, fl
         allreduce(limbs)
         mean = (limbs[0].double() * float(2.0 ** -hb0) + limbs[1].double() * float(2.0 ** -(hb0 + 32))) / n_tot
-        d2 = (x - mean) ** 2
-        d2max = float(allreduce(d2.max().reshape(1) if N else x.new_zeros(1), op=MAXOP))
+        if use_kernels:
+            xc = torch.empty_like(x)
+            mx = torch.zeros(2, dtype=torch.int64, device=dev)
+            _fit_stats(x, 2, mx, mean=mean.contiguous(), y=xc)
+            mx = allreduce(mx, op=MAXOP).view(torch.float64)
+            d2max, cmax = float(mx[0]), float(mx[1])
+        else:
+            xc = x - mean
+            d2 = xc ** 2
+            d2max = float(allreduce((d2.max().reshape(1) if N else x.new_zeros(1)).view(torch.int64),
+                                    op=MAXOP).view(torch.float64))
+            cmax = float(allreduce((xc.abs().max().reshape(1) if N else x.new_zeros(1)).view(torch.int64),
+                                   op=MAXOP).view(torch.float64))
         sh = 40 if d2max <= 0 else int(max(0, min(40, np.floor(61 - np.log2(d2max * float(n_tot) + 1.0)))))
-        q = allreduce(torch.round(d2 * float(2.0 ** sh)).to(torch.int64).sum(0))
-        del d2
+        if use_kernels:
+            q = torch.zeros(d, dtype=torch.int64, device=dev)
+            _fit_stats(xc, 3, q, scale=2.0 ** sh)
+        else:
+            q = torch.round(xc ** 2 * float(2.0 ** sh)).to(torch.int64).sum(0)
+        allreduce(q)
         var = q.double() * float(2.0 ** -sh) / n_tot
         self.tol_abs = float(var.mean()) * tol
         self.mean = mean
         self.center = center
         if center:
-            x = x - mean
+            x = xc
             centers = (init.double().to(dev) - mean).contiguous()
+            max_abs = cmax
         else:
             centers = init.double().to(dev).contiguous().clone()
-        max_abs = allreduce(x.abs().max().reshape(1) if N else x.new_zeros(1), op=MAXOP)
-        self.hb = _fix_hi_bits(float(max_abs))
+            max_abs = amax
+        self.hb = _fix_hi_bits(max_abs)
         self.x, self.centers = x, centers
         self.group, self.allreduce = group, allreduce
         self.distributed = distributed
@@ -576,6 +615,16 @@ def kmeans_plusplus(x, K, seed=0, n_local_trials=None):
     return centers
 
 
+_pinned = {}
+
+
+def _pinned_labels(n):
+    t = _pinned.get(n)
+    if t is None:
+        t = _pinned[n] = torch.empty(n, dtype=torch.int32).pin_memory()
+    return t
+
+
 class KMeans:
     """Drop-in for the pickled sklearn estimator the reference passes around
     (learnKmeansDictionary.py:41-47): exposes n_clusters, cluster_centers_ [K,d] float64 (numpy),
@@ -596,6 +645,7 @@ class KMeans:
         # to fit() (default: this process alone); `fixed_iters` = run exactly that many iterations
         self.group = group
         self.fixed_iters = fixed_iters
+        self.copy_labels = True       # False: labels_ is a view of a reused pinned buffer (benchmarks)
 
     def _dev(self):
         return torch.device(self.device) if self.device is not None else torch.device(
@@ -624,7 +674,13 @@ class KMeans:
             if best is None or r["inertia"] < best["inertia"]:
                 best = r
         self.cluster_centers_ = best["centers"].cpu().numpy()
-        self.labels_ = best["labels"].cpu().numpy()
+        # labels come back through a pinned staging buffer (kept per size: a 40 MB pageable D2H copy
+        # costs as much as the whole fit)
+        lab = best["labels"]
+        stage = _pinned_labels(lab.numel())
+        stage.copy_(lab, non_blocking=True)
+        torch.cuda.current_stream(lab.device).synchronize()
+        self.labels_ = stage.numpy().copy() if self.copy_labels else stage.numpy()
         self.inertia_ = best["inertia"]
         self.n_iter_ = best["n_iter"]
         return self
