@@ -261,7 +261,7 @@ def extras(dev, peaks, rank, world, args):
         "roofline": {"bound": "hbm", "kernel": "assign query kernel", "kernel_ms": ms_q,
                      "achieved": by / (ms_q * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                      "frac": by / (ms_q * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_launch": by,
-                     "traffic": profile_traffic("r2_ncu_assign.csv", "assign")}}
+                     "traffic": profile_traffic("r2_ncu_assign.csv", "query_kernel")}}
     if rank != 0:
         return out
     if world == 1:
@@ -577,7 +577,7 @@ def main():
             "gpu_launches": 5 * steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": profile_traffic("r2_ncu_lloyd.csv", "assign"),
+                         "traffic": profile_traffic("r2_ncu_lloyd.csv", "query_kernel"),
                          "peak_source": peak_src, "kernel": "Lloyd E+M kernel (assign query, fp64, accumulate)",
                          "kernel_ms": kernel_ms, "kernel_ms_first_iteration": em_ms[0],
                          "kernel_ms_last_iteration": em_ms[-1], "grid_build_ms_unsharded": build_ms,

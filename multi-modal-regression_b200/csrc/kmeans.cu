@@ -107,7 +107,7 @@ __device__ __forceinline__ double limbs_to_double(long long hi, long long lo, do
     unsigned long long kept = (unsigned long long)(m >> shift);
     const unsigned __int128 dropped = m & ((((unsigned __int128)1) << shift) - 1);
     if (dropped != 0) kept |= 1ull;                   // sticky bit, 11 bits below the double mantissa
-    r = __ull2double_rn(kept) * exp2((double)shift);
+    r = __ull2double_rn(kept) * __longlong_as_double((long long)(1023 + shift) << 52);   // * 2^shift
   }
   r *= inv_scale_lo;                                  // power of two: exact
   return neg ? -r : r;
@@ -236,13 +236,26 @@ __global__ void __launch_bounds__(kXfThreads) kmeans_xfin_kernel(const XfinParam
   if (!s_last) return;
   __threadfence();
   const volatile KmCtl* vc = ctl;
-  long long big_cnt = vc->p_cnt[0];
-  int big = vc->p_idx[0], n_empty = vc->p_empty[0];
-  for (int b = 1; b < (int)gridDim.x; ++b) {
-    const long long c = vc->p_cnt[b];
-    const int i = vc->p_idx[b];
-    if (c > big_cnt || (c == big_cnt && i < big)) { big_cnt = c; big = i; }
-    n_empty += vc->p_empty[b];
+  // block partials -> heaviest cluster / empty census: one entry per lane (all loads in flight at
+  // once; a serial loop of dependent L2 round trips cost more than the rest of the kernel), reduced
+  // with shuffles.  The result does not depend on the order: (max count, lowest index), integer sum.
+  long long big_cnt = -1;
+  int big = 0x7fffffff, n_empty = 0;
+  {
+    long long c0 = -1, c1 = -1;
+    int i0 = 0x7fffffff, i1 = 0x7fffffff, e0 = 0, e1 = 0;
+    if (lane < (int)gridDim.x) { c0 = vc->p_cnt[lane]; i0 = vc->p_idx[lane]; e0 = vc->p_empty[lane]; }
+    if (lane + 32 < (int)gridDim.x) { c1 = vc->p_cnt[lane + 32]; i1 = vc->p_idx[lane + 32]; e1 = vc->p_empty[lane + 32]; }
+    if (c1 > c0 || (c1 == c0 && i1 < i0)) { c0 = c1; i0 = i1; }
+    e0 += e1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long oc = __shfl_xor_sync(BDP_FULL_MASK, c0, o);
+      const int oi = __shfl_xor_sync(BDP_FULL_MASK, i0, o);
+      if (oc > c0 || (oc == c0 && oi < i0)) { c0 = oc; i0 = oi; }
+      e0 += __shfl_xor_sync(BDP_FULL_MASK, e0, o);
+    }
+    big_cnt = c0; big = i0; n_empty = e0;               // every warp computes the same values
   }
   if (n_empty > 0) {
     // sklearn _average_centers on a cluster that stayed empty: it copies row `big` as it stands when
@@ -264,8 +277,18 @@ __global__ void __launch_bounds__(kXfThreads) kmeans_xfin_kernel(const XfinParam
     __syncthreads();
   }
   // shift^2 in a FIXED order (every rank must take the same stopping decision)
+  // (per thread: up to 8 independent loads per pass, then a fixed left-to-right sum)
   double acc = 0.0;
-  for (int jj = tid; jj < P.K; jj += kXfThreads) acc += vc->sh[jj];
+  for (int j0 = tid; j0 < P.K; j0 += 8 * kXfThreads) {
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int jj = j0 + q * kXfThreads;
+      v[q] = jj < P.K ? vc->sh[jj] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += v[q];
+  }
   s_red[tid] = acc;
   __syncthreads();
   for (int o = kXfThreads / 2; o > 0; o >>= 1) {

@@ -9,9 +9,9 @@ OUT=gpurun_out
 METRICS="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,smsp__inst_executed.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"
 # 1) launch list of the benchmark command (after it exited 0 without ncu)
 if [[ " $FAMILIES " == *" list "* ]]; then
-python bench.py --steps 5 --warmup 3 --no-extras > $OUT/plain_bench_$TAG.log 2>&1 || exit 1
+timeout 200 python bench.py --steps 5 --warmup 3 --no-extras > $OUT/plain_bench_$TAG.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file $OUT/launches_bench_$TAG.csv python bench.py --steps 5 --warmup 3 --no-extras > $OUT/ncu_bench_$TAG.log 2>&1
+    --log-file $OUT/launches_bench_$TAG.csv timeout 400 python bench.py --steps 5 --warmup 3 --no-extras > $OUT/ncu_bench_$TAG.log 2>&1
 fi
 # 2) full-set captures, a few launches per kernel family
 python profiles/prof_targets.py assign loss lloyd head > $OUT/plain_prof_$TAG.log 2>&1 || exit 1
