@@ -753,11 +753,15 @@ __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restr
     }
   }
   if (out.world > 1) {
-    // every store of this block is ordered before its ticket; the last block publishes the slab
-    __threadfence_system();
+    // Every store of this block is ordered before its ticket: the block barrier makes them visible to
+    // thread 0, whose system-scope fence is cumulative (one fence per block — a fence in every thread
+    // made the sharded build slower than the local one).  The last block publishes the slab.
     __syncthreads();
     __shared__ int s_last;
-    if (threadIdx.x == 0) s_last = (atomicAdd(&hdr->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      s_last = (atomicAdd(&hdr->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
     __syncthreads();
     if (s_last && threadIdx.x < out.world) {
       __threadfence_system();

@@ -228,10 +228,12 @@ __global__ void __launch_bounds__(kXfThreads) kmeans_xfin_kernel(const XfinParam
     for (int i = blockIdx.x * kXfThreads + tid; i < P.A; i += gridDim.x * kXfThreads)
       nxt[i] = (P.incremental && i < P.A - 2) ? cur[i] : 0ull;
   }
-  // 5. the last block to arrive closes the iteration
-  __threadfence();
+  // 5. the last block to arrive closes the iteration (block barrier, then ONE cumulative fence)
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
