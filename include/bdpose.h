@@ -286,6 +286,17 @@ int bdp_keygrid_stats(const void* x, int x_dtype, int64_t N, int d, int K, const
 int64_t bdp_keygrid_bytes(int K, int d);
 int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
                       void* stream);
+/* Fixed-geometry grid for the k-means loop (learnKmeansDictionary.py:41-42: one data set, many
+ * dictionaries).  bdp_keygrid_prepare lays the grid over the caller's box [box_lo, box_hi] ([d] fp64,
+ * device; the bounding box of the rows) instead of the dictionary's and marks every cell "scan the
+ * dictionary"; bdp_keygrid_occupancy sets occ[c] = 1 (occ [bdp_keygrid_coarse_cells(K, d)] int32,
+ * zeroed by the caller) for every coarse cell c that holds a row of x [N, d] fp64 — with the query
+ * kernel's own point -> cell arithmetic.  bdp_kmeans_run then rebuilds only the listed cells. */
+int64_t bdp_keygrid_coarse_cells(int K, int d);
+int bdp_keygrid_prepare(const double* box_lo, const double* box_hi, int K, int d, void* grid,
+                        int64_t grid_bytes, void* stream);
+int bdp_keygrid_occupancy(const double* x, int64_t N, int d, int K, const void* grid,
+                          int64_t grid_bytes, int32_t* occ, void* stream);
 int bdp_assign_nearest_grid(const void* x, int x_dtype, int64_t N, int d, const double* centers,
                             int K, const void* grid, int64_t grid_bytes, int32_t* labels32,
                             int64_t* labels64, float* residual, double* min_sqdist, void* stream);
@@ -358,6 +369,13 @@ int bdp_kmeans_finalize(const int64_t* acc, int K, int d, int fix_hi_bits,
  *     every rank's key-grid buffer, allocated like the exchange buffers: the build is then SHARDED —
  *     a rank builds the cells of one slab of the grid and stores them into every rank's buffer over
  *     NVLink, and the E+M kernel waits until all slabs have arrived (flags in the exchange buffer).
+ *     cells (NULL: the grid geometry follows the dictionary's bounding box and every cell is rebuilt
+ *     every iteration) = ascending list of the n_cells coarse cells of a FIXED-geometry grid
+ *     (bdp_keygrid_prepare + bdp_keygrid_occupancy) that hold rows of the fit, identical on every
+ *     rank: only those cells are rebuilt (the rest of the box is never queried), a rank's slab is its
+ *     share of the list, and the exchange kernel renews the build's counters and fp32 keys, so an
+ *     iteration is three launches.  Labels do not depend on it: a query that reaches a cell no build
+ *     has written scans the dictionary.
  *     BDP_KMEANS_NEEDS_HOST: an empty cluster appeared; the caller relocates (scikit-learn
  *     _relocate_empty_clusters_dense) on the summed accumulator, finalises with bdp_kmeans_finalize,
  *     clears status.state and resumes with iter0 = status.iter_done.
@@ -382,7 +400,7 @@ int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers2, int K, v
                    int64_t grid_bytes, void* const* grid_peers, int32_t* labels, void* const* xchg,
                    const void* xchg_multicast, int world, int rank, int fix_hi_bits, int64_t iter0,
                    int n_iters, int check, int incremental, double tol_abs, void* ctl,
-                   void* const* em_events, void* stream);
+                   void* const* em_events, const int32_t* cells, int n_cells, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (a) category-conditioned bin-delta heads.

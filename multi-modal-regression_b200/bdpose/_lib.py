@@ -63,7 +63,10 @@ SIGNATURES = {
     "bdp_kmeans_exchange_finalize": (_int, [_p, _p, _int, _int, _int, _int, _int, _int, _i64, _int, _int,
                                             _f64, _p, _p, _p, _p]),
     "bdp_kmeans_run": (_int, [_p, _i64, _int, _p, _int, _p, _i64, _p, _p, _p, _p, _int, _int, _int, _i64,
-                              _int, _int, _int, _f64, _p, _p, _p]),
+                              _int, _int, _int, _f64, _p, _p, _p, _int, _p]),
+    "bdp_keygrid_coarse_cells": (_i64, [_int, _int]),
+    "bdp_keygrid_prepare": (_int, [_p, _p, _int, _int, _p, _i64, _p]),
+    "bdp_keygrid_occupancy": (_int, [_p, _i64, _int, _int, _p, _i64, _p, _p]),
     "bdp_gemm_tf32": (_int, [_p, _int, _i64, _i64, _p, _int, _i64, _i64, _p, _int, _i64, _i64, _i64,
                              _i64, _i64, _int, _int, _i64, _int, _p]),
     "bdp_gemm_tf32_splits": (_int, [_i64, _int]),

@@ -288,6 +288,15 @@ class LloydLoop:
             if sg is not None:
                 self.grid = ops.KeyGrid(centers, buf=sg[0], build=False)
                 self.grid_ptrs = sg[1]
+        # fixed-geometry grid: laid over the bounding box of the ROWS once per fit, and only the coarse
+        # cells that hold rows (on any rank) are rebuilt each iteration — the rest of the box is never
+        # queried (uniform rotations fill 52 % of their bounding cube).  The loop owns this grid.
+        self.cells, self.n_cells = None, 0
+        if self.grid is not None and self.mode != "nccl" and \
+                os.environ.get("BDPOSE_KMEANS_FIXED_GRID", "1") != "0":
+            if self.grid_ptrs is None:
+                self.grid = ops.KeyGrid(centers, build=False)
+            self._fix_geometry()
         self._tmp_shift = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._tmp_empty = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.n_iter, self.strict, self.stopped = 0, False, False
@@ -295,6 +304,34 @@ class LloydLoop:
         # with the key grid; the NCCL fallback all-reduces its accumulator in place and recomputes
         self.incremental = self.grid is not None and self.mode != "nccl" and \
             os.environ.get("BDPOSE_KMEANS_INCREMENTAL", "1") != "0"
+
+    def _fix_geometry(self):
+        import torch.distributed as dist
+        lib = L.lib()
+        g, x, dev = self.grid, self.x, self.dev
+        inf = float("inf")
+        if self.N > 0:
+            lo, hi = torch.aminmax(x, dim=0)
+        else:
+            lo, hi = x.new_full((self.d,), inf), x.new_full((self.d,), -inf)
+        if self.world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        lo, hi = lo.contiguous(), hi.contiguous()
+        occ = torch.zeros(lib.bdp_keygrid_coarse_cells(self.K, self.d), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.bdp_keygrid_prepare(lo.data_ptr(), hi.data_ptr(), self.K, self.d, g.buf.data_ptr(),
+                                         g.nbytes, L.stream_ptr())
+            L.check(st, "bdp_keygrid_prepare")
+            st = lib.bdp_keygrid_occupancy(L.ptr(x), self.N, self.d, self.K, g.buf.data_ptr(), g.nbytes,
+                                           occ.data_ptr(), L.stream_ptr())
+            L.check(st, "bdp_keygrid_occupancy")
+        if self.world > 1:
+            # (also orders every rank's prepare before any peer's first slab store into its grid)
+            dist.all_reduce(occ, op=dist.ReduceOp.MAX, group=self.group)
+        self.cells = torch.nonzero(occ).reshape(-1).to(torch.int32).contiguous()
+        self.n_cells = int(self.cells.numel())
+        self.n_coarse = int(occ.numel())
 
     def reset(self, centers):
         """Start over from `centers` (same data): accumulators, flags, labels and status cleared."""
@@ -330,7 +367,9 @@ class LloydLoop:
                                     self.grid_ptrs, self.labels.data_ptr(), self.ptrs, self.ex.mc,
                                     self.world, self.rank,
                                     self.hb, i0, n, 1 if check else 0, 1 if self.incremental else 0,
-                                    self.tol_abs, self.ctl.data_ptr(), ev, L.stream_ptr())
+                                    self.tol_abs, self.ctl.data_ptr(), ev,
+                                    None if self.cells is None else self.cells.data_ptr(), self.n_cells,
+                                    L.stream_ptr())
         L.check(st, "bdp_kmeans_run")
 
     def _launch_nccl(self, i0, check):

@@ -575,11 +575,17 @@ template <int D>
 __global__ void __launch_bounds__(256) keygrid_header_kernel(const double* __restrict__ centers, int K,
                                                              int G, double margin_frac,
                                                              GridHdr* __restrict__ hdr,
-                                                             float4* __restrict__ cf32, const int* stop) {
+                                                             float4* __restrict__ cf32, const int* stop,
+                                                             int keep_geometry) {
   if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
-  __shared__ GridHdr s_hdr;
-  compute_header<D>(centers, K, G, margin_frac, &s_hdr);
-  if (threadIdx.x == 0) { s_hdr.side_next = 0u; s_hdr.ticket = 0u; *hdr = s_hdr; }
+  if (keep_geometry) {
+    // fixed-geometry grid (bdp_keygrid_prepare): only the build counters and the fp32 keys are renewed
+    if (threadIdx.x == 0) { hdr->side_next = 0u; hdr->ticket = 0u; }
+  } else {
+    __shared__ GridHdr s_hdr;
+    compute_header<D>(centers, K, G, margin_frac, &s_hdr);
+    if (threadIdx.x == 0) { s_hdr.side_next = 0u; s_hdr.ticket = 0u; *hdr = s_hdr; }
+  }
   for (int k = threadIdx.x; k < K; k += blockDim.x) {   // fp32 copy of the keys for the box tests
     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -601,7 +607,8 @@ constexpr int kCoarseListCap = 1024;
 template <int D>
 __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restrict__ cf32, int K,
                                                            GridHdr* __restrict__ hdr, const BuildOut out,
-                                                           int64_t coarse0, int active, const int* stop) {
+                                                           int64_t coarse0, int active, const int* stop,
+                                                           const int* __restrict__ cells) {
   if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
   if (!active) {                                       // a rank with an empty slab only publishes its flag
     if (out.world > 1 && threadIdx.x < out.world) {
@@ -619,7 +626,8 @@ __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restr
   unsigned short* s_ids = s_list + ((cap + 1 + 7) & ~7);                            // [kChildren][32]
   const int G = hdr->G, Gc = G / 4;
   const int lane = threadIdx.x & 31;
-  const int64_t parent = coarse0 + blockIdx.x;
+  // cells != NULL: the build covers a LIST of coarse cells (those that hold rows of the fit)
+  const int64_t parent = cells != nullptr ? (int64_t)__ldg(cells + coarse0 + blockIdx.x) : coarse0 + blockIdx.x;
   float org[D], cel[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) { org[k] = (float)hdr->origin[k]; cel[k] = (float)hdr->cell[k]; }
@@ -1157,10 +1165,17 @@ extern "C" int64_t bdp_keygrid_bytes(int K, int d) {
 // rank derives the same grid geometry, builds the coarse cells of ITS slab only (whole layers along
 // the last axis) and stores their fine / side records into every rank's grid; the query waits for all
 // slabs (gflags).
+// cells != NULL (fixed-geometry grid of a k-means fit, bdp_keygrid_prepare): only the n_cells listed
+// coarse cells are built — the ones that hold rows — and a rank's slab is its share of that list.
+// header_mode: 0 = geometry from the dictionary's bounding box (header kernel), 1 = keep the geometry,
+// renew counters + fp32 keys (header kernel), 2 = nothing (the exchange kernel of the previous
+// iteration has renewed them).
 int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
-                       const int* stop, const bdpi_grid_peers* peers, cudaStream_t st) {
+                       const int* stop, const bdpi_grid_peers* peers, cudaStream_t st,
+                       const int* cells, int n_cells, int header_mode) {
   BDP_REQUIRE(centers != nullptr, "keygrid_build: NULL centers");
   BDP_REQUIRE(d == 3 || d == 4, "keygrid_build: d must be 3 or 4 (got %d)", d);
+  BDP_REQUIRE(cells != nullptr || header_mode == 0, "keygrid_build: header_mode %d needs a cell list", header_mode);
   int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_build");
   if (rc != BDP_OK) return rc;
   const GridPtrs g = keygrid_pointers(grid, K, d);
@@ -1170,8 +1185,6 @@ int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t 
   const int world = (peers && peers->world > 1) ? peers->world : 1;
   const int rank = world > 1 ? peers->rank : 0;
   BDP_REQUIRE(world <= BDP_KMEANS_MAX_RANKS && rank >= 0 && rank < world, "keygrid_build: rank %d of %d", rank, world);
-  // slab of this rank: coarse layers [zc0, zc1) along the last axis
-  const int zc0 = (int)((int64_t)rank * Gc / world), zc1 = (int)((int64_t)(rank + 1) * Gc / world);
   BuildOut out = {};
   out.world = world; out.rank = rank;
   out.side_per_rank = (unsigned)(g.n_side / world);
@@ -1183,29 +1196,143 @@ int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t 
     out.fine[q] = gq.fine; out.side[q] = gq.side;
     out.gflags[q] = world > 1 ? peers->gflags[q] : nullptr;
   }
-  const int64_t layer_c = ipow64(Gc, d - 1);
-  const int64_t coarse0 = zc0 * layer_c, n_coarse = (zc1 - zc0) * layer_c;
+  int64_t coarse0, n_coarse;
+  if (cells != nullptr) {
+    BDP_REQUIRE(n_cells >= 0 && n_cells <= g.n_coarse, "keygrid_build: %d cells of %lld", n_cells, (long long)g.n_coarse);
+    coarse0 = (int64_t)rank * n_cells / world;
+    n_coarse = (int64_t)(rank + 1) * n_cells / world - coarse0;
+  } else {
+    // slab of this rank: coarse layers [zc0, zc1) along the last axis
+    const int zc0 = (int)((int64_t)rank * Gc / world), zc1 = (int)((int64_t)(rank + 1) * Gc / world);
+    const int64_t layer_c = ipow64(Gc, d - 1);
+    coarse0 = zc0 * layer_c; n_coarse = (zc1 - zc0) * layer_c;
+  }
   const int cap = K < kCoarseListCap ? K : kCoarseListCap;
   const size_t smem = (size_t)cap * 16 + (size_t)(((cap + 1 + 7) & ~7) + (d == 3 ? 64 : 256) * kSideWidth) * 2;
   const unsigned blocks = (unsigned)(n_coarse > 0 ? n_coarse : 1);
   const int active = n_coarse > 0 ? 1 : 0;
   if (d == 3) {
-    keygrid_header_kernel<3><<<1, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.cf32, stop);
+    if (header_mode != 2)
+      keygrid_header_kernel<3><<<1, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.cf32, stop, header_mode);
     if (active || world > 1)
-      keygrid_cell_kernel<3><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, active, stop);
+      keygrid_cell_kernel<3><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, active, stop, cells);
   } else {
-    keygrid_header_kernel<4><<<1, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.cf32, stop);
+    if (header_mode != 2)
+      keygrid_header_kernel<4><<<1, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.cf32, stop, header_mode);
     if (active || world > 1)
-      keygrid_cell_kernel<4><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, active, stop);
+      keygrid_cell_kernel<4><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, active, stop, cells);
   }
   BDP_CUDA_CHECK_LAUNCH("keygrid kernels");
+  return BDP_OK;
+}
+
+// header and fp32-key array of a grid buffer (kmeans.cu: the exchange kernel renews them)
+void bdpi_keygrid_parts(void* grid, int K, int d, void** hdr, void** cf32) {
+  const GridPtrs g = keygrid_pointers(grid, K, d);
+  *hdr = g.hdr; *cf32 = g.cf32;
+}
+
+namespace {
+// Fixed geometry over the caller's box (widened by 1e-4 of its largest extent); counters reset.
+__global__ void keygrid_prepare_kernel(GridHdr* __restrict__ hdr, int d, int G, const double* __restrict__ lo,
+                                       const double* __restrict__ hi) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double ext = 0.0;
+  bool finite = true;
+  for (int k = 0; k < d; ++k) {
+    finite = finite && isfinite(lo[k]) && isfinite(hi[k]) && hi[k] >= lo[k];
+    ext = fmax(ext, hi[k] - lo[k]);
+  }
+  const bool ok = finite && ext > 0.0 && isfinite(ext);
+  const double margin = ext * 1e-4;
+  for (int k = 0; k < 4; ++k) {
+    double o = 0.0, c = 1.0;
+    if (k < d && ok) {
+      o = lo[k] - margin;
+      c = (hi[k] - lo[k] + 2.0 * margin) / (double)G;
+    }
+    hdr->origin[k] = o; hdr->cell[k] = c; hdr->inv_cell[k] = 1.0 / c;
+    hdr->origin32[k] = (float)o; hdr->inv_cell32[k] = (float)(1.0 / c);
+  }
+  hdr->G = G;
+  hdr->enabled = ok ? 1 : 0;
+  hdr->side_next = 0u; hdr->ticket = 0u;
+}
+
+// Coarse cells that hold at least one row: the point -> cell map is the query kernel's, expression
+// for expression (fp32 FMA + floor on the fp32 copy of the coordinate), so a row marks exactly the
+// coarse parent of the fine cell its query will read.
+template <int D>
+__global__ void __launch_bounds__(256) keygrid_occupancy_kernel(const double* __restrict__ x, int64_t N,
+                                                                const GridHdr* __restrict__ hdr,
+                                                                int* __restrict__ occ) {
+  if (hdr->enabled == 0) return;
+  float g_inv[D], g_off[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    g_inv[k] = (float)hdr->inv_cell[k];
+    g_off[k] = (float)(-hdr->origin[k] * hdr->inv_cell[k]);
+  }
+  const int G = hdr->G, Gc = G / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    bool ok = true;
+    int cidx = 0, mul = 1;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const float xf = (float)__ldcs(x + i * D + k);
+      const float t = fmaf(xf, g_inv[k], g_off[k]);
+      const int ck = __float2int_rd(t);
+      ok = ok && ((unsigned)ck < (unsigned)G);
+      cidx += (ck >> 2) * mul;
+      mul *= Gc;
+    }
+    if (ok) occ[cidx] = 1;        // every writer stores the same value
+  }
+}
+}  // namespace
+
+extern "C" int64_t bdp_keygrid_coarse_cells(int K, int d) {
+  if ((d != 3 && d != 4) || K < 1 || K > kGridMaxK) return -1;
+  return ipow64(keygrid_G(K, d) / 4, d);
+}
+
+extern "C" int bdp_keygrid_prepare(const double* box_lo, const double* box_hi, int K, int d, void* grid,
+                                   int64_t grid_bytes, void* stream) {
+  BDP_REQUIRE(box_lo && box_hi, "keygrid_prepare: NULL box");
+  BDP_REQUIRE(d == 3 || d == 4, "keygrid_prepare: d must be 3 or 4 (got %d)", d);
+  int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_prepare");
+  if (rc != BDP_OK) return rc;
+  const GridPtrs g = keygrid_pointers(grid, K, d);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // every cell starts as "overflowed": a query that reaches a cell no build has written scans the
+  // dictionary (exact), so the occupancy list is an optimisation, never a correctness condition
+  BDP_CUDA_CALL(cudaMemsetAsync(g.fine, 0xFF, (size_t)g.n_fine * 16, st));
+  keygrid_prepare_kernel<<<1, 32, 0, st>>>(g.hdr, d, g.G, box_lo, box_hi);
+  BDP_CUDA_CHECK_LAUNCH("keygrid_prepare_kernel");
+  return BDP_OK;
+}
+
+extern "C" int bdp_keygrid_occupancy(const double* x, int64_t N, int d, int K, const void* grid,
+                                     int64_t grid_bytes, int32_t* occ, void* stream) {
+  BDP_REQUIRE(N >= 0 && occ, "keygrid_occupancy: bad arguments");
+  BDP_REQUIRE(d == 3 || d == 4, "keygrid_occupancy: d must be 3 or 4 (got %d)", d);
+  int rc = keygrid_check(grid, grid_bytes, K, d, "keygrid_occupancy");
+  if (rc != BDP_OK) return rc;
+  if (N == 0) return BDP_OK;
+  BDP_REQUIRE(x != nullptr, "keygrid_occupancy: x is NULL");
+  const GridPtrs g = keygrid_pointers(grid, K, d);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)(ceil_div64(N, 256) < 2368 ? ceil_div64(N, 256) : 2368);
+  if (d == 3) keygrid_occupancy_kernel<3><<<blocks, 256, 0, st>>>(x, N, g.hdr, occ);
+  else keygrid_occupancy_kernel<4><<<blocks, 256, 0, st>>>(x, N, g.hdr, occ);
+  BDP_CUDA_CHECK_LAUNCH("keygrid_occupancy_kernel");
   return BDP_OK;
 }
 
 extern "C" int bdp_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
                                  void* stream) {
   return bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr, nullptr,
-                            reinterpret_cast<cudaStream_t>(stream));
+                            reinterpret_cast<cudaStream_t>(stream), nullptr, 0, 0);
 }
 
 extern "C" int bdp_keygrid_stats(const void* x, int x_dtype, int64_t N, int d, int K, const void* grid,

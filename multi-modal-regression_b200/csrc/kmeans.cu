@@ -23,7 +23,9 @@
 
 // internal entry points of assign.cu (same shared object, not part of the C ABI)
 int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t grid_bytes,
-                       const int* stop, const bdpi_grid_peers* peers, cudaStream_t st);
+                       const int* stop, const bdpi_grid_peers* peers, cudaStream_t st,
+                       const int* cells, int n_cells, int header_mode);
+void bdpi_keygrid_parts(void* grid, int K, int d, void** hdr, void** cf32);
 int bdpi_lloyd_step_grid(const double* x, int64_t N, int d, const double* centers, int K,
                          const void* grid, int64_t grid_bytes, int32_t* labels, int64_t* acc,
                          int fix_hi_bits, int64_t* stats, double* inertia, int update,
@@ -77,6 +79,10 @@ struct XfinParams {
   const double* c_old;
   double* c_new;
   KmCtl* ctl;
+  // fixed-geometry key grid of the fit (NULL: the build's own header kernel does this): the exchange
+  // kernel renews the fp32 copy of the keys and the build counters for the next iteration's build
+  float4* cf32;
+  bdp_assign::GridHdr* ghdr;
 };
 
 __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
@@ -187,13 +193,16 @@ __global__ void __launch_bounds__(kXfThreads) kmeans_xfin_kernel(const XfinParam
     double sh = 0.0;
     if (cnt > 0) {
       const double alpha = 1.0 / (double)cnt;        // sklearn _average_centers: c *= 1/weight
+      float cf[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         const double c = limbs_to_double((long long)a[2 * k], (long long)a[2 * k + 1], P.inv_scale_lo) * alpha;
         P.c_new[(size_t)j * D + k] = c;
+        cf[k] = (float)c;
         const double df = c - P.c_old[(size_t)j * D + k];
         sh += df * df;
       }
+      if (P.cf32 != nullptr) P.cf32[j] = make_float4(cf[0], cf[1], cf[2], cf[3]);
     } else {
       empty = 1;                                      // the last block fills these in
     }
@@ -267,13 +276,16 @@ __global__ void __launch_bounds__(kXfThreads) kmeans_xfin_kernel(const XfinParam
       if (vc->cnt[jj] != 0) continue;
       const double alpha = (big < jj && big_cnt > 0) ? 1.0 / (double)big_cnt : 1.0;
       double sh = 0.0;
+      float cf[4] = {0.f, 0.f, 0.f, 0.f};
       for (int k = 0; k < D; ++k) {
         const unsigned long long hi = xsum(P, big * W + 2 * k), lo = xsum(P, big * W + 2 * k + 1);
         const double c = limbs_to_double((long long)hi, (long long)lo, P.inv_scale_lo) * alpha;
         P.c_new[(size_t)jj * D + k] = c;
+        cf[k] = (float)c;
         const double df = c - P.c_old[(size_t)jj * D + k];
         sh += df * df;
       }
+      if (P.cf32 != nullptr) P.cf32[jj] = make_float4(cf[0], cf[1], cf[2], cf[3]);
       ctl->sh[jj] = sh;
     }
     __syncthreads();
@@ -305,6 +317,7 @@ __global__ void __launch_bounds__(kXfThreads) kmeans_xfin_kernel(const XfinParam
     ctl->n_empty = n_empty;
     ctl->iter_done = (long long)P.flag_value;
     ctl->ticket = 0u;
+    if (P.ghdr != nullptr) { P.ghdr->side_next = 0u; P.ghdr->ticket = 0u; }
     int state = BDP_KMEANS_RUNNING;
     if (n_empty > 0) state = BDP_KMEANS_NEEDS_HOST;          // relocation runs on the host (rare)
     else if (P.check) {
@@ -341,11 +354,11 @@ extern "C" int64_t bdp_kmeans_xchg_bytes(int K, int d) {
   return (int64_t)(2 * ((int64_t)K * (2 * d + 1) + 2) + 2 * kMaxWorld) * 8;
 }
 
-extern "C" int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_multicast, int world,
-                                            int rank, int K, int d, int fix_hi_bits, int parity,
-                                            int64_t flag_value, int check, int incremental,
-                                            double tol_abs, const double* centers_old,
-                                            double* centers_new, void* ctl, void* stream) {
+namespace {
+int exchange_finalize(void* const* xchg, const void* xchg_multicast, int world, int rank, int K, int d,
+                      int fix_hi_bits, int parity, int64_t flag_value, int check, int incremental,
+                      double tol_abs, const double* centers_old, double* centers_new, void* ctl,
+                      void* fixed_grid, void* stream) {
   int rc = check_common(K, d, world, rank, "kmeans_exchange_finalize");
   if (rc != BDP_OK) return rc;
   BDP_REQUIRE(xchg && centers_old && centers_new && ctl, "kmeans_exchange_finalize: NULL buffer");
@@ -362,8 +375,24 @@ extern "C" int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_
   P.inv_scale_lo = ldexp(1.0, -(fix_hi_bits + 32));
   P.tol_abs = tol_abs; P.c_old = centers_old; P.c_new = centers_new;
   P.ctl = reinterpret_cast<KmCtl*>(ctl);
+  if (fixed_grid != nullptr) {
+    void *h, *c;
+    bdpi_keygrid_parts(fixed_grid, K, d, &h, &c);
+    P.ghdr = reinterpret_cast<bdp_assign::GridHdr*>(h);
+    P.cf32 = reinterpret_cast<float4*>(c);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return d == 3 ? launch_xfin<3>(P, st) : launch_xfin<4>(P, st);
+}
+}  // namespace
+
+extern "C" int bdp_kmeans_exchange_finalize(void* const* xchg, const void* xchg_multicast, int world,
+                                            int rank, int K, int d, int fix_hi_bits, int parity,
+                                            int64_t flag_value, int check, int incremental,
+                                            double tol_abs, const double* centers_old,
+                                            double* centers_new, void* ctl, void* stream) {
+  return exchange_finalize(xchg, xchg_multicast, world, rank, K, d, fix_hi_bits, parity, flag_value,
+                           check, incremental, tol_abs, centers_old, centers_new, ctl, nullptr, stream);
 }
 
 // n_iters Lloyd iterations as one launch sequence: [key-grid build, E+M step, exchange+finalise] x n.
@@ -371,12 +400,14 @@ extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers
                               int64_t grid_bytes, void* const* grid_peers, int32_t* labels,
                               void* const* xchg, const void* xchg_multicast, int world, int rank,
                               int fix_hi_bits, int64_t iter0, int n_iters, int check, int incremental,
-                              double tol_abs, void* ctl, void* const* em_events, void* stream) {
+                              double tol_abs, void* ctl, void* const* em_events,
+                              const int32_t* cells, int n_cells, void* stream) {
   int rc = check_common(K, d, world, rank, "kmeans_run");
   if (rc != BDP_OK) return rc;
   BDP_REQUIRE(centers2 && labels && xchg && ctl, "kmeans_run: NULL buffer");
   BDP_REQUIRE(N >= 0 && (x != nullptr || N == 0), "kmeans_run: x is NULL");
   BDP_REQUIRE(iter0 >= 0 && n_iters >= 0, "kmeans_run: negative iteration range");
+  BDP_REQUIRE(cells == nullptr || (grid != nullptr && n_cells >= 0), "kmeans_run: a cell list needs the key grid");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int A = K * (2 * d + 1) + 2;
   const int* stop = reinterpret_cast<const int*>(ctl);          // KmCtl::state
@@ -406,7 +437,10 @@ extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers
       // (a rank without rows still builds its slab: the peers' queries read it)
       gp.flag_value = (unsigned long long)(gi + 1);
       if (N > 0 || shard) {
-        rc = bdpi_keygrid_build(c_cur, K, d, grid, grid_bytes, stop, shard ? &gp : nullptr, st);
+        // fixed-geometry grid (cells != NULL): the header kernel runs once per call, after that the
+        // exchange kernel of the previous iteration has renewed the counters and the fp32 keys
+        rc = bdpi_keygrid_build(c_cur, K, d, grid, grid_bytes, stop, shard ? &gp : nullptr, st, cells,
+                                n_cells, cells == nullptr ? 0 : (it == 0 ? 1 : 2));
         if (rc != BDP_OK) return rc;
       }
       if ((rc = mark(1)) != BDP_OK) return rc;
@@ -422,8 +456,9 @@ extern "C" int bdp_kmeans_run(const double* x, int64_t N, int d, double* centers
                            stop, st);
     }
     if (rc != BDP_OK) return rc;
-    rc = bdp_kmeans_exchange_finalize(xchg, xchg_multicast, world, rank, K, d, fix_hi_bits, cur,
-                                      gi + 1, check, incremental, tol_abs, c_cur, c_new, ctl, stream);
+    rc = exchange_finalize(xchg, xchg_multicast, world, rank, K, d, fix_hi_bits, cur, gi + 1, check,
+                           incremental, tol_abs, c_cur, c_new, ctl,
+                           (grid != nullptr && cells != nullptr && (N > 0 || shard)) ? grid : nullptr, stream);
     if (rc != BDP_OK) return rc;
     if ((rc = mark(3)) != BDP_OK) return rc;
   }
@@ -535,7 +570,7 @@ extern "C" int bdp_kmeans_iteration(const double* x, int64_t N, int d, const dou
   BDP_CUDA_CALL(cudaMemsetAsync(acc_stats, 0, (n_acc + 2) * sizeof(int64_t), st));
   int rc;
   if (grid) {
-    rc = bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr, nullptr, st);
+    rc = bdpi_keygrid_build(centers, K, d, grid, grid_bytes, nullptr, nullptr, st, nullptr, 0, 0);
     if (rc != BDP_OK) return rc;
     rc = bdpi_lloyd_step_grid(x, N, d, centers, K, grid, grid_bytes, labels, acc_stats, fix_hi_bits,
                               acc_stats + n_acc, inertia, update, nullptr, nullptr, 0, 0ull, 0, st);

@@ -141,3 +141,87 @@ def test_host_to_host_pipeline(cuda, N, chunk):
     b_d, r_d = G.assign_labels(y.to(cuda), c)
     assert b_h.dtype == torch.int64 and not b_h.is_cuda
     assert torch.equal(b_h, b_d.cpu()) and torch.equal(r_h, r_d.cpu())
+
+
+def _clustered(rng, n, n_blobs=12, spread=0.15):
+    """Pascal-like pose data: rotations concentrated around a few viewpoints, plus one far outlier
+    that stretches the bounding box (most coarse cells of the fixed-geometry grid hold no row)."""
+    cen = rand_rot(rng, n_blobs)[0] * 0.6
+    x = cen[rng.integers(0, n_blobs, n)] + rng.standard_normal((n, 3)) * spread
+    x[0] = [3.0, -3.0, 2.5]
+    return x
+
+
+@pytest.mark.parametrize("data", ["uniform", "clustered"])
+def test_fixed_geometry_fit_identical(cuda, data, monkeypatch):
+    """The k-means loop's fixed-geometry grid (box of the rows, only the occupied coarse cells rebuilt,
+    counters / fp32 keys renewed by the exchange kernel) against the per-iteration dictionary-box grid
+    and the brute-force scan: same iteration count, labels and centres bit for bit."""
+    from bdpose import kmeans
+    rng = np.random.default_rng(23)
+    Xn = rand_rot(rng, 200_000)[0] if data == "uniform" else _clustered(rng, 200_000)
+    X = torch.from_numpy(Xn).to(cuda)
+    init = X[1:301].clone()
+    fs = kmeans.FitSetup(X, init, group=kmeans.LOCAL)
+    lab = torch.full((X.shape[0],), -1, dtype=torch.int32, device=cuda)
+    from bdpose import ops
+    loop = kmeans.LloydLoop(fs.x, fs.centers, lab, fs.hb, ops.KeyGrid(fs.centers), kmeans.LOCAL, fs.tol_abs)
+    assert loop.cells is not None and 0 < loop.n_cells <= loop.n_coarse
+    if data == "clustered":
+        assert loop.n_cells < loop.n_coarse // 2, (loop.n_cells, loop.n_coarse)
+    outs = []
+    for fixed, use_grid in (("1", True), ("0", True), ("1", False)):
+        monkeypatch.setenv("BDPOSE_KMEANS_FIXED_GRID", fixed)
+        for kw in (dict(max_iter=25), dict(fixed_iters=9)):
+            outs.append(kmeans.kmeans_lloyd(X, init, use_grid=use_grid, **kw))
+    for a, b in ((0, 2), (0, 4), (1, 3), (1, 5)):
+        assert outs[a]["n_iter"] == outs[b]["n_iter"]
+        assert torch.equal(outs[a]["labels"], outs[b]["labels"])
+        assert torch.equal(outs[a]["centers"], outs[b]["centers"])
+        # (the inertia is a floating-point sum whose order differs between the kernels)
+        assert outs[a]["inertia"] == pytest.approx(outs[b]["inertia"], rel=1e-12)
+
+
+def test_prepared_grid_scans_until_built(cuda):
+    """bdp_keygrid_prepare marks every cell "scan the dictionary": a query through a prepared but
+    unbuilt grid is exact (the occupied-cell list is an optimisation, not a correctness condition),
+    and bdp_keygrid_occupancy marks the coarse parents of exactly the cells the rows fall into."""
+    from bdpose import ops, _lib as L
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rand_rot(rng, 20_000)[0]).to(cuda)
+    c = x[:100].clone().contiguous()
+    g = ops.KeyGrid(c, build=False)
+    lo, hi = torch.aminmax(x, dim=0)
+    lib = L.lib()
+    L.check(lib.bdp_keygrid_prepare(lo.contiguous().data_ptr(), hi.contiguous().data_ptr(), 100, 3,
+                                    g.buf.data_ptr(), g.nbytes, L.stream_ptr()), "prepare")
+    a = ops.assign_nearest(x, c, grid=g)
+    b = ops.assign_nearest(x, c, grid=None)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    st = ops.keygrid_stats(g, x)
+    assert st["outside_grid"] == 0 and st["overflow_cells"] == x.shape[0]
+    nc = lib.bdp_keygrid_coarse_cells(100, 3)
+    occ = torch.zeros(nc, dtype=torch.int32, device=cuda)
+    L.check(lib.bdp_keygrid_occupancy(x.data_ptr(), x.shape[0], 3, 100, g.buf.data_ptr(), g.nbytes,
+                                      occ.data_ptr(), L.stream_ptr()), "occupancy")
+    # the same map in numpy (fp32 FMA is not available there: compare with a tolerance-free superset
+    # check instead — every marked cell holds a row within one fine cell of it, every row's cell is marked)
+    hdr = np.frombuffer(bytes(g.buf[:160].cpu().numpy()), dtype=np.float64, count=12)
+    org, inv = hdr[0:3], hdr[8:11]
+    G = int(np.frombuffer(bytes(g.buf[96:100].cpu().numpy()), dtype=np.int32)[0])
+    t = (x.cpu().numpy() - org) * inv
+    fine = np.floor(t).astype(np.int64)
+    assert fine.min() >= 0 and fine.max() < G
+    frac = t - fine
+    safe = ((frac > 1e-3) & (frac < 1 - 1e-3)).all(1)          # rows whose cell no rounding can change
+    Gc = G // 4
+    coarse = (fine[:, 0] // 4) + Gc * ((fine[:, 1] // 4) + Gc * (fine[:, 2] // 4))
+    occ_h = occ.cpu().numpy()
+    assert occ_h[coarse[safe]].all()
+    allowed = set()
+    for sx in (-2e-3, 2e-3):
+        for sy in (-2e-3, 2e-3):
+            for sz in (-2e-3, 2e-3):
+                f = np.clip(np.floor(t + np.array([sx, sy, sz])).astype(np.int64), 0, G - 1)
+                allowed |= set(((f[:, 0] // 4) + Gc * ((f[:, 1] // 4) + Gc * (f[:, 2] // 4))).tolist())
+    assert set(np.nonzero(occ_h)[0].tolist()) <= allowed
