@@ -285,48 +285,53 @@ __device__ __forceinline__ void row_softmax_ce(const LossParams& P, int64_t row,
     }
   }
   mi = __reduce_min_sync(BDP_FULL_MASK, mi);
-  // the target logit sits in exactly one lane's registers (predicated selects: indexing v[] with a
-  // runtime index would push it to local memory)
-  float xt = 0.f;
+  // the target logit sits in exactly one lane's registers.  tgt is warp-uniform, so the vector index
+  // and the component are selected with uniform predicates (7 selects for KV = 2 instead of a
+  // compare + select per element), then the owning lane broadcasts.
+  float xt;
+  {
+    const int tj = tgt >> 7, tq = tgt & 3;
+    float4 w = v[0];
 #pragma unroll
-  for (int j = 0; j < KV; ++j) {
-    const int base = (lane + j * 32) * 4;
-    xt = (tgt == base) ? v[j].x : xt;
-    xt = (tgt == base + 1) ? v[j].y : xt;
-    xt = (tgt == base + 2) ? v[j].z : xt;
-    xt = (tgt == base + 3) ? v[j].w : xt;
+    for (int j = 1; j < KV; ++j)
+      if (tj == j) w = v[j];
+    const float a = (tq & 1) ? w.y : w.x, b = (tq & 1) ? w.w : w.z;
+    xt = __shfl_sync(BDP_FULL_MASK, (tq & 2) ? b : a, (tgt >> 2) & 31);
   }
-  xt = __shfl_sync(BDP_FULL_MASK, xt, (tgt >> 2) & 31);
-  // ex2.approx on (x - m) * log2(e): 3 instructions instead of ~10, relative error ~2^-22, far
-  // inside the 1e-5 bar (the sum s and every probability carry it once)
+  // 2^(x*log2e - m*log2e): one FMA + ex2.approx per element.  The product m*log2e is rounded once
+  // (mh); its rounding error ml = m*log2e - mh (exact, one more FMA per row) multiplies every term by
+  // the same 2^ml, which cancels in the probabilities and is taken out of log(s) below.
+  const float kLog2e = 1.4426950408889634f;
+  const float mh = m * kLog2e;
+  const float ml = fmaf(m, kLog2e, -mh);
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < KV; ++j) {
     float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      e[q] = ex2_approx((e[q] - m) * 1.4426950408889634f);   // exp(-inf) = 0 for the padding lanes
+      e[q] = ex2_approx(fmaf(e[q], kLog2e, -mh));              // exp(-inf) = 0 for the padding lanes
       s += e[q];
     }
     v[j] = make_float4(e[0], e[1], e[2], e[3]);
   }
   s = warp_sum(s);
-  ce = (m - xt) + logf(s);
+  ce = (m - xt) + fmaf(-ml, 0.6931471805599453f, logf(s));
   amax = mi;
   if (P.grad_logits) {
-    const float sc = P.inv_B / s;
+    const float sc = __fdividef(P.inv_B, s);                   // s in [1, K]: 2 ulp
     float4* dst = reinterpret_cast<float4*>(P.grad_logits + row * P.ld);
+    const int tv = tgt >> 2, tq = tgt & 3;
 #pragma unroll
     for (int j = 0; j < KV; ++j) {
       const int i = lane + j * 32;
       if (i < nvec) {
-        const int base = i * 4;
-        float4 o = make_float4(v[j].x * sc, v[j].y * sc, v[j].z * sc, v[j].w * sc);
-        if (tgt >= base && tgt < base + 4) {
-          const int q = tgt - base;
-          if (q == 0) o.x -= P.inv_B; else if (q == 1) o.y -= P.inv_B;
-          else if (q == 2) o.z -= P.inv_B; else o.w -= P.inv_B;
-        }
+        const float sub = (i == tv) ? P.inv_B : 0.f;
+        float4 o;
+        o.x = fmaf(v[j].x, sc, tq == 0 ? -sub : 0.f);
+        o.y = fmaf(v[j].y, sc, tq == 1 ? -sub : 0.f);
+        o.z = fmaf(v[j].z, sc, tq == 2 ? -sub : 0.f);
+        o.w = fmaf(v[j].w, sc, tq == 3 ? -sub : 0.f);
         stg_stream(dst + i, o);
       }
     }
