@@ -268,8 +268,9 @@ class LloydLoop:
     x [N_local, d] fp64 (this rank's shard, already centred), centers [K, d] fp64, labels [N_local]
     int32 (previous labels in / new labels out)."""
 
-    def __init__(self, x, centers, labels, hb, grid, group, tol_abs):
+    def __init__(self, x, centers, labels, hb, grid, group, tol_abs, box=None):
         lib = L.lib()
+        self.box = box           # max |coordinate| over ALL ranks' rows if the caller knows it (FitSetup)
         self.x, self.labels, self.hb, self.grid, self.group = x, labels, hb, grid, group
         self.tol_abs = tol_abs
         self.dev = x.device
@@ -310,14 +311,18 @@ class LloydLoop:
         lib = L.lib()
         g, x, dev = self.grid, self.x, self.dev
         inf = float("inf")
-        if self.N > 0:
-            lo, hi = torch.aminmax(x, dim=0)
+        if self.box is not None:
+            # the cube [-max|x|, max|x|]^d (FitSetup has the global maximum already: no extra pass)
+            lo, hi = x.new_full((self.d,), -float(self.box)), x.new_full((self.d,), float(self.box))
         else:
-            lo, hi = x.new_full((self.d,), inf), x.new_full((self.d,), -inf)
-        if self.world > 1:
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
-            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
-        lo, hi = lo.contiguous(), hi.contiguous()
+            if self.N > 0:
+                lo, hi = torch.aminmax(x, dim=0)
+            else:
+                lo, hi = x.new_full((self.d,), inf), x.new_full((self.d,), -inf)
+            if self.world > 1:
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+            lo, hi = lo.contiguous(), hi.contiguous()
         occ = torch.zeros(lib.bdp_keygrid_coarse_cells(self.K, self.d), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             st = lib.bdp_keygrid_prepare(lo.data_ptr(), hi.data_ptr(), self.K, self.d, g.buf.data_ptr(),
@@ -546,6 +551,7 @@ class FitSetup:
             centers = init.double().to(dev).contiguous().clone()
             max_abs = amax
         self.hb = _fix_hi_bits(max_abs)
+        self.max_abs = max_abs
         self.x, self.centers = x, centers
         self.group, self.allreduce = group, allreduce
         self.distributed = distributed
@@ -584,7 +590,7 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     iters = fixed_iters if fixed_iters is not None else max_iter
     exchange = "host-loop"
     if _backend is None:
-        loop = LloydLoop(x, centers, state.labels, hb, grid, group, tol_abs)
+        loop = LloydLoop(x, centers, state.labels, hb, grid, group, tol_abs, box=fs.max_abs)
         loop.iterate(iters, check=fixed_iters is None)
         centers, n_iter, strict, exchange = loop.centers.clone(), loop.n_iter, loop.strict, loop.mode
         iters = 0

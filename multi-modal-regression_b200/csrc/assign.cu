@@ -607,10 +607,10 @@ constexpr int kCoarseListCap = 1024;
 template <int D>
 __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restrict__ cf32, int K,
                                                            GridHdr* __restrict__ hdr, const BuildOut out,
-                                                           int64_t coarse0, int active, const int* stop,
+                                                           int64_t coarse0, int64_t n_coarse, const int* stop,
                                                            const int* __restrict__ cells) {
   if (stop != nullptr && *reinterpret_cast<const volatile int*>(stop) != 0) return;
-  if (!active) {                                       // a rank with an empty slab only publishes its flag
+  if (n_coarse <= 0) {                                 // a rank with an empty slab only publishes its flag
     if (out.world > 1 && threadIdx.x < out.world) {
       __threadfence_system();
       st_release_sys(out.gflags[threadIdx.x] + out.rank, out.flag_value);
@@ -626,8 +626,13 @@ __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restr
   unsigned short* s_ids = s_list + ((cap + 1 + 7) & ~7);                            // [kChildren][32]
   const int G = hdr->G, Gc = G / 4;
   const int lane = threadIdx.x & 31;
+  // A block walks the slab with the grid's stride: one block per coarse cell on a single GPU; in a
+  // sharded build a few cells per block, so that the system-scope fence that orders a block's peer
+  // stores before its ticket (one NVLink round trip with the block's resources held) is paid once per
+  // block instead of once per cell.
+  for (int64_t ci = blockIdx.x; ci < n_coarse; ci += gridDim.x) {
   // cells != NULL: the build covers a LIST of coarse cells (those that hold rows of the fit)
-  const int64_t parent = cells != nullptr ? (int64_t)__ldg(cells + coarse0 + blockIdx.x) : coarse0 + blockIdx.x;
+  const int64_t parent = cells != nullptr ? (int64_t)__ldg(cells + coarse0 + ci) : coarse0 + ci;
   float org[D], cel[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) { org[k] = (float)hdr->origin[k]; cel[k] = (float)hdr->cell[k]; }
@@ -759,6 +764,8 @@ __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restr
         for (int v = 0; v < 4; ++v) dst[v] = q[v];
       }
     }
+  }
+  __syncthreads();                                     // the shared lists are reused by the next cell
   }
   if (out.world > 1) {
     // Every store of this block is ordered before its ticket: the block barrier makes them visible to
@@ -1209,18 +1216,21 @@ int bdpi_keygrid_build(const double* centers, int K, int d, void* grid, int64_t 
   }
   const int cap = K < kCoarseListCap ? K : kCoarseListCap;
   const size_t smem = (size_t)cap * 16 + (size_t)(((cap + 1 + 7) & ~7) + (d == 3 ? 64 : 256) * kSideWidth) * 2;
-  const unsigned blocks = (unsigned)(n_coarse > 0 ? n_coarse : 1);
-  const int active = n_coarse > 0 ? 1 : 0;
+  // sharded build: ~4 resident blocks per SM walk the slab (see the kernel); local build: one block per cell
+  int64_t nb = n_coarse > 0 ? n_coarse : 1;
+  if (world > 1 && nb > 4 * (int64_t)bdp_num_sms()) nb = 4 * (int64_t)bdp_num_sms();
+  const unsigned blocks = (unsigned)nb;
+  const bool active = n_coarse > 0;
   if (d == 3) {
     if (header_mode != 2)
       keygrid_header_kernel<3><<<1, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.cf32, stop, header_mode);
     if (active || world > 1)
-      keygrid_cell_kernel<3><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, active, stop, cells);
+      keygrid_cell_kernel<3><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, n_coarse, stop, cells);
   } else {
     if (header_mode != 2)
       keygrid_header_kernel<4><<<1, 256, 0, st>>>(centers, K, G, margin_frac, g.hdr, g.cf32, stop, header_mode);
     if (active || world > 1)
-      keygrid_cell_kernel<4><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, active, stop, cells);
+      keygrid_cell_kernel<4><<<blocks, 256, smem, st>>>(g.cf32, K, g.hdr, out, coarse0, n_coarse, stop, cells);
   }
   BDP_CUDA_CHECK_LAUNCH("keygrid kernels");
   return BDP_OK;

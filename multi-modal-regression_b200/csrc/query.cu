@@ -584,8 +584,6 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
   }
 }
 
-// Threads per CTA (one CTA per SM): the assign form fits 64 registers and runs 32 warps per SM; the
-// Lloyd form (fixed-point limbs + 13 shared atomics per rotation) needs ~120 and runs 16.
 template <typename T, int D, bool LLOYD, bool LAB64, int kQThreads>
 int launch_query_nt(const AssignParams& P, cudaStream_t st) {
   constexpr int kQWarps = kQThreads / 32;
@@ -627,12 +625,14 @@ int launch_query_nt(const AssignParams& P, cudaStream_t st) {
   return BDP_OK;
 }
 
-// One CTA of 1024 threads per SM (64 registers: 32 warps hide the scattered L2 record loads).  A
-// 512-thread / 128-register build of the same kernel was slower (170 vs 137 us for 10 M rotations) and
-// is not kept; dictionaries too large for this form's shared memory take the brute-force scan.
+// One CTA per SM.  Threads per CTA trade registers against warps: 1024 threads leave 64 registers (the
+// compiler then rematerialises tile indices and parameters all over the loop), 512 threads / 128
+// registers starve the schedulers (170 vs 137 us for 10 M rotations), 768 / 80 measured 133 us and
+// 896 / 72 129 us (E+M step of the k-means bench: 156 vs 161 us) — 28 warps it is.  Dictionaries too
+// large for this form's shared memory take the brute-force scan.
 template <typename T, int D, bool LLOYD, bool LAB64>
 int launch_query(const AssignParams& P, cudaStream_t st) {
-  return launch_query_nt<T, D, LLOYD, LAB64, 1024>(P, st);
+  return launch_query_nt<T, D, LLOYD, LAB64, 896>(P, st);
 }
 
 }  // namespace
