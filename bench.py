@@ -396,7 +396,8 @@ def main():
     fs = kmeans.FitSetup(xs, init)                     # centring, tolerance, fixed-point scale
     labels = torch.full((n_local,), -1, dtype=torch.int32, device=dev)
     grid = ops.KeyGrid(fs.centers)
-    loop = kmeans.LloydLoop(fs.x, fs.centers, labels, fs.hb, grid, None, fs.tol_abs)
+    loop = kmeans.LloydLoop(fs.x, fs.centers, labels, fs.hb, grid, None, fs.tol_abs, box=fs.max_abs)
+    n_cells, n_coarse = loop.n_cells, getattr(loop, "n_coarse", 0)
 
     def fit_region(n):
         loop.reset(fs.centers)
@@ -447,7 +448,7 @@ def main():
             fa = kmeans.FitSetup(xa, init, group=kmeans.LOCAL)
             la = torch.full((xa.shape[0],), -1, dtype=torch.int32, device=dev)
             single = kmeans.LloydLoop(fa.x, fa.centers, la, fa.hb, ops.KeyGrid(fa.centers), kmeans.LOCAL,
-                                      fa.tol_abs)
+                                      fa.tol_abs, box=fa.max_abs)
             single.launch(0, steps, False)
             torch.cuda.synchronize()
             single.n_iter = steps
@@ -561,9 +562,10 @@ def main():
                             "across iterations at 4-8 GPUs as in any real fit (no flush in the timed loop; "
                             "ms_per_step_l2_flushed re-times the iterations one by one with a 256 MB write "
                             "in between)" % (n_local * 24 // 1_000_000, n_local * 4 // 1_000_000),
-                      "algorithm": "key grid (candidate pruning) rebuilt every iteration, sharded over the "
-                                   "ranks; exact int64 fixed-point cluster sums, incremental M-step; "
-                                   "exchange " + parity["exchange"]},
+                      "algorithm": "key grid (candidate pruning) over the bounding box of the rotations, its "
+                                   "%d occupied coarse cells (of %d) rebuilt every iteration, sharded over "
+                                   "the ranks; exact int64 fixed-point cluster sums, incremental M-step; "
+                                   "exchange %s" % (n_cells, n_coarse, parity["exchange"])},
             "ms_per_step_l2_flushed": ms_step_flushed,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "rotation-iterations/s", "ms_per_fit": float(ms_e2e),
@@ -574,7 +576,9 @@ def main():
                     "note": "KMeans.fit on a pinned host shard: H2D, centring / variance, the iterations, "
                             "final E-step + inertia, labels and centres D2H; a step is one iteration, so "
                             "the per-step byte counts are the per-fit counts divided by the iterations"},
-            "gpu_launches": 5 * steps,
+            # per iteration: key-grid cell kernel, E+M kernel, exchange+finalise kernel; one header
+            # kernel per bdp_kmeans_run call
+            "gpu_launches": 3 * steps + 1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": profile_traffic("r2_ncu_lloyd.csv", "query_kernel"),
@@ -584,8 +588,9 @@ def main():
                          "algorithmic_bytes_per_launch": n_local * BYTES_PER_ROT_ITER,
                          "note": "28 B/rotation-iteration x rotations of one rank per launch, duration = mean over "
                                  "the E+M kernels of the timed fit's iterations (CUDA events inside the loop); "
-                                 "an iteration also runs the 3 key-grid build launches (sharded over the ranks) "
-                                 "and the exchange+finalise kernel"},
+                                 "an iteration also runs the key-grid cell kernel (occupied cells only, sharded "
+                                 "over the ranks) and the exchange+finalise kernel; grid_build_ms_unsharded is a "
+                                 "full dictionary-box build (bdp_keygrid_build) for reference"},
             "iteration_anatomy": anatomy,
             "parity": parity,
             "cpu_baseline": cpu,

@@ -297,6 +297,17 @@ int bdp_keygrid_prepare(const double* box_lo, const double* box_hi, int K, int d
                         int64_t grid_bytes, void* stream);
 int bdp_keygrid_occupancy(const double* x, int64_t N, int d, int K, const void* grid,
                           int64_t grid_bytes, int32_t* occ, void* stream);
+/* Rows of a fit in cell order of a PREPARED grid (bdp_keygrid_prepare): perm [N] int32 receives the
+ * permutation (row i of x_sorted [N, d] is row perm[i] of x), occ (NULL: skip) the occupied coarse
+ * cells as bdp_keygrid_occupancy marks them.  A warp of the E+M kernel then works on one or two
+ * cells (one cell-record line, the same candidate keys in every lane).  Labels and cluster sums do
+ * not depend on the order of the rows; bdp_scatter_i32 (dst[perm[i]] = src[i]) takes the labels back
+ * to the caller's order.  workspace: bdp_cellsort_workspace_bytes(N, K, d) device bytes. */
+int64_t bdp_cellsort_workspace_bytes(int64_t N, int K, int d);
+int bdp_cellsort(const double* x, int64_t N, int d, int K, void* grid, int64_t grid_bytes,
+                 int32_t* occ, void* workspace, int64_t workspace_bytes, int32_t* perm,
+                 double* x_sorted, void* stream);
+int bdp_scatter_i32(const int32_t* src, const int32_t* perm, int64_t N, int32_t* dst, void* stream);
 int bdp_assign_nearest_grid(const void* x, int x_dtype, int64_t N, int d, const double* centers,
                             int K, const void* grid, int64_t grid_bytes, int32_t* labels32,
                             int64_t* labels64, float* residual, double* min_sqdist, void* stream);

@@ -67,6 +67,9 @@ SIGNATURES = {
     "bdp_keygrid_coarse_cells": (_i64, [_int, _int]),
     "bdp_keygrid_prepare": (_int, [_p, _p, _int, _int, _p, _i64, _p]),
     "bdp_keygrid_occupancy": (_int, [_p, _i64, _int, _int, _p, _i64, _p, _p]),
+    "bdp_cellsort_workspace_bytes": (_i64, [_i64, _int, _int]),
+    "bdp_cellsort": (_int, [_p, _i64, _int, _int, _p, _i64, _p, _p, _i64, _p, _p, _p]),
+    "bdp_scatter_i32": (_int, [_p, _p, _i64, _p, _p]),
     "bdp_gemm_tf32": (_int, [_p, _int, _i64, _i64, _p, _int, _i64, _i64, _p, _int, _i64, _i64, _i64,
                              _i64, _i64, _int, _int, _i64, _int, _p]),
     "bdp_gemm_tf32_splits": (_int, [_i64, _int]),

@@ -144,6 +144,23 @@ def _no_stack():
     return None
 
 
+def _sentinel(stack):
+    """Version counters of the first and last head's fc1 weight.  The autograd Functions below read
+    the CURRENT stacked weights in backward; an optimizer step (or load_state_dict) between forward
+    and backward bumps every Parameter's counter, so two of the 336 are enough to refuse what stock
+    torch refuses — checking all of them would cost more than the step's whole host budget."""
+    hs = stack.heads
+    return (hs[0]._modules["fc1"]._parameters["weight"]._version,
+            hs[-1]._modules["fc1"]._parameters["weight"]._version)
+
+
+def _check_sentinel(ctx):
+    if _sentinel(ctx.stack) != ctx.sentinel:
+        raise RuntimeError("one of the variables needed for gradient computation has been modified by an "
+                           "inplace operation: the head weights changed between forward and backward "
+                           "(optimizer.step() / load_state_dict before backward())")
+
+
 class HeadStack:
     """Keeps the parameters of a list of identical 3-layer MLP modules (fc1, bn1, fc2, bn2, fc3) in
     STACKED device buffers that the grouped kernels consume, while every module keeps its own
@@ -410,6 +427,7 @@ class _HeadFn(torch.autograd.Function):
             buf["nb1"] += 1
             buf["nb2"] += 1
         ctx.stack = stack
+        ctx.sentinel = _sentinel(stack)
         ctx.saved = (x, mix, saved)
         ctx.training = training
         ctx.precise = PRECISION == "fp32"
@@ -417,6 +435,7 @@ class _HeadFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *dys):
+        _check_sentinel(ctx)
         stack = ctx.stack
         buf = stack.buf
         x, mix, saved = ctx.saved
@@ -508,11 +527,13 @@ class _HeadAllFn(torch.autograd.Function):
             ys.append(y.transpose(0, 1).contiguous())
             off += Hg
         ctx.stack, ctx.training = stack, training
+        ctx.sentinel = _sentinel(stack)
         ctx.saved = (x, h1, a1, m1, is1, h2, a2, m2, is2)
         return tuple(ys)
 
     @staticmethod
     def backward(ctx, *dys):
+        _check_sentinel(ctx)
         stack = ctx.stack
         buf = stack.buf
         x, h1, a1, m1, is1, h2, a2, m2, is2 = ctx.saved
@@ -763,11 +784,13 @@ class _Mlp2Fn(torch.autograd.Function):
         y = torch.baddbmm(buf["b2"].unsqueeze(1), a1.view(B, H, N1).transpose(0, 1),
                           buf["w2"].transpose(1, 2))
         ctx.stack, ctx.training = stack, training
+        ctx.sentinel = _sentinel(stack)
         ctx.saved = (x, h1, a1, m1, is1)
         return y.transpose(0, 1).contiguous()
 
     @staticmethod
     def backward(ctx, dy):
+        _check_sentinel(ctx)
         stack = ctx.stack
         buf = stack.buf
         x, h1, a1, m1, is1 = ctx.saved

@@ -293,11 +293,14 @@ class LloydLoop:
         # cells that hold rows (on any rank) are rebuilt each iteration — the rest of the box is never
         # queried (uniform rotations fill 52 % of their bounding cube).  The loop owns this grid.
         self.cells, self.n_cells = None, 0
+        # rows in cell order (bdp_cellsort): the loop then works on its own sorted copy of the rows and
+        # its own label array; finish() scatters the labels back into the caller's array
+        self.perm, self.user_labels = None, labels
         if self.grid is not None and self.mode != "nccl" and \
                 os.environ.get("BDPOSE_KMEANS_FIXED_GRID", "1") != "0":
             if self.grid_ptrs is None:
                 self.grid = ops.KeyGrid(centers, build=False)
-            self._fix_geometry()
+            self._fix_geometry(sort=os.environ.get("BDPOSE_KMEANS_SORT", "1") != "0")
         self._tmp_shift = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._tmp_empty = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.n_iter, self.strict, self.stopped = 0, False, False
@@ -306,7 +309,7 @@ class LloydLoop:
         self.incremental = self.grid is not None and self.mode != "nccl" and \
             os.environ.get("BDPOSE_KMEANS_INCREMENTAL", "1") != "0"
 
-    def _fix_geometry(self):
+    def _fix_geometry(self, sort=True):
         import torch.distributed as dist
         lib = L.lib()
         g, x, dev = self.grid, self.x, self.dev
@@ -328,15 +331,37 @@ class LloydLoop:
             st = lib.bdp_keygrid_prepare(lo.data_ptr(), hi.data_ptr(), self.K, self.d, g.buf.data_ptr(),
                                          g.nbytes, L.stream_ptr())
             L.check(st, "bdp_keygrid_prepare")
-            st = lib.bdp_keygrid_occupancy(L.ptr(x), self.N, self.d, self.K, g.buf.data_ptr(), g.nbytes,
-                                           occ.data_ptr(), L.stream_ptr())
-            L.check(st, "bdp_keygrid_occupancy")
+            if sort and self.N > 0:
+                nws = lib.bdp_cellsort_workspace_bytes(self.N, self.K, self.d)
+                ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+                perm = torch.empty(self.N, dtype=torch.int32, device=dev)
+                xs = torch.empty_like(x)
+                st = lib.bdp_cellsort(x.data_ptr(), self.N, self.d, self.K, g.buf.data_ptr(), g.nbytes,
+                                      occ.data_ptr(), ws.data_ptr(), nws, perm.data_ptr(), xs.data_ptr(),
+                                      L.stream_ptr())
+                L.check(st, "bdp_cellsort")
+                self.x, self.perm = xs, perm
+                self.labels = torch.full((self.N,), -1, dtype=torch.int32, device=dev)
+                del ws
+            else:
+                st = lib.bdp_keygrid_occupancy(L.ptr(x), self.N, self.d, self.K, g.buf.data_ptr(), g.nbytes,
+                                               occ.data_ptr(), L.stream_ptr())
+                L.check(st, "bdp_keygrid_occupancy")
         if self.world > 1:
             # (also orders every rank's prepare before any peer's first slab store into its grid)
             dist.all_reduce(occ, op=dist.ReduceOp.MAX, group=self.group)
         self.cells = torch.nonzero(occ).reshape(-1).to(torch.int32).contiguous()
         self.n_cells = int(self.cells.numel())
         self.n_coarse = int(occ.numel())
+
+    def finish(self):
+        """Labels of the loop's rows back into the caller's array, in the caller's row order."""
+        if self.perm is not None:
+            with torch.cuda.device(self.dev):
+                st = L.lib().bdp_scatter_i32(self.labels.data_ptr(), self.perm.data_ptr(), self.N,
+                                             self.user_labels.data_ptr(), L.stream_ptr())
+            L.check(st, "bdp_scatter_i32")
+        return self.user_labels
 
     def reset(self, centers):
         """Start over from `centers` (same data): accumulators, flags, labels and status cleared."""
@@ -589,11 +614,15 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     n_iter = 0
     iters = fixed_iters if fixed_iters is not None else max_iter
     exchange = "host-loop"
+    loop = None
     if _backend is None:
         loop = LloydLoop(x, centers, state.labels, hb, grid, group, tol_abs, box=fs.max_abs)
         loop.iterate(iters, check=fixed_iters is None)
         centers, n_iter, strict, exchange = loop.centers.clone(), loop.n_iter, loop.strict, loop.mode
         iters = 0
+        # (the loop may work on a cell-sorted copy of the rows with its own label array: the final
+        # E-step runs on those, the labels are scattered back at the end)
+        x, state.labels = loop.x, loop.labels
     for it in range(iters):
         # host-driven loop (stand-in backends only): one all-reduce + one status read per iteration
         state.acc_stats.zero_()
@@ -625,6 +654,8 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     else:
         lab = state.labels.long()
         inertia = allreduce(((x - centers[lab]) ** 2).sum().reshape(1))
+    if loop is not None:
+        state.labels = loop.finish()
     if center:
         centers = centers + mean
     return dict(centers=centers, labels=state.labels, inertia=float(inertia), n_iter=n_iter,

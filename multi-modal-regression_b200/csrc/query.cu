@@ -124,38 +124,93 @@ __device__ __forceinline__ void flush_acc(unsigned* s_acc32, int K, unsigned lon
 // too large for shared memory.  Leaving a cluster = adding the NEGATED two-limb number
 // (-(hi 2^32 + lo) = (-hi - [lo != 0]) 2^32 + (2^32 - lo) mod 2^32), so one code path serves both.
 template <int D>
-__device__ __forceinline__ void acc_one(long long hi, unsigned lo, unsigned member, int k,
-                                        unsigned* a) {
+__device__ __forceinline__ void acc_one(long long hi, unsigned lo, int k, unsigned* a) {
   const unsigned ub = (unsigned)(hi + 2147483648LL);      // |hi| < 2^30 by the choice of the scale
   atomicAdd(a + 4 * k, ub & 0xFFFFu);
   atomicAdd(a + 4 * k + 1, ub >> 16);
   atomicAdd(a + 4 * k + 2, lo & 0xFFFFu);
   atomicAdd(a + 4 * k + 3, lo >> 16);
-  (void)member;
 }
 
+// The same additions for a GROUP of lanes that target the same cluster (rows sorted by cell: most
+// lanes of a warp do): the 16-bit chunks are summed across the group with the REDUX unit (32 x 2^16
+// fits easily) and the group's leader issues ONE atomic per counter — without this, 32 lanes hammering
+// the same 14 shared counters serialise (first iteration of a sorted fit: 451 us instead of 212).
+// Smallest group worth aggregating: the groups of a warp take the REDUX path one after the other
+// (~150 cycles each), while direct atomics of all lanes run together and only serialise g-fold on a
+// counter shared by g lanes (14 g cycles): aggregation pays for the big groups of the first iterations
+// of a sorted fit, not for the two or three rows that cross a cell boundary later on.
+constexpr int kAggMin = 16;
 template <int D>
-__device__ __noinline__ void lloyd_move(const double* x, int to, int from, double scale_hi,
-                                        unsigned* s_acc32, unsigned long long* acc) {
+__device__ __forceinline__ void acc_group(unsigned grp, bool leader, const long long hi[D],
+                                          const unsigned lo[D], unsigned member_delta, unsigned* a) {
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const unsigned ub = (unsigned)(hi[k] + 2147483648LL);
+    const unsigned s0 = __reduce_add_sync(grp, ub & 0xFFFFu), s1 = __reduce_add_sync(grp, ub >> 16);
+    const unsigned s2 = __reduce_add_sync(grp, lo[k] & 0xFFFFu), s3 = __reduce_add_sync(grp, lo[k] >> 16);
+    if (leader) {
+      atomicAdd(a + 4 * k, s0);
+      atomicAdd(a + 4 * k + 1, s1);
+      atomicAdd(a + 4 * k + 2, s2);
+      atomicAdd(a + 4 * k + 3, s3);
+    }
+  }
+  if (leader) {
+    const unsigned n = (unsigned)__popc(grp);
+    atomicAdd(a + 4 * D, n);
+    atomicAdd(a + 4 * D + 1, member_delta * n);
+  }
+}
+
+// (arguments by value: a pointer to the caller's copy of the rotation forces it through local memory)
+template <int D>
+__device__ __noinline__ void lloyd_move(double x0, double x1, double x2, double x3, int to, int from,
+                                        double scale_hi, unsigned* s_acc32, unsigned long long* acc) {
   constexpr int W = AccLayout<D>::W;
+  const double x[4] = {x0, x1, x2, x3};
   long long hi[D], lw[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) to_limbs(x[k], scale_hi, hi[k], lw[k]);
   if (s_acc32 != nullptr) {
-    unsigned* a = s_acc32 + (size_t)to * W;
+    const unsigned act = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    {
+      unsigned lo[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) acc_one<D>(hi[k], (unsigned)lw[k], 1u, k, a);
-    atomicAdd(a + 4 * D, 1u);
-    atomicAdd(a + 4 * D + 1, 1u);
+      for (int k = 0; k < D; ++k) lo[k] = (unsigned)lw[k];
+      unsigned* a = s_acc32 + (size_t)to * W;
+      const unsigned grp = __match_any_sync(act, to);
+      if (__popc(grp) < kAggMin) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc_one<D>(hi[k], lo[k], k, a);
+        atomicAdd(a + 4 * D, 1u);
+        atomicAdd(a + 4 * D + 1, 1u);
+      } else {
+        acc_group<D>(grp, lane == (unsigned)(__ffs(grp) - 1), hi, lo, 1u, a);
+      }
+    }
+    const unsigned actf = __ballot_sync(act, from >= 0);
     if (from >= 0) {
-      unsigned* b = s_acc32 + (size_t)from * W;
+      // leaving a cluster = adding the NEGATED two-limb number
+      long long nh[D];
+      unsigned nl[D];
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         const unsigned lo = (unsigned)lw[k];
-        acc_one<D>(-hi[k] - (lo != 0u ? 1 : 0), 0u - lo, 0u, k, b);
+        nh[k] = -hi[k] - (lo != 0u ? 1 : 0);
+        nl[k] = 0u - lo;
       }
-      atomicAdd(b + 4 * D, 1u);
-      atomicAdd(b + 4 * D + 1, 0xFFFFFFFFu);             // member count - 1
+      unsigned* b = s_acc32 + (size_t)from * W;
+      const unsigned grp = __match_any_sync(actf, from);
+      if (__popc(grp) < kAggMin) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc_one<D>(nh[k], nl[k], k, b);
+        atomicAdd(b + 4 * D, 1u);
+        atomicAdd(b + 4 * D + 1, 0xFFFFFFFFu);             // member count - 1
+      } else {
+        acc_group<D>(grp, lane == (unsigned)(__ffs(grp) - 1), nh, nl, 0xFFFFFFFFu, b);
+      }
     }
   } else {
     if (from >= 0) {
@@ -482,10 +537,9 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
             // to the new one" for the rotations that moved equals a recomputation bit for bit —
             // and after the first iterations most rotations stay where they are
             if (P.update && (moved || !P.incremental)) {
-              double xm[D];
-#pragma unroll
-              for (int k = 0; k < D; ++k) xm[k] = (double)xst[p * D + k];
-              lloyd_move<D>(xm, label[p], (P.incremental && moved) ? olab[p] : -1, P.scale_hi,
+              lloyd_move<D>((double)xst[p * D], (double)xst[p * D + 1], (double)xst[p * D + 2],
+                            D == 4 ? (double)xst[p * D + D - 1] : 0.0, label[p],
+                            (P.incremental && moved) ? olab[p] : -1, P.scale_hi,
                             acc_in_smem ? s_acc32 : nullptr, P.acc);
             }
           }

@@ -227,3 +227,30 @@ def test_joint_cat_pose_model_golden(cuda, golden, multires):
         es = model(x.detach())
     for i, y in enumerate(es):
         scale_close(y, torch.from_numpy(g[tag + "eval_y%d" % i]), FP32_TOL, "joint %s eval y%d" % (tag, i))
+
+
+def test_weights_changed_between_forward_and_backward(cuda):
+    """Stock torch refuses a backward whose saved weights were modified in place; the fused heads read
+    the current stacked weights in backward, so an optimizer step in between must be refused too
+    (sentinel version counters) — and the normal two-forwards-one-backward pattern of
+    the scripts (learnGeodesicBDModel.py:116-120, 183) must keep working."""
+    import binDeltaModels as M
+    torch.manual_seed(3)
+    m = M.OneBinDeltaModel("none", 3, 16, 64, 40, 24, 3)
+    m.feature_model = torch.nn.Identity()
+    m.cuda().train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    x = torch.randn(8, 64, device=cuda)
+    lab = torch.randint(0, 3, (8, 1), device=cuda)
+    y1, y2 = m(x, lab)
+    z1, z2 = m(x * 0.5, lab)
+    (y1.sum() + y2.sum() + z1.sum() + z2.sum()).backward()      # two forwards, one backward: fine
+    opt.step()
+    opt.zero_grad()
+    y1, y2 = m(x, lab)
+    opt.zero_grad()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(1e-3)                                        # what an optimizer step does
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        (y1.sum() + y2.sum()).backward()

@@ -169,12 +169,14 @@ def test_fixed_geometry_fit_identical(cuda, data, monkeypatch):
     assert loop.cells is not None and 0 < loop.n_cells <= loop.n_coarse
     if data == "clustered":
         assert loop.n_cells < loop.n_coarse // 2, (loop.n_cells, loop.n_coarse)
+    assert loop.perm is not None and torch.equal(loop.x, fs.x[loop.perm.long()])     # rows in cell order
     outs = []
-    for fixed, use_grid in (("1", True), ("0", True), ("1", False)):
+    for fixed, use_grid, srt in (("1", True, "1"), ("0", True, "1"), ("1", False, "1"), ("1", True, "0")):
         monkeypatch.setenv("BDPOSE_KMEANS_FIXED_GRID", fixed)
+        monkeypatch.setenv("BDPOSE_KMEANS_SORT", srt)
         for kw in (dict(max_iter=25), dict(fixed_iters=9)):
             outs.append(kmeans.kmeans_lloyd(X, init, use_grid=use_grid, **kw))
-    for a, b in ((0, 2), (0, 4), (1, 3), (1, 5)):
+    for a, b in ((0, 2), (0, 4), (0, 6), (1, 3), (1, 5), (1, 7)):
         assert outs[a]["n_iter"] == outs[b]["n_iter"]
         assert torch.equal(outs[a]["labels"], outs[b]["labels"])
         assert torch.equal(outs[a]["centers"], outs[b]["centers"])
@@ -225,3 +227,44 @@ def test_prepared_grid_scans_until_built(cuda):
                 f = np.clip(np.floor(t + np.array([sx, sy, sz])).astype(np.int64), 0, G - 1)
                 allowed |= set(((f[:, 0] // 4) + Gc * ((f[:, 1] // 4) + Gc * (f[:, 2] // 4))).tolist())
     assert set(np.nonzero(occ_h)[0].tolist()) <= allowed
+
+
+def test_cellsort_is_a_permutation_in_cell_order(cuda):
+    """bdp_cellsort: perm is a permutation, x_sorted = x[perm], the cell ids are non-decreasing along
+    it, the occupied-cell marks equal bdp_keygrid_occupancy's, and bdp_scatter_i32 inverts the order."""
+    from bdpose import ops, _lib as L
+    rng = np.random.default_rng(9)
+    x = torch.from_numpy(rand_rot(rng, 123_457)[0]).to(cuda)
+    K, d, N = 300, 3, x.shape[0]
+    g = ops.KeyGrid(x[:K].clone().contiguous(), build=False)
+    lo, hi = torch.aminmax(x, dim=0)
+    lib = L.lib()
+    L.check(lib.bdp_keygrid_prepare(lo.contiguous().data_ptr(), hi.contiguous().data_ptr(), K, d,
+                                    g.buf.data_ptr(), g.nbytes, L.stream_ptr()), "prepare")
+    nc = lib.bdp_keygrid_coarse_cells(K, d)
+    occ_a = torch.zeros(nc, dtype=torch.int32, device=cuda)
+    occ_b = torch.zeros(nc, dtype=torch.int32, device=cuda)
+    nws = lib.bdp_cellsort_workspace_bytes(N, K, d)
+    ws = torch.empty(nws, dtype=torch.uint8, device=cuda)
+    perm = torch.empty(N, dtype=torch.int32, device=cuda)
+    xs = torch.empty_like(x)
+    L.check(lib.bdp_cellsort(x.data_ptr(), N, d, K, g.buf.data_ptr(), g.nbytes, occ_a.data_ptr(),
+                             ws.data_ptr(), nws, perm.data_ptr(), xs.data_ptr(), L.stream_ptr()), "cellsort")
+    L.check(lib.bdp_keygrid_occupancy(x.data_ptr(), N, d, K, g.buf.data_ptr(), g.nbytes, occ_b.data_ptr(),
+                                      L.stream_ptr()), "occupancy")
+    p = perm.long()
+    assert torch.equal(torch.sort(p).values, torch.arange(N, device=cuda))
+    assert torch.equal(xs, x[p])
+    assert torch.equal(occ_a, occ_b)
+    hdr = np.frombuffer(bytes(g.buf[:160].cpu().numpy()), dtype=np.float64, count=12)
+    G = int(np.frombuffer(bytes(g.buf[96:100].cpu().numpy()), dtype=np.int32)[0])
+    t = (xs.cpu().numpy() - hdr[0:3]) * hdr[8:11]
+    fine = np.floor(t).astype(np.int64)
+    frac = t - fine
+    safe = ((frac > 1e-3) & (frac < 1 - 1e-3)).all(1)          # rows whose cell no rounding can change
+    cid = fine[:, 0] + G * (fine[:, 1] + G * fine[:, 2])
+    assert (np.diff(cid[safe]) >= 0).all()
+    lab = torch.arange(N, dtype=torch.int32, device=cuda)
+    out = torch.full((N,), -7, dtype=torch.int32, device=cuda)
+    L.check(lib.bdp_scatter_i32(lab.data_ptr(), perm.data_ptr(), N, out.data_ptr(), L.stream_ptr()), "scatter")
+    assert torch.equal(out[p], lab)
