@@ -253,8 +253,13 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
   double* s_cd = reinterpret_cast<double*>(sp); sp += C.cd_smem ? a16((size_t)K * D * 8) : 0;
   unsigned* s_acc32 = reinterpret_cast<unsigned*>(sp);
   sp += (LLOYD && C.acc_smem) ? a16((size_t)K * (4 * D + 2) * 4) : 0;
-  constexpr int LB_IN = LLOYD ? WPTS * 4 : 0;                           // previous labels in
-  constexpr int LB_OUT = WPTS * ((!LLOYD && LAB64) ? 8 : 4);            // labels out
+  // Lloyd mode: the previous / new labels of a tile are one coalesced 8-byte load / store per lane
+  // (256 contiguous bytes per warp) — fewer instructions than a second bulk copy per tile plus the
+  // staging store, proxy fence and bulk store on the way out (with rows in cell order the kernel is
+  // bound by issue slots, not by the L1 any more); the next tile's labels are fetched while the
+  // current tile is processed.
+  constexpr int LB_IN = 0;
+  constexpr int LB_OUT = LLOYD ? 0 : WPTS * (LAB64 ? 8 : 4);            // labels out (assign mode)
   constexpr int RB_OUT = LLOYD ? 0 : RB;
   const int per_warp = nst * (XB + LB_IN) + 2 * (LB_OUT + RB_OUT);
   unsigned char* wbase = sp + (size_t)warp * per_warp;
@@ -328,10 +333,16 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
   auto issue = [&](int k, int s) {                          // lane 0: this warp's k-th TMA tile -> stage s
     const int64_t tile = gw + (int64_t)k * TW;
     const uint32_t bar = smem_u32(&s_full[warp][s]);
-    mbar_expect_tx(bar, (uint32_t)(XB + LB_IN));
+    mbar_expect_tx(bar, (uint32_t)XB);
     bulk_load(smem_u32(w_x + s * XB), xg + tile * (int64_t)(WPTS * D), XB, bar);
-    if (LLOYD) bulk_load(smem_u32(w_lin + s * LB_IN), P.labels32 + tile * WPTS, LB_IN, bar);
   };
+  // previous labels of tile t for this lane (Lloyd; the 16-byte aligned path only, else read per tile)
+  const bool lab_vec = LLOYD && C.use_tma;
+  auto fetch_labels = [&](int t) -> int2 {
+    if (lab_vec && t < n_full) return __ldcs(reinterpret_cast<const int2*>(P.labels32 + (int64_t)t * WPTS) + lane);
+    return make_int2(0, 0);
+  };
+  int2 lab_next = fetch_labels(gw);
   if (lane == 0) {
     for (int k = 0; k < m_tma && k < nst; ++k) issue(k, k);
   }
@@ -353,16 +364,17 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
       const bool tma = tile < n_full;
       const int s = tma ? stage : 0;
       unsigned char* xs = w_x + s * XB;
-      unsigned char* ls = w_lin + s * LB_IN;
+      int2 lab_cur = lab_next;
       if (tma) {
+        if (LLOYD) lab_next = fetch_labels(tile + TW);       // in flight while this tile is processed
         mbar_wait(smem_u32(&s_full[warp][s]), phase);
       } else {
         // generic fill (unaligned arrays, or the partial last tile): coalesced loads, zero padding
         T* xw = reinterpret_cast<T*>(xs);
         for (int i = lane; i < WPTS * D; i += 32) xw[i] = i < nval * D ? __ldcs(xg + base * D + i) : (T)0;
         if (LLOYD) {
-          int* lw = reinterpret_cast<int*>(ls);
-          for (int i = lane; i < WPTS; i += 32) lw[i] = i < nval ? __ldcs(P.labels32 + base + i) : 0;
+          lab_cur.x = lane * PTS < nval ? __ldcs(P.labels32 + base + lane * PTS) : 0;
+          lab_cur.y = lane * PTS + 1 < nval ? __ldcs(P.labels32 + base + lane * PTS + 1) : 0;
         }
         __syncwarp();
       }
@@ -371,10 +383,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
       // original values (exact re-check, residual, M-step of a moved rotation) read the stage again.
       const T* xst = reinterpret_cast<const T*>(xs) + lane * (PTS * D);
       int olab[PTS];
-      if (LLOYD) {                                          // Lloyd data is fp64: PTS == 2
-        const int2 o = *(reinterpret_cast<const int2*>(ls) + lane);
-        olab[0] = o.x; olab[PTS - 1] = o.y;
-      }
+      if (LLOYD) { olab[0] = lab_cur.x; olab[PTS - 1] = lab_cur.y; }   // Lloyd data is fp64: PTS == 2
 
       // phase 1: cells and the 16-byte record of every rotation (all loads in flight together).  The
       // point -> cell map runs in fp32 for fp64 rotations too (the fp32 copy is needed for the screen
@@ -510,8 +519,10 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
       const int ob = (int)(done_tiles & 1);
       unsigned char* lo = w_lout + ob * LB_OUT;
       unsigned char* ro = w_rout + ob * RB_OUT;
-      if (lane == 0) bulk_wait_read<1>();                  // the store that last used this buffer is out
-      __syncwarp();
+      if (!LLOYD) {
+        if (lane == 0) bulk_wait_read<1>();                // the store that last used this buffer is out
+        __syncwarp();
+      }
       float rout[LLOYD ? 1 : PTS * D];
 #pragma unroll
       for (int p = 0; p < PTS; ++p) {
@@ -551,7 +562,12 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
       }
       // labels (and residuals) of the lane -> staging buffer, vector stores
       if (LLOYD) {
-        *(reinterpret_cast<int2*>(lo) + lane) = make_int2(label[0], label[PTS - 1]);
+        if (tma && lab_vec) {
+          __stcs(reinterpret_cast<int2*>(P.labels32 + base) + lane, make_int2(label[0], label[PTS - 1]));
+        } else {
+          if (valid[0]) __stcs(P.labels32 + base + lane * PTS, label[0]);
+          if (valid[PTS - 1]) __stcs(P.labels32 + base + lane * PTS + (PTS - 1), label[PTS - 1]);
+        }
       } else if (LAB64) {
         if (PTS == 4) {
           uint4* d4 = reinterpret_cast<uint4*>(lo) + lane * 2;
@@ -580,22 +596,20 @@ __global__ void __launch_bounds__(kQThreads, 1) query_kernel(const AssignParams 
             dst[v] = make_uint2(__float_as_uint(rout[2 * v]), __float_as_uint(rout[2 * v + 1]));
         }
       }
-      if (tma) {
+      if (LLOYD) {
+        // (labels already stored from registers)
+      } else if (tma) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (LLOYD) {
-            bulk_store(P.labels32 + base, smem_u32(lo), LB_OUT);
-          } else {
-            if (LAB64) bulk_store(P.labels64 + base, smem_u32(lo), LB_OUT);
-            else bulk_store(P.labels32 + base, smem_u32(lo), LB_OUT);
-            if (P.residual) bulk_store(P.residual + base * D, smem_u32(ro), RB_OUT);
-          }
+          if (LAB64) bulk_store(P.labels64 + base, smem_u32(lo), LB_OUT);
+          else bulk_store(P.labels32 + base, smem_u32(lo), LB_OUT);
+          if (P.residual) bulk_store(P.residual + base * D, smem_u32(ro), RB_OUT);
           bulk_commit();
         }
       } else {
         __syncwarp();
-        if (LLOYD || !LAB64) {
+        if (!LAB64) {
           const int* l32 = reinterpret_cast<const int*>(lo);
           for (int i = lane; i < nval; i += 32) __stcs(P.labels32 + base + i, l32[i]);
         } else {
@@ -650,8 +664,8 @@ int launch_query_nt(const AssignParams& P, cudaStream_t st) {
   const size_t rec = (size_t)K * 16 + (D == 4 ? a16((size_t)K * 4) : 0);
   const size_t cd = a16((size_t)K * D * 8);
   const size_t acc = a16((size_t)K * (4 * D + 2) * 4);
-  const int lb_in = LLOYD ? G_::WPTS * 4 : 0;
-  const int lb_out = G_::WPTS * ((!LLOYD && LAB64) ? 8 : 4);
+  const int lb_in = 0;                                        // (Lloyd labels travel through registers)
+  const int lb_out = LLOYD ? 0 : G_::WPTS * (LAB64 ? 8 : 4);
   const int rb_out = LLOYD ? 0 : G_::RB;
   auto warp_bytes = [&](int nst) { return (size_t)nst * (G_::XB + lb_in) + 2 * (size_t)(lb_out + rb_out); };
   // what goes to shared memory, in order of value: ring stages, Lloyd accumulators, fp64 keys
@@ -679,14 +693,16 @@ int launch_query_nt(const AssignParams& P, cudaStream_t st) {
   return BDP_OK;
 }
 
-// One CTA per SM.  Threads per CTA trade registers against warps: 1024 threads leave 64 registers (the
-// compiler then rematerialises tile indices and parameters all over the loop), 512 threads / 128
-// registers starve the schedulers (170 vs 137 us for 10 M rotations), 768 / 80 measured 133 us and
-// 896 / 72 129 us (E+M step of the k-means bench: 156 vs 161 us) — 28 warps it is.  Dictionaries too
-// large for this form's shared memory take the brute-force scan.
+// One CTA per SM.  Threads per CTA trade registers against warps.  Label generation (rows in arbitrary
+// order: bound by L1 wavefronts and latency): 1024 threads leave 64 registers and the compiler
+// rematerialises tile indices and parameters all over the loop (137 us for 10 M rotations), 512 / 128
+// starve the schedulers (170 us), 768 / 80 measured 133 us and 896 / 72 129 us.  The Lloyd step runs on
+// rows in cell order (cellsort.cu) and is bound by issue slots: there the 32 warps of the 1024-thread
+// form win (E+M mean 123 us against 127 us at 896 and 138 us at 768).  Dictionaries too large for this
+// form's shared memory take the brute-force scan.
 template <typename T, int D, bool LLOYD, bool LAB64>
 int launch_query(const AssignParams& P, cudaStream_t st) {
-  return launch_query_nt<T, D, LLOYD, LAB64, 896>(P, st);
+  return launch_query_nt<T, D, LLOYD, LAB64, LLOYD ? 1024 : 896>(P, st);
 }
 
 }  // namespace
