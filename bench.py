@@ -134,6 +134,16 @@ def profile_traffic(fname, kernel_substr):
     (columns picked by profiles/pick_metrics.py), or None."""
     path = os.path.join(ROOT, "profiles", fname)
     try:
+        if fname.endswith(".txt"):
+            # "metric value unit" lines of ONE kernel launch (scratch/prof_loop.sh: a steady-state E+M
+            # kernel of the loop as the bench runs it)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = 0.0
+            for line in open(path):
+                f = line.split()
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(f[1]) * scale.get(f[2], 1.0)
+            return tot or None
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
@@ -261,7 +271,7 @@ def extras(dev, peaks, rank, world, args):
         "roofline": {"bound": "hbm", "kernel": "assign query kernel", "kernel_ms": ms_q,
                      "achieved": by / (ms_q * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                      "frac": by / (ms_q * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_launch": by,
-                     "traffic": profile_traffic("r2_ncu_assign.csv", "query_kernel")}}
+                     "traffic": profile_traffic("r2f_ncu_assign.csv", "query_kernel")}}
     if rank != 0:
         return out
     if world == 1:
@@ -303,7 +313,7 @@ def extras(dev, peaks, rank, world, args):
         "roofline": {"bound": "hbm", "kernel": "bd_loss_kernel", "achieved": by / (ms_r * 1e-3) / 1e9,
                      "peak": hbm, "unit": "GB/s", "frac": by / (ms_r * 1e-3) / 1e9 / hbm,
                      "frac_through_autograd": by / (ms_a * 1e-3) / 1e9 / hbm,
-                     "traffic": profile_traffic("r2_ncu_loss.csv", "bd_loss")}}
+                     "traffic": profile_traffic("r2f_ncu_loss.csv", "bd_loss")}}
     del score, delta
     # ---- config 5: evaluation over 1 M predictions -------------------------------------------------
     a = x[:1_000_000].contiguous(); b = x[1_000_000:2_000_000].contiguous()
@@ -581,7 +591,7 @@ def main():
             "gpu_launches": 3 * steps + 1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": profile_traffic("r2_ncu_lloyd.csv", "query_kernel"),
+                         "traffic": profile_traffic("r2f_em_steady_raw.txt", "query_kernel"),
                          "peak_source": peak_src, "kernel": "Lloyd E+M kernel (assign query, fp64, accumulate)",
                          "kernel_ms": kernel_ms, "kernel_ms_first_iteration": em_ms[0],
                          "kernel_ms_last_iteration": em_ms[-1], "grid_build_ms_unsharded": build_ms,

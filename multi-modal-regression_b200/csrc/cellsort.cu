@@ -24,20 +24,19 @@ void bdpi_keygrid_parts(void* grid, int K, int d, void** hdr, void** cf32);
 namespace {
 
 // cell id of every row (the query kernel's point -> cell map, expression for expression) and the row
-// indices; rows outside the grid get the id one past the last cell.  occ (optional): coarse cells
-// that hold a row.
+// indices; rows outside the grid get the id one past the last cell.
 template <int D>
 __global__ void __launch_bounds__(256) cell_keys_kernel(const double* __restrict__ x, int64_t N,
                                                         const GridHdr* __restrict__ hdr,
                                                         unsigned* __restrict__ keys,
-                                                        unsigned* __restrict__ idx, int* __restrict__ occ) {
+                                                        unsigned* __restrict__ idx) {
   float g_inv[D], g_off[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     g_inv[k] = (float)hdr->inv_cell[k];
     g_off[k] = (float)(-hdr->origin[k] * hdr->inv_cell[k]);
   }
-  const int G = hdr->G, Gc = G / 4;
+  const int G = hdr->G;
   const bool on = hdr->enabled != 0;
   unsigned n_fine = 1;
 #pragma unroll
@@ -45,7 +44,6 @@ __global__ void __launch_bounds__(256) cell_keys_kernel(const double* __restrict
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
     bool ok = on;
     unsigned cidx = 0, mul = 1;
-    int coarse = 0, cmul = 1;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       const float xf = (float)x[i * D + k];               // (L1 serves the row's other coordinates)
@@ -54,13 +52,38 @@ __global__ void __launch_bounds__(256) cell_keys_kernel(const double* __restrict
       ok = ok && ((unsigned)ck < (unsigned)G);
       cidx += (unsigned)ck * mul;
       mul *= (unsigned)G;
-      coarse += (ck >> 2) * cmul;
-      cmul *= Gc;
     }
     keys[i] = ok ? cidx : n_fine;
     idx[i] = (unsigned)i;
-    // (every writer stores the same value; test first: same-address stores serialise in the L2)
-    if (ok && occ != nullptr && __ldcg(occ + coarse) == 0) occ[coarse] = 1;
+  }
+}
+
+// Occupied coarse cells from the SORTED cell ids: a row marks its coarse cell only where the coarse id
+// differs from the previous row's — a few ten thousand stores instead of one per row (ten million
+// stores to a few thousand words serialise in the L2: 350 us for the pass).
+template <int D>
+__global__ void __launch_bounds__(256) occ_from_sorted_kernel(const unsigned* __restrict__ keys, int64_t N,
+                                                              const GridHdr* __restrict__ hdr,
+                                                              int* __restrict__ occ) {
+  const int G = hdr->G, Gc = G / 4;
+  unsigned n_fine = 1;
+#pragma unroll
+  for (int k = 0; k < D; ++k) n_fine *= (unsigned)G;
+  auto coarse_of = [&](unsigned key) -> int {
+    if (key >= n_fine) return -1;
+    int c = 0, cmul = 1;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      c += (int)((key % (unsigned)G) >> 2) * cmul;
+      key /= (unsigned)G;
+      cmul *= Gc;
+    }
+    return c;
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = coarse_of(keys[i]);
+    const int p = i > 0 ? coarse_of(keys[i - 1]) : -2;
+    if (c >= 0 && c != p) occ[c] = 1;
   }
 }
 
@@ -137,14 +160,19 @@ extern "C" int bdp_cellsort(const double* x, int64_t N, int d, int K, void* grid
   void* temp = w + 3 * nb;
   const int bits = key_bits(K, d);
   size_t temp_bytes = cub_temp_bytes(N, bits);
-  if (d == 3) cell_keys_kernel<3><<<grid_for(N), 256, 0, st>>>(x, N, hdr, keys_in, idx_in, occ);
-  else cell_keys_kernel<4><<<grid_for(N), 256, 0, st>>>(x, N, hdr, keys_in, idx_in, occ);
+  if (d == 3) cell_keys_kernel<3><<<grid_for(N), 256, 0, st>>>(x, N, hdr, keys_in, idx_in);
+  else cell_keys_kernel<4><<<grid_for(N), 256, 0, st>>>(x, N, hdr, keys_in, idx_in);
   BDP_CUDA_CHECK_LAUNCH("cell_keys_kernel");
   BDP_CUDA_CALL(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in,
                                                 reinterpret_cast<unsigned*>(perm), (int)N, 0, bits, st));
   if (d == 3) gather_rows_kernel<3><<<grid_for(N), 256, 0, st>>>(x, N, reinterpret_cast<unsigned*>(perm), x_sorted);
   else gather_rows_kernel<4><<<grid_for(N), 256, 0, st>>>(x, N, reinterpret_cast<unsigned*>(perm), x_sorted);
   BDP_CUDA_CHECK_LAUNCH("gather_rows_kernel");
+  if (occ != nullptr) {
+    if (d == 3) occ_from_sorted_kernel<3><<<grid_for(N), 256, 0, st>>>(keys_out, N, hdr, occ);
+    else occ_from_sorted_kernel<4><<<grid_for(N), 256, 0, st>>>(keys_out, N, hdr, occ);
+    BDP_CUDA_CHECK_LAUNCH("occ_from_sorted_kernel");
+  }
   return BDP_OK;
 }
 

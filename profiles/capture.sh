@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
 fi
 # 2) full-set captures, a few launches per kernel family
 python profiles/prof_targets.py assign loss lloyd head > $OUT/plain_prof_$TAG.log 2>&1 || exit 1
-for spec in "assign:query_kernel|keygrid:4" "loss:bd_loss_kernel:2" "lloyd:query_kernel|keygrid|kmeans_xfin:20" "head:gemm_tf32_kernel|bn_relu|fc3_:38"; do
+for spec in "assign:query_kernel|keygrid:4" "loss:bd_loss_kernel:2" "lloyd:query_kernel|keygrid|kmeans_xfin|cell_keys|gather_rows|RadixSort|scatter_i32|fit_stats:60" "head:gemm_tf32_kernel|bn_relu|fc3_:38"; do
   which=${spec%%:*}; rest=${spec#*:}; rx=${rest%%:*}; cnt=${rest##*:}
   [[ " $FAMILIES " == *" $which "* ]] || continue
   ncu --set full --clock-control none --import-source on -k regex:"$rx" -c $cnt -f -o /tmp/prof_${which} \

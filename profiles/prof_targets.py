@@ -28,7 +28,7 @@ if "loss" in which:
         ops.bd_loss_raw(score, bins, delta, x[:B].contiguous(), keys, L.POSE_GEODESIC_AA, True)
 if "lloyd" in which:
     xd = x.double().contiguous()
-    kmeans.kmeans_lloyd(xd, centers.clone(), fixed_iters=4, group=kmeans.LOCAL)
+    kmeans.kmeans_lloyd(xd, centers.clone(), fixed_iters=8, group=kmeans.LOCAL)
 if "eval" in which:
     a = x[:1_000_000].contiguous(); b = x[1_000_000:2_000_000].contiguous()
     labels = torch.randint(0, 12, (1_000_000,), device=dev)
