@@ -268,3 +268,18 @@ def test_cellsort_is_a_permutation_in_cell_order(cuda):
     out = torch.full((N,), -7, dtype=torch.int32, device=cuda)
     L.check(lib.bdp_scatter_i32(lab.data_ptr(), perm.data_ptr(), N, out.data_ptr(), L.stream_ptr()), "scatter")
     assert torch.equal(out[p], lab)
+
+
+def test_quaternion_fit_through_the_sorted_loop(cuda):
+    """d = 4 (quaternion dictionaries, learnKmeansDictionary with quaternion targets): the loop's d = 4
+    instantiations (fixed-geometry grid, occupied cells, cell sort, label scatter) against the
+    brute-force fit — same iterations, labels and centres bit for bit; N not a multiple of the tile."""
+    from bdpose import kmeans
+    rng = np.random.default_rng(41)
+    X = torch.from_numpy(rand_rot(rng, 90_007)[1]).to(cuda)
+    init = X[:150].clone()
+    a = kmeans.kmeans_lloyd(X, init, max_iter=12, use_grid=True)
+    b = kmeans.kmeans_lloyd(X, init, max_iter=12, use_grid=False)
+    assert a["n_iter"] == b["n_iter"]
+    assert torch.equal(a["labels"], b["labels"])
+    assert torch.equal(a["centers"], b["centers"])
