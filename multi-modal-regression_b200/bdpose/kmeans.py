@@ -609,7 +609,7 @@ def kmeans_lloyd(x, init, max_iter=300, tol=1e-4, group=None, fixed_iters=None, 
     centers_new = torch.empty_like(centers)
     grid = None
     if use_grid is True or (use_grid == "auto" and ops.KeyGrid.supported(K, d, N)):
-        grid = ops.KeyGrid(centers)
+        grid = ops.KeyGrid(centers, build=False)      # (every user rebuilds it for its own centres)
     strict = False
     n_iter = 0
     iters = fixed_iters if fixed_iters is not None else max_iter
