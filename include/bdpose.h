@@ -271,7 +271,7 @@ int bdp_kmeans_lloyd_step(const double* x, int64_t N, int d, const double* cente
  * outside the grid and cells with overflowing lists take the brute-force path inside the kernel.
  *   bdp_keygrid_bytes(K, d)       device bytes the caller allocates for the grid (-1: unsupported;
  *                                 supported: d = 3|4, 1 <= K <= 4096)
- *   bdp_keygrid_build(...)        (re)builds the grid for `centers` [K, d] fp64 — three small
+ *   bdp_keygrid_build(...)        (re)builds the grid for `centers` [K, d] fp64 — two small
  *                                 launches, no host synchronisation; rebuild whenever centers change
  *   bdp_assign_nearest_grid       bdp_assign_nearest with a prebuilt grid (16-byte aligned)
  *   bdp_kmeans_lloyd_step_grid    bdp_kmeans_lloyd_step with a prebuilt grid

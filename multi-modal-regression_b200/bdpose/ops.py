@@ -314,7 +314,7 @@ def error_stats(err_deg, labels=None, num_classes=1):
 # (c) assignment
 # ------------------------------------------------------------------------------------------------
 # Nearest-key queries go through the key grid (candidate pruning, include/bdpose.h) when the
-# dictionary and the batch are big enough for the three small build launches to pay off.
+# dictionary and the batch are big enough for the two small build launches to pay off.
 GRID_MIN_K = 8
 GRID_MIN_N = 1 << 15
 _grid_ws = {}     # (device index, stream, bytes) -> grid buffer, reused (rebuilt on every call)
