@@ -242,6 +242,30 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def kmeans_k200_leg(dev, K=200, steps=20):
+    """The headline loop at K = 200 (one GPU): ms per Lloyd iteration, CUDA events around the loop."""
+    from bdpose import ops, kmeans
+    xs = kmeans_chunks(range(N_CHUNKS), dev)
+    init = synth_rotations(N_ROT // N_CHUNKS, 100, dev, torch.float64)[:K].clone()
+    fs = kmeans.FitSetup(xs, init, group=kmeans.LOCAL)
+    labels = torch.full((xs.shape[0],), -1, dtype=torch.int32, device=dev)
+    loop = kmeans.LloydLoop(fs.x, fs.centers, labels, fs.hb, ops.KeyGrid(fs.centers, build=False), kmeans.LOCAL,
+                            fs.tol_abs, box=fs.max_abs)
+    ms = 0.0
+    for rep in range(2):
+        loop.reset(fs.centers)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop.launch(0, steps, False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_iteration": ms, "rotation_iterations_per_s": N_ROT / (ms * 1e-3), "K": K,
+            "iterations": steps, "hbm_frac_whole_iteration": N_ROT * BYTES_PER_ROT_ITER / (ms * 1e-3) / 1e9
+            / measured_peaks()[0]["hbm_gbs"], "occupied_coarse_cells": [loop.n_cells, getattr(loop, "n_coarse", 0)]}
+
+
 # ---------------------------------------------------------------------------------------------------
 # extras: the other BASELINE.json configs, short runs
 # ---------------------------------------------------------------------------------------------------
@@ -292,6 +316,9 @@ def extras(dev, peaks, rank, world, args):
             out["label_generation_10M_K1000"]["cpu_baseline"] = {"error": str(e)}
     # clustered dictionary (Pascal-like azimuth / elevation / tilt poses): list lengths + slow path
     out["label_generation_clustered"] = clustered_leg(dev, ops, hbm)
+    if world == 1:
+        # configs[2] also names K = 200: the same fixed-work fit at the smaller dictionary
+        out["kmeans_10M_K200"] = kmeans_k200_leg(dev)
     # ---- config 1b: fused loss fwd+bwd, 1 M rows, K=200, through autograd ---------------------------
     B, K = 1_000_000, 200
     score = torch.randn(B, K, device=dev, requires_grad=True)
