@@ -253,6 +253,82 @@ def test_one_bin_delta_model_golden(cuda, golden):
     scale_close(e2, torch.from_numpy(g["eval_y2"]), FP32_TOL, "eval y2")
 
 
+def _head_node(t):
+    """The autograd node of the fused head (bdpose.head._HeadFn) behind an output tensor: its ctx
+    keeps (x, mix, saved) — saved = h1 | a1 | h2 | a2 | BatchNorm statistics (csrc/head_seq.cu)."""
+    seen, todo = set(), [t.grad_fn]
+    while todo:
+        n = todo.pop()
+        if n is None or n in seen:
+            continue
+        seen.add(n)
+        if hasattr(n, "stack") and isinstance(getattr(n, "saved", None), tuple):
+            return n
+        todo.extend(f for f, _ in n.next_functions)
+    raise AssertionError("no fused-head node behind the output")
+
+
+def test_pascal_head_gradients_1e5_given_relu_masks(cuda):
+    """north_star's 1e-5 on the head GRADIENTS, element by element, at full size (C=12, K=200,
+    2048-1000-500, B=32).  The only thing that keeps a plain comparison from that bar is the ReLU
+    decision of the ~0.5 pre-activations per forward that sit within fp32 rounding of zero (flip_close
+    above; the reference's own fp32 run differs from the exact value there too).  Here the float64
+    oracle formula is evaluated with the ReLU masks the CUDA path actually took (read from its saved
+    activations): every other source of error — five 3xTF32 GEMMs, two BatchNorm forward / backward
+    reductions, the label-selected fc3 — then has to stay below 1e-5 of each tensor's scale."""
+    import copy
+    import torch.nn.functional as F
+    import binDeltaModels as M
+    torch.manual_seed(1)
+    C, K, N0, N1, N2, nd, B = 12, 200, 2048, 1000, 500, 3, 32
+    ref64 = O.OneBinDeltaHeads(C, K, N0, N1, N2, nd)
+    model = M.OneBinDeltaModel("none", C, K, N0, N1, N2, nd)
+    model.feature_model = torch.nn.Identity()
+    model.load_state_dict(ref64.state_dict())
+    ref64 = copy.deepcopy(ref64).double().train()
+    model.cuda().train()
+    x0 = torch.randn(B, N0)
+    label = torch.randint(0, C, (B, 1))
+    w1, w2 = torch.randn(B, K), torch.randn(B, nd)
+    xg = x0.clone().to(cuda).requires_grad_(True)
+    y1, y2 = model(xg, label.to(cuda))
+    node = _head_node(y1)
+    saved = node.saved[2]
+    H = 2 * C
+    F1, F2 = H * N1, H * N2
+    a1 = saved[B * F1:2 * B * F1].view(B, H, N1)
+    a2 = saved[2 * B * F1 + B * F2:2 * B * F1 + 2 * B * F2].view(B, H, N2)
+    m1, m2 = (a1 > 0).cpu(), (a2 > 0).cpu()
+    ((y1 * w1.to(cuda)).sum() + (y2 * w2.to(cuda)).sum()).backward()
+
+    # float64 evaluation of the reference formula (binDeltaModels.py:62-75, 112-121) with those masks
+    heads = list(ref64.bin_models) + list(ref64.res_models)      # the stack's head order
+    xr = x0.double().requires_grad_(True)
+    outs = []
+    n_flip = 0
+    for h, m in enumerate(heads):
+        z1 = F.batch_norm(m.fc1(xr), None, None, m.bn1.weight, m.bn1.bias, True, 0.1, 1e-5)
+        n_flip += int(((z1 > 0) != m1[:, h]).sum())
+        z2 = F.batch_norm(m.fc2(z1 * m1[:, h]), None, None, m.bn2.weight, m.bn2.bias, True, 0.1, 1e-5)
+        n_flip += int(((z2 > 0) != m2[:, h]).sum())
+        outs.append(m.fc3(z2 * m2[:, h]))
+    sel = label.view(-1)
+    r1 = torch.stack(outs[:C], 1)[torch.arange(B), sel]
+    r2 = torch.stack(outs[C:], 1)[torch.arange(B), sel]
+    ((r1 * w1.double()).sum() + (r2 * w2.double()).sum()).backward()
+    print("[masks] %d of %d ReLU decisions differ from the float64 evaluation" % (n_flip, B * (F1 + F2)))
+    assert n_flip <= 8, "ReLU masks differ in %d places: more than rounding at zero explains" % n_flip
+    scale_close(y1, r1, FP32_TOL, "y1"); scale_close(y2, r2, FP32_TOL, "y2")
+    scale_close(xg.grad, xr.grad, FP32_TOL, "dx")
+    p64 = dict(ref64.named_parameters())
+    for k, p in model.named_parameters():
+        ref = p64[k].grad
+        if ref is None or float(ref.abs().max()) == 0.0:
+            assert p.grad is not None and float(p.grad.abs().max()) == 0.0, k
+        else:
+            scale_close(p.grad, ref, FP32_TOL, k)
+
+
 def test_pascal_head_vs_oracle_full_size(cuda):
     """BASELINE config 1: C=12, K=200, 2048-1000-500, B=32 — fused model vs the oracle's module-by-
     module evaluation, with the two-forwards-one-backward pattern of the training scripts.
