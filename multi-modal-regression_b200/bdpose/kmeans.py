@@ -691,14 +691,16 @@ def kmeans_plusplus(x, K, seed=0, n_local_trials=None):
     return centers
 
 
-_pinned = {}
+_pinned = [None]
 
 
 def _pinned_labels(n):
-    t = _pinned.get(n)
-    if t is None:
-        t = _pinned[n] = torch.empty(n, dtype=torch.int32).pin_memory()
-    return t
+    """ONE pinned staging buffer, grown on demand (a buffer per distinct n would pin host memory for
+    good in a process that fits many different shards)."""
+    t = _pinned[0]
+    if t is None or t.numel() < n:
+        t = _pinned[0] = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
+    return t[:n]
 
 
 class KMeans:
