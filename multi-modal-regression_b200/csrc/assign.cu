@@ -604,6 +604,9 @@ __global__ void __launch_bounds__(256) keygrid_header_kernel(const double* __res
 // The box tests run in fp32 with relaxed thresholds (a candidate list has to CONTAIN every key that
 // can be nearest; a few extra keys only cost query time — the query itself is exact).
 constexpr int kCoarseListCap = 1024;
+// (62 registers: 4 blocks = 32 warps per SM, 74 % of the issue slots busy, profiles/r2g_cell_kernel_*.
+// Capping the registers at 48 / 40 for 5 / 6 resident blocks was measured: 43-44 us instead of 39 —
+// the extra warps do not make up for the rematerialised index and box arithmetic.)
 template <int D>
 __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restrict__ cf32, int K,
                                                            GridHdr* __restrict__ hdr, const BuildOut out,
@@ -630,22 +633,29 @@ __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restr
   // sharded build a few cells per block, so that the system-scope fence that orders a block's peer
   // stores before its ticket (one NVLink round trip with the block's resources held) is paid once per
   // block instead of once per cell.
-  for (int64_t ci = blockIdx.x; ci < n_coarse; ci += gridDim.x) {
-  // cells != NULL: the build covers a LIST of coarse cells (those that hold rows of the fit)
-  const int64_t parent = cells != nullptr ? (int64_t)__ldg(cells + coarse0 + ci) : coarse0 + ci;
+  // (32-bit cell arithmetic: a grid has at most 24^4 fine cells; the 64-bit form paid three emulated
+  // divisions per level and block)
   float org[D], cel[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) { org[k] = (float)hdr->origin[k]; cel[k] = (float)hdr->cell[k]; }
+  const int c0 = (int)coarse0, nc = (int)n_coarse;
+  for (int ci = blockIdx.x; ci < nc; ci += gridDim.x) {
+  // cells != NULL: the build covers a LIST of coarse cells (those that hold rows of the fit)
+  const unsigned parent = cells != nullptr ? (unsigned)__ldg(cells + c0 + ci) : (unsigned)(c0 + ci);
   // boxes in fp32, widened by kBoxEps of a cell (query rounding) + 1e-5 of a cell (their own rounding)
   constexpr float kEps = (float)kBoxEps + 1e-5f;
+  int pc[D];                                           // coarse coordinates of the parent
+  {
+    unsigned pr = parent;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { pc[k] = (int)(pr % (unsigned)Gc); pr /= (unsigned)Gc; }
+  }
   // (a) coarse box -> s_list, s_cf
   {
     float lo[D], hi[D];
-    int64_t pr = parent;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const int ck = (int)(pr % Gc);
-      pr /= Gc;
+      const int ck = pc[k];
       lo[k] = fmaf((float)(4 * ck) - kEps, cel[k], org[k]) - 1e-6f * fabsf(org[k]);
       hi[k] = fmaf((float)(4 * ck + 4) + kEps, cel[k], org[k]) + 1e-6f * fabsf(org[k]);
     }
@@ -657,17 +667,16 @@ __global__ void __launch_bounds__(256) keygrid_cell_kernel(const float4* __restr
   // (b) fine children
   const int child = threadIdx.x / kSubs, sub = threadIdx.x % kSubs;
   float lo[D], hi[D];
-  int64_t pr = parent, cell = 0, mul = 1;
+  unsigned cell = 0, mul = 1;
   int ch = child;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
-    const int ck = 4 * (int)(pr % Gc) + (ch & 3);
-    pr /= Gc;
+    const int ck = 4 * pc[k] + (ch & 3);
     ch >>= 2;
     lo[k] = fmaf((float)ck - kEps, cel[k], org[k]) - 1e-6f * fabsf(org[k]);
     hi[k] = fmaf((float)(ck + 1) + kEps, cel[k], org[k]) + 1e-6f * fabsf(org[k]);
-    cell += (int64_t)ck * mul;
-    mul *= G;
+    cell += (unsigned)ck * mul;
+    mul *= (unsigned)G;
   }
   float u = INFINITY;
   int pj = 0x7fffffff;                                  // pivot: position in the list
