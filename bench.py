@@ -9,7 +9,7 @@ timed from the init after `--warmup W` untimed ones.  With --gpus N the SAME 10 
 over the ranks (strong scaling); the per-iteration exchange of the cluster sums is fused into the
 finalise kernel over symmetric memory (no NCCL call in the loop).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extras]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extras] [--multi-extras]
 
 Prints ONE JSON line (rank 0).  `value` = rotation-iterations/s with the shard resident in HBM;
 `e2e` = the same metric through the public API (bdpose.kmeans.KMeans.fit on a pinned HOST array: H2D of
@@ -18,7 +18,7 @@ the shard, centring, the iterations, final E-step, D2H of labels and centres ins
 (the reference's own call, same explicit init) on the host cores, bounded sample; `parity` = the
 centres of the timed fit hashed on every rank (ranks agree; equal to a single-GPU fit of the same
 data).  `extras` carries the other BASELINE.json configs (label generation, fused loss, evaluation,
-head + loss) with their own roofline / CPU numbers.
+head + loss) with their own roofline / CPU numbers; they run at N = 1 (at N > 1 only with --multi-extras).
 """
 import argparse
 import csv
@@ -391,6 +391,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--multi-extras", action="store_true",
+                    help="with --gpus N > 1: also run the extras' multi-rank legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -569,8 +571,16 @@ def main():
 
     del loop, labels, xs, fs
     ex = {}
-    if not args.no_extras:
-        ex = extras(dev, peaks, rank, world, args)
+    # extras run on one GPU by default.  Under torchrun their multi-rank legs (data-parallel head step,
+    # label generation on every rank) are opt-in (--multi-extras): the strong-scaling line the driver
+    # records must not depend on them, and the driver truncates them out of its N>1 records anyway
+    if not args.no_extras and (world == 1 or args.multi_extras):
+        try:
+            ex = extras(dev, peaks, rank, world, args)
+        except Exception as e:
+            if world > 1:
+                raise           # the other ranks sit in a collective: fail loudly
+            ex = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         cpu = None
