@@ -51,7 +51,10 @@ WORKLOAD = ("configs[2]: k-means pose-dictionary learning, 10M random rotations 
 def bench_config(steps):
     """The workload both arms (this one and --impl reference) run: identical on both lines."""
     return {"workload": WORKLOAD, "n_rotations_total": N_ROT, "K": K_DICT, "x_dtype": "f64",
-            "init": "first K rotations (explicit)", "iterations_timed": steps}
+            "init": "first K rotations (explicit)", "iterations_timed": steps,
+            "l2": "inputs larger than L2: the 10M fp64 rotations + labels are 280 MB per pass (126 MB L2); "
+                  "sharded over 4-8 GPUs a shard fits the L2 and stays there across iterations as in any "
+                  "real fit - ms_per_step_l2_flushed re-times the iterations with a 256 MB write in between"}
 
 
 def synth_rotations(n, seed, device, dtype=torch.float32):
