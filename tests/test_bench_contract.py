@@ -29,3 +29,19 @@ def test_reference_arm_json_line():
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"]
     assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches the reference arm like its own arm (torchrun, N > 1): rank 0 alone runs and
+    prints the line, the other ranks exit 0 without work."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+           "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT,
+                         env=dict(os.environ, BDP_BENCH_REF_ROTATIONS="200000"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["config"] == json.loads(json.dumps(__import__("bench").bench_config(1)))
